@@ -1,0 +1,185 @@
+/*
+ * vmvo_b200.h -- C ABI of the B200-native VMVO window search (libvmvo_b200.so).
+ *
+ * The reference (AdityaNG/VehicleModelVisualOdometry) is pure Python and has no FFI; the
+ * boundary it offers is the set of Python signatures on the optimize_trajectory_v2 path.
+ * Each entry point below names the reference interface it stands in for (file:line,
+ * relative to the reference root).  INTEGRATION.md shows the ctypes binding a maintainer
+ * of the reference would add.
+ *
+ * Conventions
+ *   - plain C types; every `const T* d_xxx` / `T* d_xxx` is a DEVICE pointer owned by the
+ *     caller (e.g. torch.Tensor.data_ptr()); the library allocates nothing persistent
+ *     except the opaque vmvo_ctx (work counter, error text);
+ *   - calls are stream-ordered on the caller's `stream` (a cudaStream_t passed as void*)
+ *     and asynchronous; one host thread per ctx;
+ *   - return value: vmvo_status (0 = ok); vmvo_last_error(ctx) gives the text.
+ *   - pose streams are float4 (x [m], y [m], theta [rad], v [m/s]) per frame, all drives
+ *     concatenated; `d_drive_offsets[n_drives + 1]` delimits them; `d_time` is float64 [s].
+ */
+#ifndef VMVO_B200_H
+#define VMVO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VMVO_ABI_VERSION 1
+
+typedef struct vmvo_ctx vmvo_ctx;
+
+typedef enum vmvo_status {
+  VMVO_OK = 0,
+  VMVO_ERR_BAD_ARG = 1,
+  VMVO_ERR_CUDA = 2,
+  VMVO_ERR_UNSUPPORTED = 3
+} vmvo_status;
+
+/* enumerations used inside vmvo_search_cfg */
+enum { VMVO_WINDOW_FRAMES = 0, VMVO_WINDOW_TIME = 1 };
+enum { VMVO_TARGET_TIME = 0, VMVO_TARGET_TRAVERSE = 1 };
+enum { VMVO_SEED_DATA = 0, VMVO_SEED_GIVEN = 1, VMVO_SEED_CHAINED = 2 };
+enum { VMVO_PRIMARY_VO = 0, VMVO_PRIMARY_GPS = 1 };
+
+/* per-window status bits */
+enum {
+  VMVO_WIN_EMPTY = 1,     /* fewer than two targets, N == 0  (vmvo/utils/mpc.py:42-43)      */
+  VMVO_WIN_NONFINITE = 2, /* NaN/Inf among the window's inputs: argmin degenerates to 0     */
+  VMVO_WIN_TOO_LONG = 4   /* more poses than cfg.max_window_poses: window not searched      */
+};
+
+/* per-sequence failure kinds of vmvo_rollout_* (the two asserts of bicycle_model.py:48-62) */
+enum { VMVO_FAIL_NONE = 0, VMVO_FAIL_STEER = 1, VMVO_FAIL_ACCEL = 2 };
+
+/*
+ * Search configuration: the derived spec of DESIGN.md section 2.
+ * Constants default to vmvo/constants.py:3-7; horizon_time to optimize_trajectory_v2.py:35.
+ */
+typedef struct vmvo_search_cfg {
+  int32_t grid_v;           /* G_v accelerations in [-max_accel, +max_accel]               */
+  int32_t grid_s;           /* G_s steering rates in [-max_steer_rate, +max_steer_rate]    */
+  int32_t window_mode;      /* VMVO_WINDOW_*                                               */
+  int32_t window_frames;    /* W steps => W+1 poses per window (frames mode)               */
+  int32_t horizon_frames;   /* int(horizon_time * FPS) (time mode): n_windows = n - 2*this */
+  int32_t target_mode;      /* VMVO_TARGET_*                                               */
+  int32_t target_offset;    /* 1: state k vs target k-1 (mpc.py:70-78); 0: state k vs k    */
+  int32_t seed_mode;        /* VMVO_SEED_*                                                 */
+  int32_t primary;          /* stream that defines the window frame and the seeds          */
+  int32_t max_window_poses; /* capacity per window (<= 256)                                */
+  double horizon_time;      /* seconds (time mode)                                         */
+  double w_vo, w_gps, w_imu;/* cost weights; a zero weight drops the term                  */
+  double k_steer;           /* K of mpc.py:31                                              */
+  double wheel_base, steering_ratio, max_steer, max_accel, max_steer_rate;
+} vmvo_search_cfg;
+
+/* One record per window; also the unit of the multi-GPU gather (64 bytes). */
+typedef struct vmvo_window_result {
+  int32_t best_idx;      /* flat index i*G_s + j of the argmin hypothesis, -1 if none      */
+  int32_t n_steps;       /* N = number of targets - 1                                      */
+  int32_t status;        /* VMVO_WIN_* bits                                                */
+  int32_t n_rescored;    /* hypotheses re-scored in float64 (diagnostic)                   */
+  double best_cost;      /* float64 cost of the argmin hypothesis                          */
+  double v_seed, s_seed; /* window seeds V_w [m/s], S_w [deg]                              */
+  double x1, y1, theta1; /* pose after the first step of the best rollout (local frame)    */
+} vmvo_window_result;
+
+/* ---- context ---------------------------------------------------------------------- */
+int vmvo_abi_version(void);
+int vmvo_ctx_create(int device, vmvo_ctx** out);
+int vmvo_ctx_destroy(vmvo_ctx* ctx);
+const char* vmvo_last_error(const vmvo_ctx* ctx);
+/* fills *cfg with the defaults described above (32x32 grid, frames mode, W = 30) */
+void vmvo_search_cfg_default(vmvo_search_cfg* cfg);
+/* number of windows of a drive of n_frames frames: max(0, n - 2*horizon)
+ * (vmvo/scripts/optimize_trajectory_v2.py:48) */
+int64_t vmvo_window_count(const vmvo_search_cfg* cfg, int64_t n_frames);
+
+/* ---- a8: window extents ------------------------------------------------------------
+ * Replaces the per-window np.searchsorted pair of Trajectory.sub_trajectory_from_time
+ * (vmvo/schema.py:117-127) for every window of every drive at once.
+ * d_window_offsets[n_drives + 1] is the prefix sum of vmvo_window_count per drive.
+ * Outputs (length d_window_offsets[n_drives]): absolute start frame, pose count, drive. */
+int vmvo_plan_windows(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int32_t n_drives,
+                      const int64_t* d_drive_offsets, const int64_t* d_window_offsets,
+                      int64_t n_windows, const double* d_time, int64_t* d_win_start,
+                      int32_t* d_win_len, int32_t* d_win_drive, void* stream);
+
+/* ---- a7, a9, a10, a11: the fused window search --------------------------------------
+ * Replaces mpc_run (vmvo/utils/mpc.py:14-122) and the window preparation around it
+ * (schema.py:59-115 local frame, mpc.py:125-141 decimation, optimize_trajectory_v2.py:57-91
+ * seed + re-rollout) for n_windows windows.  d_gps / d_imu / d_seeds may be NULL when the
+ * cfg does not use them.  d_seeds is [n_windows][2] = (V_w, S_w) for VMVO_SEED_GIVEN.
+ * Optional outputs (NULL to skip), row stride out_stride (>= max steps):
+ *   d_out_poses [n_windows][out_stride][3]  rollout (x, y, theta) of the argmin hypothesis
+ *   d_out_steer [n_windows][out_stride]     its steering sequence [deg] (mpc_run's return)
+ *   d_out_vel   [n_windows][out_stride]     its velocity sequence [m/s]                  */
+int vmvo_grid_search_f32(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n_windows,
+                         const int64_t* d_win_start, const int32_t* d_win_len,
+                         const int32_t* d_win_drive, const double* d_dt_per_drive,
+                         const float* d_vo, const float* d_gps, const float* d_imu,
+                         const double* d_seeds, vmvo_window_result* d_results,
+                         double* d_out_poses, double* d_out_steer, double* d_out_vel,
+                         int32_t out_stride, void* stream);
+
+/* ---- a12: write-back and blends -----------------------------------------------------
+ * Replaces optimize_trajectory_v2.py:32-33,122-137: output columns start as the VO stream,
+ * window i overwrites x,y[i : i+N_i] with its local-frame rollout (later windows win),
+ * theta[i] / velocity[i] become the VO/GPS blends when d_gps != NULL.
+ * total_frames = d_drive_offsets[n_drives] (passed by value so the call stays
+ * asynchronous).  Outputs are float64 [total_frames] each.                              */
+int vmvo_write_back_f32(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int32_t n_drives,
+                        int64_t total_frames, const int64_t* d_drive_offsets, const int64_t* d_window_offsets,
+                        const double* d_dt_per_drive, const float* d_vo, const float* d_gps,
+                        const vmvo_window_result* d_results, double* d_out_x, double* d_out_y,
+                        double* d_out_theta, double* d_out_vel, void* stream);
+
+/* ---- a1, a2: batched model rollout --------------------------------------------------
+ * Replaces BicycleModel.run / run_sequence (vmvo/bicycle_model.py:40-92) for n_seq
+ * independent sequences of n_steps steps.  d_steer / d_vel are [n_seq][n_steps]
+ * (steering-wheel degrees, m/s), d_state0 [n_seq][4] = (x, y, theta, velocity).
+ * d_out [n_seq][n_steps][3] = (x, y, theta) after each step.  d_fail [n_seq][2] =
+ * (VMVO_FAIL_* kind, step index) of the first violated bound, kind 0 when feasible.   */
+int vmvo_rollout_f64(vmvo_ctx* ctx, int64_t n_seq, int32_t n_steps, const double* d_steer,
+                     const double* d_vel, double dt, const double* d_state0,
+                     double max_steer, double max_accel, double* d_out, int32_t* d_fail,
+                     void* stream);
+int vmvo_rollout_f32(vmvo_ctx* ctx, int64_t n_seq, int32_t n_steps, const float* d_steer,
+                     const float* d_vel, float dt, const float* d_state0, float max_steer,
+                     float max_accel, float* d_out, int32_t* d_fail, void* stream);
+
+/* ---- a10: cost of given control sequences -------------------------------------------
+ * The closure `cost` inside mpc_run (vmvo/utils/mpc.py:56-85): n_seq steering sequences
+ * [n_seq][n_steps] at constant speed `velocity`, against one target polyline
+ * d_target_xy [n_steps + 1][2]; d_cost [n_seq].                                        */
+int vmvo_sequence_cost_f64(vmvo_ctx* ctx, int64_t n_seq, int32_t n_steps, const double* d_steer,
+                           double velocity, double dt, const double* d_target_xy, double k_steer,
+                           double* d_cost, void* stream);
+
+/* ---- a7, a8, a9 as stand-alone operators (used by the Trajectory facade) ------------ */
+/* Trajectory.sub_trajectory (vmvo/schema.py:59-115): local frame of n poses.           */
+int vmvo_extract_window_f64(vmvo_ctx* ctx, int32_t n, const double* d_x, const double* d_y,
+                            const double* d_theta, double* d_lx, double* d_ly, double* d_lth,
+                            void* stream);
+/* np.searchsorted(time, t0, 'left'), np.searchsorted(time, t1, 'right')
+ * (vmvo/schema.py:119-120); d_extent[2].                                               */
+int vmvo_time_extent_f64(vmvo_ctx* ctx, int64_t n, const double* d_time, double t0, double t1,
+                         int64_t* d_extent, void* stream);
+/* traverse_trajectory (vmvo/utils/mpc.py:125-141): kept indices and their count.       */
+int vmvo_traverse_f64(vmvo_ctx* ctx, int32_t n, const double* d_xy, double D, int32_t* d_keep,
+                      int32_t* d_count, void* stream);
+
+/* ---- measurement helpers ------------------------------------------------------------ */
+/* Issue-rate microbenchmarks used for the roofline denominators (bench.py): each thread
+ * runs `iters` dependent-free MUFU (kind 0: sin+cos pairs), FFMA (kind 1) or DFMA (kind 2)
+ * operations; d_sink receives one float per thread.                                     */
+int vmvo_peak_probe(vmvo_ctx* ctx, int32_t kind, int32_t blocks, int32_t threads,
+                    int32_t iters, float* d_sink, void* stream);
+/* kernels launched by this ctx since creation (for bench.py's gpu_launches)             */
+int64_t vmvo_launch_count(const vmvo_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VMVO_B200_H */

@@ -1,0 +1,89 @@
+"""GPU parity of the fused window search against the oracle (through the C ABI).
+
+Bar (BASELINE.json north_star): selected hypothesis indices bit-exact; rollout poses within
+1e-4 m / 1e-5 rad -- the float64 re-score puts the measured deviation near 1e-13, asserted
+here at 1e-9.
+"""
+import dataclasses
+import zlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vmvo_oracle as O
+from tests.helpers import assert_records_match, oracle_windows, spec_of
+from vehiclemodelvisualodometry_b200 import (DriveSet, SearchConfig, grid_search, optimize_drives,
+                                             plan_windows)
+from vehiclemodelvisualodometry_b200.synthetic import synthetic_drives
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    "vo_4x4": SearchConfig(grid_v=4, grid_s=4, window_frames=10),
+    "vo_5x7": SearchConfig(grid_v=5, grid_s=7, window_frames=12),
+    "vo_1x9": SearchConfig(grid_v=1, grid_s=9, window_frames=16),
+    "vo_9x1": SearchConfig(grid_v=9, grid_s=1, window_frames=16),
+    "vo_16x16": SearchConfig(grid_v=16, grid_s=16, window_frames=20),
+    "vo_32x32_w30": SearchConfig(grid_v=32, grid_s=32, window_frames=30),
+    "vo_offset0": SearchConfig(grid_v=12, grid_s=12, window_frames=20, target_offset=0),
+    "gps_traverse": SearchConfig(grid_v=8, grid_s=24, window_frames=40, target_mode="traverse",
+                                 primary="gps", w_vo=0.0, w_gps=1.0),
+    "vo_gps": SearchConfig(grid_v=16, grid_s=12, window_frames=24, w_vo=1.0, w_gps=0.25),
+    "vo_gps_imu": SearchConfig(grid_v=16, grid_s=16, window_frames=24, w_vo=1.0, w_gps=0.5, w_imu=40.0),
+    "vo_imu": SearchConfig(grid_v=8, grid_s=32, window_frames=30, w_imu=10.0),
+    "vo_ksteer": SearchConfig(grid_v=8, grid_s=16, window_frames=20, k_steer=5e-6),
+    "time_windows": SearchConfig(grid_v=8, grid_s=8, window_mode="time", horizon_time=1.5,
+                                 horizon_frames=29),
+    "w70_three_rounds": SearchConfig(grid_v=8, grid_s=8, window_frames=70),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_search_matches_oracle(cuda_device, name):
+    cfg = CASES[name]
+    n = 2 * cfg.horizon() + 25
+    batch = synthetic_drives(2, n, seed=zlib.crc32(name.encode()) % 1000)
+    drives = DriveSet.from_arrays(list(batch.time), [batch.dt] * 2, vo=list(batch.vo), gps=list(batch.gps),
+                                  imu=list(batch.imu))
+    plan = plan_windows(cfg, drives)
+    assert plan.n_windows == 2 * 25
+    out = grid_search(cfg, drives, plan, want_rollouts=True)
+    rec = out.records()
+    ref = []
+    for d in range(2):
+        ref += oracle_windows(cfg, batch.time[d], batch.dt, batch.vo[d], batch.gps[d], batch.imu[d])
+    assert_records_match(rec, ref)
+    poses, steer, vel = out.poses.cpu().numpy(), out.steer.cpu().numpy(), out.vel.cpu().numpy()
+    for w, r in enumerate(ref):
+        N = r.n_steps
+        np.testing.assert_allclose(poses[w, :N], r.poses, rtol=0, atol=1e-9)
+        np.testing.assert_array_equal(steer[w, :N], r.steer)     # IEEE ops only: bit-exact
+        np.testing.assert_array_equal(vel[w, :N], r.vel)
+
+
+def test_given_seeds(cuda_device):
+    cfg = SearchConfig(grid_v=8, grid_s=8, window_frames=15, seed_mode="given")
+    batch = synthetic_drives(1, 60, seed=4)
+    rng = np.random.default_rng(0)
+    seeds = np.stack([rng.uniform(0, 15, 30), rng.uniform(-460, 460, 30)], axis=1)
+    drives = DriveSet.from_arrays([batch.time[0]], [batch.dt], vo=[batch.vo[0]])
+    plan = plan_windows(cfg, drives)
+    rec = grid_search(cfg, drives, plan, seeds=torch.as_tensor(seeds)).records()
+    ref = oracle_windows(cfg, batch.time[0], batch.dt, batch.vo[0], seeds=seeds)
+    assert_records_match(rec, ref)
+
+
+def test_window_range_and_out_buffer(cuda_device):
+    cfg = SearchConfig(grid_v=8, grid_s=8, window_frames=10)
+    batch = synthetic_drives(1, 80, seed=2)
+    drives = DriveSet.from_arrays([batch.time[0]], [batch.dt], vo=[batch.vo[0]])
+    plan = plan_windows(cfg, drives)
+    full = grid_search(cfg, drives, plan).records()
+    buf = torch.zeros((plan.n_windows, 64), dtype=torch.uint8, device=cuda_device)
+    grid_search(cfg, drives, plan, window_range=(0, 23), out=buf[:23])
+    grid_search(cfg, drives, plan, window_range=(23, plan.n_windows), out=buf[23:])
+    from vehiclemodelvisualodometry_b200 import _lib
+    got = buf.cpu().numpy().view(_lib.RESULT_DTYPE).reshape(-1)
+    for f in ("best_idx", "n_steps", "status", "best_cost", "x1", "y1", "theta1"):
+        np.testing.assert_array_equal(got[f], full[f])

@@ -1,0 +1,266 @@
+"""Batched tensor API of the window search: drives in HBM -> per-window results.
+
+This is the additive API beneath the reference-shaped facades (``mpc.grid_run``,
+``optimize.optimize_trajectory``): every drive of a batch is concatenated into one float4
+pose stream per sensor, the windows of all drives are planned once
+(``vmvo_plan_windows``), searched by the fused kernel (``vmvo_grid_search_f32``) and written
+back (``vmvo_write_back_f32``).  All device work goes through the C ABI of
+include/vmvo_b200.h on the current torch stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .constants import MAX_ACCEL, MAX_STEER, MAX_STEER_RATE, STEERING_RATIO, WHEEL_BASE
+
+_ENUMS = {
+    "window_mode": {"frames": _lib.WINDOW_FRAMES, "time": _lib.WINDOW_TIME},
+    "target_mode": {"time": _lib.TARGET_TIME, "traverse": _lib.TARGET_TRAVERSE},
+    "seed_mode": {"data": _lib.SEED_DATA, "given": _lib.SEED_GIVEN, "chained": _lib.SEED_CHAINED},
+    "primary": {"vo": _lib.PRIMARY_VO, "gps": _lib.PRIMARY_GPS},
+}
+
+
+@dataclass(frozen=True)
+class SearchConfig:
+    """The search spec; field meanings as in vmvo_search_cfg."""
+
+    grid_v: int = 32
+    grid_s: int = 32
+    window_mode: str = "frames"
+    window_frames: int = 30
+    horizon_time: float = 3.0
+    horizon_frames: int = 60
+    target_mode: str = "time"
+    target_offset: int = 1
+    seed_mode: str = "data"
+    primary: str = "vo"
+    w_vo: float = 1.0
+    w_gps: float = 0.0
+    w_imu: float = 0.0
+    k_steer: float = 0.0
+    wheel_base: float = WHEEL_BASE
+    steering_ratio: float = STEERING_RATIO
+    max_steer: float = MAX_STEER
+    max_accel: float = float(MAX_ACCEL)
+    max_steer_rate: float = MAX_STEER_RATE
+    max_window_poses: int = 0          # 0: derive (frames mode: W+1; time mode: 128)
+
+    def horizon(self) -> int:
+        return self.window_frames if self.window_mode == "frames" else self.horizon_frames
+
+    def window_count(self, n_frames: int) -> int:
+        return max(0, int(n_frames) - 2 * self.horizon())
+
+    def pose_capacity(self) -> int:
+        if self.max_window_poses:
+            return int(self.max_window_poses)
+        return self.window_frames + 1 if self.window_mode == "frames" else 128
+
+    def to_c(self) -> _lib.SearchCfg:
+        c = _lib.SearchCfg()
+        for name in ("grid_v", "grid_s", "window_frames", "horizon_frames", "target_offset"):
+            setattr(c, name, int(getattr(self, name)))
+        for name, table in _ENUMS.items():
+            try:
+                setattr(c, name, table[getattr(self, name)])
+            except KeyError:
+                raise ValueError(f"{name}={getattr(self, name)!r}; expected one of {sorted(table)}")
+        c.max_window_poses = self.pose_capacity()
+        for name in ("horizon_time", "w_vo", "w_gps", "w_imu", "k_steer", "wheel_base",
+                     "steering_ratio", "max_steer", "max_accel", "max_steer_rate"):
+            setattr(c, name, float(getattr(self, name)))
+        return c
+
+
+def _as_dev(a, dtype, device) -> Optional[torch.Tensor]:
+    if a is None:
+        return None
+    if isinstance(a, torch.Tensor):
+        return a.to(device=device, dtype=dtype, non_blocking=True).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(device, non_blocking=True)
+
+
+@dataclass
+class DriveSet:
+    """Drives resident in HBM: concatenated float4 pose streams + float64 stamps."""
+
+    time: torch.Tensor                     # float64 [F]
+    vo: Optional[torch.Tensor]             # float32 [F, 4]
+    gps: Optional[torch.Tensor]            # float32 [F, 4]
+    imu: Optional[torch.Tensor]            # float32 [F]
+    drive_offsets: List[int]               # host copy, len D+1
+    d_drive_offsets: torch.Tensor          # int64 [D+1]
+    dt: torch.Tensor                       # float64 [D]   step length per drive
+
+    @property
+    def n_drives(self) -> int:
+        return len(self.drive_offsets) - 1
+
+    @property
+    def n_frames(self) -> int:
+        return self.drive_offsets[-1]
+
+    @property
+    def device(self):
+        return self.time.device
+
+    @staticmethod
+    def from_arrays(time: Sequence, dt: Sequence[float], vo: Optional[Sequence] = None,
+                    gps: Optional[Sequence] = None, imu: Optional[Sequence] = None,
+                    device=None) -> "DriveSet":
+        """``time[d]`` float64 [n_d]; ``vo[d]`` / ``gps[d]`` [n_d, 4]; ``imu[d]`` [n_d]."""
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        lens = [len(t) for t in time]
+        offs = [0]
+        for n in lens:
+            offs.append(offs[-1] + n)
+
+        def cat(parts, dtype, width):
+            if parts is None:
+                return None
+            arrs = []
+            for d, p in enumerate(parts):
+                a = p.detach().cpu().numpy() if isinstance(p, torch.Tensor) else np.asarray(p)
+                if a.shape[0] != lens[d] or (width and (a.ndim != 2 or a.shape[1] != width)):
+                    raise ValueError(f"drive {d}: stream shape {a.shape} does not match {lens[d]} frames")
+                arrs.append(a.astype(dtype, copy=False))
+            return np.concatenate(arrs, axis=0) if arrs else np.zeros((0, width) if width else (0,), dtype)
+
+        return DriveSet(
+            time=_as_dev(cat(time, np.float64, 0), torch.float64, device),
+            vo=_as_dev(cat(vo, np.float32, 4), torch.float32, device),
+            gps=_as_dev(cat(gps, np.float32, 4), torch.float32, device),
+            imu=_as_dev(cat(imu, np.float32, 0), torch.float32, device),
+            drive_offsets=offs,
+            d_drive_offsets=torch.tensor(offs, dtype=torch.int64, device=device),
+            dt=_as_dev(np.asarray(dt, dtype=np.float64), torch.float64, device),
+        )
+
+
+@dataclass
+class WindowPlan:
+    window_offsets: List[int]              # host, len D+1
+    d_window_offsets: torch.Tensor         # int64 [D+1]
+    win_start: torch.Tensor                # int64 [n_windows] absolute frame index
+    win_len: torch.Tensor                  # int32 [n_windows]
+    win_drive: torch.Tensor                # int32 [n_windows]
+
+    @property
+    def n_windows(self) -> int:
+        return self.window_offsets[-1]
+
+
+def plan_windows(cfg: SearchConfig, drives: DriveSet) -> WindowPlan:
+    """a8 for every window of every drive (vmvo/schema.py:117-127, …v2.py:48)."""
+    ctx = _lib.context(drives.device.index)
+    c = cfg.to_c()
+    woffs = [0]
+    for d in range(drives.n_drives):
+        woffs.append(woffs[-1] + cfg.window_count(drives.drive_offsets[d + 1] - drives.drive_offsets[d]))
+    n = woffs[-1]
+    dev = drives.device
+    plan = WindowPlan(
+        window_offsets=woffs,
+        d_window_offsets=torch.tensor(woffs, dtype=torch.int64, device=dev),
+        win_start=torch.empty(n, dtype=torch.int64, device=dev),
+        win_len=torch.empty(n, dtype=torch.int32, device=dev),
+        win_drive=torch.empty(n, dtype=torch.int32, device=dev),
+    )
+    if n:
+        ctx.check(ctx.lib.vmvo_plan_windows(
+            ctx.handle, C.byref(c), drives.n_drives, _lib.ptr(drives.d_drive_offsets),
+            _lib.ptr(plan.d_window_offsets), n, _lib.ptr(drives.time), _lib.ptr(plan.win_start),
+            _lib.ptr(plan.win_len), _lib.ptr(plan.win_drive), _lib.stream_ptr(dev)), "vmvo_plan_windows")
+    return plan
+
+
+@dataclass
+class SearchOutput:
+    results: torch.Tensor                          # uint8 [n, 64]: vmvo_window_result records
+    poses: Optional[torch.Tensor] = None           # float64 [n, stride, 3]
+    steer: Optional[torch.Tensor] = None           # float64 [n, stride]
+    vel: Optional[torch.Tensor] = None             # float64 [n, stride]
+
+    def records(self) -> np.ndarray:
+        """Host copy as a NumPy record array (synchronises)."""
+        return self.results.cpu().numpy().view(_lib.RESULT_DTYPE).reshape(-1)
+
+
+def grid_search(cfg: SearchConfig, drives: DriveSet, plan: WindowPlan,
+                window_range: Optional[Tuple[int, int]] = None, seeds: Optional[torch.Tensor] = None,
+                want_rollouts: bool = False, out: Optional[torch.Tensor] = None) -> SearchOutput:
+    """The fused search over windows [lo, hi) of the plan (default: all).
+
+    ``out``: optional uint8 [n, 64] tensor the records are written into (e.g. this rank's
+    slice of the gather buffer, scheduler.py).
+    """
+    ctx = _lib.context(drives.device.index)
+    c = cfg.to_c()
+    lo, hi = (0, plan.n_windows) if window_range is None else window_range
+    n = hi - lo
+    dev = drives.device
+    results = out if out is not None else torch.empty((n, 64), dtype=torch.uint8, device=dev)
+    if results.shape != (n, 64) or results.dtype != torch.uint8 or not results.is_contiguous():
+        raise ValueError("out must be a contiguous uint8 [n_windows, 64] tensor")
+    so = SearchOutput(results=results)
+    stride = cfg.pose_capacity() - 1
+    if want_rollouts:
+        so.poses = torch.full((n, stride, 3), float("nan"), dtype=torch.float64, device=dev)
+        so.steer = torch.full((n, stride), float("nan"), dtype=torch.float64, device=dev)
+        so.vel = torch.full((n, stride), float("nan"), dtype=torch.float64, device=dev)
+    d_seeds = None
+    if seeds is not None:
+        d_seeds = _as_dev(seeds, torch.float64, dev)
+        if d_seeds.shape != (plan.n_windows, 2):
+            raise ValueError("seeds must be [n_windows, 2]")
+        d_seeds = d_seeds[lo:hi].contiguous()
+    if n:
+        ctx.check(ctx.lib.vmvo_grid_search_f32(
+            ctx.handle, C.byref(c), n, _lib.ptr(plan.win_start[lo:hi]), _lib.ptr(plan.win_len[lo:hi]),
+            _lib.ptr(plan.win_drive[lo:hi]), _lib.ptr(drives.dt), _lib.ptr(drives.vo),
+            _lib.ptr(drives.gps), _lib.ptr(drives.imu), _lib.ptr(d_seeds), _lib.ptr(results),
+            _lib.ptr(so.poses), _lib.ptr(so.steer), _lib.ptr(so.vel), stride,
+            _lib.stream_ptr(dev)), "vmvo_grid_search_f32")
+    return so
+
+
+def write_back(cfg: SearchConfig, drives: DriveSet, plan: WindowPlan, results: torch.Tensor,
+               blend_gps: bool = True) -> torch.Tensor:
+    """a12: float64 [4, F] = x, y, theta, velocity (optimize_trajectory_v2.py:32-33,122-137)."""
+    ctx = _lib.context(drives.device.index)
+    c = cfg.to_c()
+    if drives.vo is None:
+        raise ValueError("write_back copies the VO stream: drives.vo is required")
+    if results.shape != (plan.n_windows, 64):
+        raise ValueError("results must hold one record per planned window")
+    out = torch.empty((4, drives.n_frames), dtype=torch.float64, device=drives.device)
+    gps = drives.gps if blend_gps else None
+    ctx.check(ctx.lib.vmvo_write_back_f32(
+        ctx.handle, C.byref(c), drives.n_drives, drives.n_frames, _lib.ptr(drives.d_drive_offsets),
+        _lib.ptr(plan.d_window_offsets), _lib.ptr(drives.dt), _lib.ptr(drives.vo), _lib.ptr(gps),
+        _lib.ptr(results), _lib.ptr(out[0]), _lib.ptr(out[1]), _lib.ptr(out[2]), _lib.ptr(out[3]),
+        _lib.stream_ptr(drives.device)), "vmvo_write_back_f32")
+    return out
+
+
+def optimize_drives(cfg: SearchConfig, drives: DriveSet, plan: Optional[WindowPlan] = None,
+                    seeds: Optional[torch.Tensor] = None) -> Tuple[SearchOutput, torch.Tensor, WindowPlan]:
+    """plan -> search -> write-back for a batch of drives on the current device."""
+    if plan is None:
+        plan = plan_windows(cfg, drives)
+    so = grid_search(cfg, drives, plan, seeds=seeds)
+    traj = write_back(cfg, drives, plan, so.results)
+    return so, traj, plan
+
+
+def hypothesis_steps(cfg: SearchConfig, records: np.ndarray) -> int:
+    """Sum over windows of G_v * G_s * N_w: the unit of the throughput metric."""
+    return int(cfg.grid_v) * int(cfg.grid_s) * int(records["n_steps"].astype(np.int64).sum())
