@@ -1,0 +1,143 @@
+"""Edge cases of the window search: structural ties, saturation, mirror symmetry, non-finite
+and empty windows, capacity overflow of the candidate list."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import vmvo_oracle as O
+from tests.helpers import assert_records_match, oracle_windows
+from vehiclemodelvisualodometry_b200 import DriveSet, SearchConfig, grid_search, plan_windows
+from vehiclemodelvisualodometry_b200.synthetic import synthetic_drives
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(cfg, time, dt, vo, gps=None, imu=None, seeds=None):
+    drives = DriveSet.from_arrays([time], [dt], vo=[vo], gps=None if gps is None else [gps],
+                                  imu=None if imu is None else [imu])
+    plan = plan_windows(cfg, drives)
+    out = grid_search(cfg, drives, plan, seeds=None if seeds is None else torch.as_tensor(seeds))
+    return out.records()
+
+
+def _straight(n, v, dt=0.05, heading=0.0):
+    t = 100.0 + np.arange(n) * dt
+    s = v * dt * np.arange(n)
+    vo = np.stack([s * np.cos(heading), s * np.sin(heading), np.full(n, heading), np.full(n, v)], axis=1)
+    return t, vo.astype(np.float32)
+
+
+def test_stationary_vehicle_all_tied_lowest_index_wins(cuda_device):
+    """V_w = 0: every a_i <= 0 row never moves, all its costs tie exactly -> index 0."""
+    cfg = SearchConfig(grid_v=8, grid_s=8, window_frames=10)
+    n = 30
+    t = 5.0 + np.arange(n) * 0.05
+    vo = np.zeros((n, 4), dtype=np.float32)
+    rec = _run(cfg, t, 0.05, vo)
+    ref = oracle_windows(cfg, t, 0.05, vo)
+    assert_records_match(rec, ref)
+    assert np.all(rec["best_idx"] == 0)
+    assert np.all(rec["n_rescored"] >= 32)      # the whole tied set was re-scored in float64
+
+
+def test_large_tied_set_overflows_candidate_list(cuda_device):
+    """64x64 grid, stationary: 2048+ exactly tied hypotheses > 1024-entry list -> flush path."""
+    cfg = SearchConfig(grid_v=64, grid_s=64, window_frames=8)
+    n = 20
+    t = 5.0 + np.arange(n) * 0.05
+    vo = np.zeros((n, 4), dtype=np.float32)
+    rec = _run(cfg, t, 0.05, vo)
+    ref = oracle_windows(cfg, t, 0.05, vo)
+    assert_records_match(rec, ref)
+    assert np.all(rec["best_idx"] == 0)
+    assert np.all(rec["n_rescored"] >= 2048)
+
+
+def test_nearly_stationary(cuda_device):
+    """Tiny V_w: decelerating rows die after one step; costs differ far below FP32 resolution."""
+    cfg = SearchConfig(grid_v=16, grid_s=16, window_frames=12)
+    rng = np.random.default_rng(1)
+    n = 40
+    t = 5.0 + np.arange(n) * 0.05
+    vo = np.zeros((n, 4), dtype=np.float32)
+    vo[:, 0] = np.cumsum(rng.normal(0, 1e-3, n))
+    vo[:, 1] = np.cumsum(rng.normal(0, 1e-3, n))
+    vo[:, 2] = rng.normal(0, 0.01, n)
+    vo[:, 3] = np.abs(rng.normal(0, 0.02, n))
+    rec = _run(cfg, t, 0.05, vo)
+    ref = oracle_windows(cfg, t, 0.05, vo)
+    assert_records_match(rec, ref)
+
+
+def test_mirror_symmetric_hypotheses_tie_exactly(cuda_device):
+    """Straight target along x with S_w = 0: rate j and G_s-1-j mirror each other and their
+    float64 costs are identical; np.argmin keeps the lower index."""
+    cfg = SearchConfig(grid_v=6, grid_s=8, window_frames=20, seed_mode="given")
+    t, vo = _straight(60, 8.0)
+    # seed speed off the true speed so the best steering rate is not the centre one
+    seeds = np.tile([[8.0, 0.0]], (20, 1))
+    rec = _run(cfg, t, 0.05, vo, seeds=seeds)
+    ref = oracle_windows(cfg, t, 0.05, vo, seeds=seeds)
+    assert_records_match(rec, ref)
+    j = rec["best_idx"] % 8
+    assert np.all(j < 4)                # of each mirrored pair the lower index won
+
+
+def test_steering_seed_saturated(cuda_device):
+    """S_w at +max_steer: every r_j >= 0 clamps to the same sequence -> exact ties."""
+    cfg = SearchConfig(grid_v=4, grid_s=9, window_frames=15, seed_mode="given")
+    batch = synthetic_drives(1, 50, seed=12)
+    seeds = np.tile([[6.0, 460.0]], (20, 1))
+    rec = _run(cfg, batch.time[0], batch.dt, batch.vo[0], seeds=seeds)
+    ref = oracle_windows(cfg, batch.time[0], batch.dt, batch.vo[0], seeds=seeds)
+    assert_records_match(rec, ref)
+
+
+def test_nonfinite_window_flagged(cuda_device):
+    cfg = SearchConfig(grid_v=4, grid_s=4, window_frames=10)
+    batch = synthetic_drives(1, 45, seed=6)
+    vo = batch.vo[0].copy()
+    vo[17, 0] = np.nan
+    vo[30, 1] = np.inf
+    rec = _run(cfg, batch.time[0], batch.dt, vo)
+    ref = oracle_windows(cfg, batch.time[0], batch.dt, vo)
+    assert_records_match(rec, ref)
+    assert np.any(rec["status"] & 2) and not np.all(rec["status"] & 2)
+    assert np.all(rec["best_idx"][(rec["status"] & 2) != 0] == 0)
+
+
+def test_traverse_empty_window_when_stationary(cuda_device):
+    """Quirk D7: a stationary window decimates to one point -> N = 0, no result."""
+    cfg = SearchConfig(grid_v=4, grid_s=4, window_frames=10, target_mode="traverse")
+    n = 40
+    t = 5.0 + np.arange(n) * 0.05
+    vo = np.zeros((n, 4), dtype=np.float32)
+    vo[:, 3] = 1.0                      # claims 1 m/s but never moves
+    rec = _run(cfg, t, 0.05, vo)
+    ref = oracle_windows(cfg, t, 0.05, vo)
+    assert_records_match(rec, ref)
+    assert np.all(rec["status"] & 1) and np.all(rec["n_steps"] == 0) and np.all(rec["best_idx"] == -1)
+
+
+def test_window_longer_than_capacity_is_flagged(cuda_device):
+    cfg = SearchConfig(grid_v=4, grid_s=4, window_mode="time", horizon_time=2.0, horizon_frames=40,
+                       max_window_poses=16)
+    batch = synthetic_drives(1, 100, seed=6)
+    rec = _run(cfg, batch.time[0], batch.dt, batch.vo[0])
+    assert np.all(rec["status"] == 4) and np.all(rec["best_idx"] == -1)
+
+
+def test_high_speed_large_heading(cuda_device):
+    """30 m/s seed, full lock available: headings of several radians, largest FP32 error band."""
+    cfg = SearchConfig(grid_v=16, grid_s=32, window_frames=60)
+    rng = np.random.default_rng(3)
+    n = 130
+    dt = 0.05
+    t = 1.0 + np.arange(n) * dt
+    th = np.cumsum(np.full(n, 0.02))
+    x = np.cumsum(30 * np.cos(th) * dt) + rng.normal(0, 0.05, n)
+    y = np.cumsum(30 * np.sin(th) * dt) + rng.normal(0, 0.05, n)
+    vo = np.stack([x, y, th, np.full(n, 30.0)], axis=1).astype(np.float32)
+    rec = _run(cfg, t, dt, vo)
+    ref = oracle_windows(cfg, t, dt, vo)
+    assert_records_match(rec, ref)

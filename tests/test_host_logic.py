@@ -1,0 +1,131 @@
+"""CPU: host-side logic -- config mapping, the C-ABI library's exports, the window scheduler,
+and the world-size-2 gather over gloo."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vmvo_oracle as O
+from tests.helpers import spec_of
+from vehiclemodelvisualodometry_b200 import SearchConfig, _lib, scheduler
+from vehiclemodelvisualodometry_b200.synthetic import synthetic_drives
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(built_library):
+    header = open(os.path.join(ROOT, "include", "vmvo_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|int64_t|void|const char\*)\s+(vmvo_[a-z0-9_]+)\(", header, re.M))
+    assert len(declared) >= 17
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    lib = ctypes.CDLL(built_library)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _lib.load().vmvo_abi_version() == 1
+
+
+def test_struct_layouts_match_the_header():
+    assert ctypes.sizeof(_lib.SearchCfg) == 10 * 4 + 10 * 8
+    assert _lib.RESULT_DTYPE.itemsize == 64
+    assert _lib.RESULT_DTYPE.fields["best_cost"][1] == 16 and _lib.RESULT_DTYPE.fields["theta1"][1] == 56
+
+
+def test_cfg_defaults_and_window_count(built_library):
+    c = _lib.default_cfg()
+    assert (c.grid_v, c.grid_s, c.window_frames, c.horizon_time) == (32, 32, 30, 3.0)
+    assert (c.wheel_base, c.steering_ratio, c.max_steer, c.max_accel, c.max_steer_rate) == (
+        O.WHEEL_BASE, O.STEERING_RATIO, O.MAX_STEER, float(O.MAX_ACCEL), O.MAX_STEER_RATE)
+    assert _lib.window_count(c, 10000) == 9940          # BASELINE config 2
+    assert _lib.window_count(c, 60) == 0 and _lib.window_count(c, 5) == 0
+    cfg = SearchConfig(window_mode="time", horizon_frames=59)
+    assert cfg.window_count(260) == 142 and _lib.window_count(cfg.to_c(), 260) == 142
+
+
+def test_search_config_maps_to_oracle_spec_and_c_struct():
+    cfg = SearchConfig(grid_v=7, grid_s=9, target_mode="traverse", primary="gps", w_vo=0.0, w_gps=2.0,
+                       k_steer=1e-6, seed_mode="given")
+    spec = spec_of(cfg)
+    assert (spec.grid_v, spec.target_mode, spec.primary, spec.w_gps) == (7, "traverse", "gps", 2.0)
+    c = cfg.to_c()
+    assert (c.grid_v, c.grid_s, c.target_mode, c.primary, c.seed_mode) == (7, 9, 1, 1, 1)
+    assert c.max_window_poses == 31 and c.w_gps == 2.0 and c.k_steer == 1e-6
+    with pytest.raises(ValueError):
+        SearchConfig(target_mode="nope").to_c()
+
+
+def test_no_gpu_means_loud_failure(built_library):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from vehiclemodelvisualodometry_b200 import BicycleModel
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        BicycleModel().run(1.0, 0.0, 0.1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.context()
+
+
+def test_shard_range_partitions_exactly():
+    for n in (0, 1, 7, 9940, 3010560):
+        for world in (1, 2, 3, 4, 8):
+            spans = [scheduler.shard_range(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1 and max(sizes) <= scheduler.shard_capacity(n, world)
+
+
+def test_assign_drives_balances():
+    counts = [5880] * 13 + [100, 19940, 7]
+    plan = scheduler.assign_drives(counts, 4)
+    assert sorted(d for r in plan for d in r) == list(range(len(counts)))
+    loads = [sum(counts[d] for d in r) for r in plan]
+    assert max(loads) - min(loads) <= max(counts)
+
+
+def test_synthetic_drive_shape():
+    b = synthetic_drives(3, 500, seed=5)
+    assert b.vo.shape == (3, 500, 4) and b.vo.dtype == np.float32 and b.time.dtype == np.float64
+    assert np.all(np.diff(b.time, axis=1) > 0) and abs(np.mean(np.diff(b.time[0])) - 0.05) < 1e-6
+    assert np.all(b.gt[..., 3] >= 0) and np.all(b.gt[..., 3] <= 15)
+    b2 = synthetic_drives(3, 500, seed=5)
+    np.testing.assert_array_equal(b.vo, b2.vo)
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+from vehiclemodelvisualodometry_b200 import scheduler, _lib
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+n = 37
+want = np.zeros(n, dtype=_lib.RESULT_DTYPE)
+want["best_idx"] = np.arange(n) * 3
+want["best_cost"] = np.arange(n) * 0.5
+def fake_search(rng, out):      # stands in for grid_search(..., window_range=rng, out=out)
+    lo, hi = rng
+    out.copy_(torch.from_numpy(want[lo:hi].view(np.uint8).reshape(hi - lo, 64)))
+got = scheduler.search_sharded(fake_search, n, torch.device("cpu"))
+rec = got.numpy().view(_lib.RESULT_DTYPE).reshape(-1)
+assert rec.shape == (n,) and np.array_equal(rec["best_idx"], want["best_idx"])
+assert np.array_equal(rec["best_cost"], want["best_cost"])
+dist.destroy_process_group()
+print("rank", sys.argv[1], "ok")
+"""
+
+
+def test_sharded_search_gathers_over_gloo_world2(tmp_path):
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
