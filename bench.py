@@ -1,0 +1,444 @@
+#!/usr/bin/env python
+"""Throughput of the VMVO window search: bicycle-model hypothesis-steps per second.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A step is one pass of the hot path over one batch of synthetic drives: window planning,
+the fused grid search and the write-back (plus, at N > 1, the all-gather of the 64-byte
+window records over NCCL).  At N = 1 the workload is BASELINE.json configs[1]: one
+10 000-frame drive, 32x32 hypothesis grid, 30-step windows (9 940 windows, 3.05e8
+hypothesis-steps).  At N > 1 every rank searches its own drive of that shape (weak scaling).
+
+Rank 0 prints ONE JSON line (see the driver's contract in the task statement).  Keys beyond
+the contract: "roofline" (SFU-issue bound, with the HBM and FP32 figures beside it),
+"cpu_baseline" (the C/OpenMP oracle port on all host cores), "windows_per_s", and
+"dense_grid" (BASELINE configs[2], 256x256 x 60 steps: the compute-bound stress the
+roofline fraction is normally quoted on).
+
+--impl reference times the CPU implementation of the same path on the host cores: the
+reference itself is pure Python and does not travel to the GPU box, so this is the oracle
+port (oracle/vmvo_oracle.c, OpenMP over windows) on the same config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "bicycle_model_hypothesis_steps_per_sec"
+UNIT = "hypothesis-steps/s"
+BASE_SEED = 1658384707877 % (2 ** 32)
+
+# algorithmic work per hypothesis-step (SURVEY.md 8d / DESIGN.md 5): tan, cos, sin = 5 MUFU
+# ops (tan = sin + cos + rcp) and 25 FP32 flops
+MUFU_PER_HSTEP = 5
+FLOP_PER_HSTEP = 25
+# executed by the kernel per hypothesis-step at C = 8 hypotheses per thread
+EXEC_MUFU_PER_HSTEP = 2.0
+
+WORKLOADS = {
+    # name: (frames per drive, grid_v, grid_s, window steps)
+    "config2_single_drive_10k_32x32_w30": (10000, 32, 32, 30),
+    "config3_dense_256x256_w60": (4216, 256, 256, 60),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="config2_single_drive_10k_32x32_w30", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-extras", action="store_true", help="skip dense-grid, probes and CPU baseline")
+    return ap.parse_args()
+
+
+def make_cfg(workload):
+    from vehiclemodelvisualodometry_b200 import SearchConfig
+
+    n, gv, gs, w = WORKLOADS[workload]
+    return n, SearchConfig(grid_v=gv, grid_s=gs, window_frames=w)
+
+
+# ---- clocks ----------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons, smax, power = [], set(), None, []
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    smax = float(f[2])
+                    power.append(float(f[3]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                      "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=smax, samples=len(sm),
+                       power_w_max=max(power) if power else None)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ---- the B200 arm --------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from vehiclemodelvisualodometry_b200 import (DriveSet, _lib, grid_search, plan_windows, write_back)
+    from vehiclemodelvisualodometry_b200 import build as vbuild
+    from vehiclemodelvisualodometry_b200.synthetic import synthetic_drives
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: no CUDA device visible (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0 and vbuild.is_stale():
+        vbuild.build_library()
+    if world > 1:
+        dist.barrier()
+    ctx = _lib.context(local_rank)
+
+    n_frames, cfg = make_cfg(args.workload)
+    batch = synthetic_drives(1, n_frames, seed=BASE_SEED + rank)
+    time_h, vo_h, gps_h, imu_h = batch.drive(0)
+    drives = DriveSet.from_arrays([time_h], [batch.dt], vo=[vo_h], device=dev)
+    plan = plan_windows(cfg, drives)
+    n_win = plan.n_windows
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # 2x the 126 MB L2
+    gathered = torch.empty((world * n_win, 64), dtype=torch.uint8, device=dev)
+    local = gathered[rank * n_win:(rank + 1) * n_win]
+
+    def step():
+        p = plan_windows(cfg, drives)
+        so = grid_search(cfg, drives, p, out=local)
+        traj = write_back(cfg, drives, p, so.results, blend_gps=False)
+        if world > 1:  # the only exchange of the path: per-window records to every rank
+            dist.all_gather_into_tensor(gathered, local)
+        return so, traj
+
+    def timed(fn, k, w):
+        for _ in range(w):
+            flush.zero_()
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        evs = []
+        for _ in range(k):
+            flush.zero_()  # evict the pose stream and the records from L2 between steps
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count()
+    total_ms = timed(step, args.steps, args.warmup)
+    launches = (ctx.launch_count() - launches0) // (args.steps + args.warmup) * args.steps
+    rec = step()[0].records()
+    torch.cuda.synchronize()
+    hsteps = int(cfg.grid_v) * int(cfg.grid_s) * int(rec["n_steps"].astype(np.int64).sum())
+    ms_per_step = total_ms / args.steps
+    value = hsteps * world / (ms_per_step * 1e-3)
+
+    # search kernel alone (the dominant kernel): average launch duration for the roofline
+    kern_ms = timed(lambda: grid_search(cfg, drives, plan, out=local), args.steps, 2) / args.steps
+
+    # end to end through the public API with HOST buffers: H2D of the pose stream and stamps,
+    # plan + search + write-back, D2H of the records and the written-back trajectory
+    vo_pin = torch.from_numpy(np.ascontiguousarray(vo_h)).pin_memory()
+    t_pin = torch.from_numpy(np.ascontiguousarray(time_h)).pin_memory()
+    rec_pin = torch.empty((n_win, 64), dtype=torch.uint8).pin_memory()
+    traj_pin = torch.empty((4, n_frames), dtype=torch.float64).pin_memory()
+
+    def e2e_step():
+        drives.vo.copy_(vo_pin, non_blocking=True)
+        drives.time.copy_(t_pin, non_blocking=True)
+        so, traj = step()
+        rec_pin.copy_(so.results, non_blocking=True)
+        traj_pin.copy_(traj, non_blocking=True)
+
+    e2e_ms = timed(e2e_step, args.steps, args.warmup) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 scan + f64 re-score",
+        "data": "synthetic (urban stop-and-go drives shaped like BDD sequences, seeds base+rank)",
+        "config": {"workload": args.workload, "frames_per_drive": n_frames, "drives_per_gpu": 1,
+                   "grid": [cfg.grid_v, cfg.grid_s], "window_steps": cfg.window_frames,
+                   "windows_per_gpu": n_win, "hypothesis_steps_per_gpu": hsteps,
+                   "cache": "256 MiB L2 flush between timed steps", "base_seed": BASE_SEED},
+        "windows_per_s": n_win * world / (ms_per_step * 1e-3),
+        "gpu_launches": int(launches),
+        "e2e": {"value": hsteps * world / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(vo_pin.numel() * 4 + t_pin.numel() * 8),
+                "d2h_bytes_per_step": int(rec_pin.numel() + traj_pin.numel() * 8)},
+        "clocks": clocks,
+        "rescored_per_window": float(rec["n_rescored"].mean()),
+    }
+
+    if rank == 0:
+        line["roofline"] = roofline(ctx, dev, hsteps, kern_ms, n_frames, n_win, clocks, args)
+        if world == 1 and not args.no_extras:
+            line["dense_grid"] = dense_grid(ctx, dev, timed, args)
+            line["cpu_baseline"] = cpu_baseline(args.workload, budget_s=12.0)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def probe_peak(ctx, dev, kind, ops_per_iter):
+    """Measured issue peak of one pipe: ops/s over the whole chip."""
+    import torch
+
+    from vehiclemodelvisualodometry_b200 import _lib
+
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    blocks, threads, iters = sms * 8, 256, 4096
+    sink = torch.empty(blocks * threads, dtype=torch.float32, device=dev)
+    best = None
+    for it in range(4):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ctx.check(ctx.lib.vmvo_peak_probe(ctx.handle, kind, blocks, threads, iters, _lib.ptr(sink),
+                                          _lib.stream_ptr(dev)), "vmvo_peak_probe")
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+        if it > 0:
+            best = ms if best is None else min(best, ms)
+    return blocks * threads * iters * ops_per_iter / (best * 1e-3)
+
+
+def roofline(ctx, dev, hsteps, kern_ms, n_frames, n_win, clocks, args):
+    import torch
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    sm_max = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
+    nominal_mufu = sms * 16 * sm_max * 1e6
+    out = {"bound": "sfu", "kernel": "vmvo_window_search_kernel", "unit": "GMUFU-op/s",
+           "kernel_ms_per_launch": kern_ms,
+           "algorithmic_mufu_per_hypothesis_step": MUFU_PER_HSTEP,
+           "executed_mufu_per_hypothesis_step": EXEC_MUFU_PER_HSTEP}
+    achieved = hsteps * MUFU_PER_HSTEP / (kern_ms * 1e-3)
+    out["achieved"] = achieved / 1e9
+    out["peak_nominal"] = nominal_mufu / 1e9
+    if not args.no_extras:
+        mufu = probe_peak(ctx, dev, 0, 16)
+        ffma = probe_peak(ctx, dev, 1, 16)
+        dfma = probe_peak(ctx, dev, 2, 8)
+        out["peak"] = mufu / 1e9
+        out["peak_source"] = "measured live: vmvo_peak_probe MUFU.SIN/COS issue rate, whole chip"
+        out["fp32_tflops_measured"] = 2 * ffma / 1e12
+        out["fp64_tflops_measured"] = 2 * dfma / 1e12
+        out["fp32_frac_algorithmic"] = hsteps * FLOP_PER_HSTEP / (kern_ms * 1e-3) / (2 * ffma)
+    else:
+        out["peak"] = nominal_mufu / 1e9
+        out["peak_source"] = "nominal: SMs x 16 MUFU lanes x max SM clock"
+    out["frac"] = out["achieved"] / out["peak"]
+    out["frac_executed"] = out["frac"] * EXEC_MUFU_PER_HSTEP / MUFU_PER_HSTEP
+    # HBM side, for the record: one read of the pose stream + one 64-byte record per window
+    algo_bytes = n_frames * 16 + n_win * (64 + 16)
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    out["hbm"] = {"algorithmic_bytes_per_launch": algo_bytes,
+                  "achieved_gbs": algo_bytes / (kern_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                  "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback",
+                  "frac": algo_bytes / (kern_ms * 1e-3) / 1e9 / hbm_peak}
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+    except Exception:
+        pass
+    out["traffic"] = traffic
+    return out
+
+
+def dense_grid(ctx, dev, timed, args):
+    """BASELINE configs[2]: 256x256 grid, 60-step windows, 4096 windows (1.6e10 hyp-steps)."""
+    import torch
+
+    from vehiclemodelvisualodometry_b200 import DriveSet, grid_search, plan_windows
+    from vehiclemodelvisualodometry_b200.synthetic import synthetic_drives
+
+    name = "config3_dense_256x256_w60"
+    n_frames, cfg = make_cfg(name)
+    batch = synthetic_drives(1, n_frames, seed=BASE_SEED + 3)
+    t, vo, _, _ = batch.drive(0)
+    drives = DriveSet.from_arrays([t], [batch.dt], vo=[vo], device=dev)
+    plan = plan_windows(cfg, drives)
+    out = torch.empty((plan.n_windows, 64), dtype=torch.uint8, device=dev)
+    k = 3
+    ms = timed(lambda: grid_search(cfg, drives, plan, out=out), k, 1) / k
+    rec = out.cpu().numpy().view(np.dtype([("i", np.int32), ("n", np.int32), ("rest", np.uint8, 56)]))
+    hsteps = cfg.grid_v * cfg.grid_s * int(rec["n"].astype(np.int64).sum())
+    return {"workload": name, "windows": plan.n_windows, "hypothesis_steps": hsteps, "kernel_ms": ms,
+            "value": hsteps / (ms * 1e-3), "unit": UNIT,
+            "achieved_gmufu": hsteps * MUFU_PER_HSTEP / (ms * 1e-3) / 1e9}
+
+
+# ---- CPU legs -------------------------------------------------------------------------------------
+def cpu_pass(workload, seed, max_windows=None, threads=0):
+    """One pass of the oracle port over (a sample of) the workload; returns (hyp-steps, seconds)."""
+    from oracle import c_oracle
+    from oracle import vmvo_oracle as O
+    from vehiclemodelvisualodometry_b200.synthetic import synthetic_drives
+
+    n_frames, cfg = make_cfg(workload)
+    batch = synthetic_drives(1, n_frames, seed=seed)
+    t, vo, _, _ = batch.drive(0)
+    spec = O.SearchSpec(grid_v=cfg.grid_v, grid_s=cfg.grid_s, window_frames=cfg.window_frames)
+    starts, lens = O.window_extents(spec, t)
+    if max_windows is not None and len(starts) > max_windows:
+        sel = np.linspace(0, len(starts) - 1, max_windows).astype(np.int64)
+        starts, lens = starts[sel], lens[sel]
+    t0 = time.perf_counter()
+    rec, steps = c_oracle.search(cfg.to_c(), starts, lens, np.zeros(len(starts), np.int32), [batch.dt],
+                                 vo, n_threads=threads)
+    return steps, time.perf_counter() - t0, len(starts)
+
+
+def cpu_baseline(workload, budget_s=12.0):
+    from oracle import c_oracle
+
+    cores = c_oracle.max_threads()
+    steps, sec, nwin = cpu_pass(workload, BASE_SEED, max_windows=256, threads=cores)  # calibration
+    rate = steps / sec
+    n_frames, cfg = make_cfg(workload)
+    total_win = n_frames - 2 * cfg.window_frames
+    per_win = cfg.grid_v * cfg.grid_s * cfg.window_frames
+    want = int(max(64, min(total_win, rate * budget_s / per_win)))
+    steps, sec, nwin = cpu_pass(workload, BASE_SEED, max_windows=want, threads=cores)
+    return {"value": steps / sec, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{nwin} of {total_win} windows of {workload}, evenly spaced; "
+                      f"oracle/vmvo_oracle.c (float64, OpenMP over windows), {sec:.1f} s"}
+
+
+def run_reference(args):
+    """The CPU implementation of the path on all host cores (oracle port; rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import c_oracle
+
+    cores = c_oracle.max_threads()
+    n_frames, cfg = make_cfg(args.workload)
+    total_win = n_frames - 2 * cfg.window_frames
+    per_win = cfg.grid_v * cfg.grid_s * cfg.window_frames
+    # bounded sample per step: size it from a calibration pass so the whole run takes ~1 min
+    steps0, sec0, _ = cpu_pass(args.workload, BASE_SEED, max_windows=128, threads=cores)
+    budget = 60.0 / max(1, args.steps + args.warmup)
+    want = int(max(64, min(total_win, (steps0 / sec0) * budget / per_win)))
+    for _ in range(args.warmup):
+        cpu_pass(args.workload, BASE_SEED, max_windows=want, threads=cores)
+    tot_steps, tot_sec, nwin = 0, 0.0, 0
+    for _ in range(args.steps):
+        s, sec, nwin = cpu_pass(args.workload, BASE_SEED, max_windows=want, threads=cores)
+        tot_steps += s
+        tot_sec += sec
+    value = tot_steps / tot_sec
+    sample = (f"{nwin} of {total_win} windows per step, evenly spaced; oracle/vmvo_oracle.c "
+              f"(float64, OpenMP over windows)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_sec / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic (same generator and seed as the b200 arm)",
+        "config": {"workload": args.workload, "frames_per_drive": n_frames,
+                   "grid": [cfg.grid_v, cfg.grid_s], "window_steps": cfg.window_frames},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "the reference is pure Python (15 us per model step, ~6.7e4 steps/s/core, SURVEY.md F8) "
+                "and cannot travel to the GPU box; this arm is its C restatement on all host threads",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

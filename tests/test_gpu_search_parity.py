@@ -58,8 +58,9 @@ def test_search_matches_oracle(cuda_device, name):
     for w, r in enumerate(ref):
         N = r.n_steps
         np.testing.assert_allclose(poses[w, :N], r.poses, rtol=0, atol=1e-9)
-        np.testing.assert_array_equal(steer[w, :N], r.steer)     # IEEE ops only: bit-exact
-        np.testing.assert_array_equal(vel[w, :N], r.vel)
+        # IEEE ops on the seeds; the seed itself carries atan's last-bit difference
+        np.testing.assert_allclose(steer[w, :N], r.steer, rtol=1e-13, atol=1e-12)
+        np.testing.assert_allclose(vel[w, :N], r.vel, rtol=1e-13, atol=1e-13)
 
 
 def test_given_seeds(cuda_device):

@@ -159,3 +159,30 @@ def test_restatement_against_live_reference():
         p = np.cumsum(rng.normal(0, 0.3, (N + 1, 2)), axis=0)
         D = float(rng.uniform(0.05, 1))
         np.testing.assert_array_equal(ref.mpc.traverse_trajectory(p, D), O.traverse_trajectory(p, D))
+
+
+def test_c_restatement_equals_numpy_oracle():
+    """oracle/vmvo_oracle.c (the fast checker / CPU baseline) against oracle/vmvo_oracle.py."""
+    from oracle import c_oracle
+    from tests.helpers import oracle_windows, spec_of
+    from vehiclemodelvisualodometry_b200 import SearchConfig
+
+    cases = [
+        SearchConfig(grid_v=16, grid_s=16, window_frames=20),
+        SearchConfig(grid_v=8, grid_s=12, window_frames=24, w_vo=1.0, w_gps=0.5, w_imu=40.0),
+        SearchConfig(grid_v=8, grid_s=24, window_frames=40, target_mode="traverse", primary="gps",
+                     w_vo=0.0, w_gps=1.0),
+        SearchConfig(grid_v=5, grid_s=7, window_frames=20, k_steer=5e-6, target_offset=0),
+    ]
+    for cfg in cases:
+        n = 2 * cfg.horizon() + 30
+        b = synthetic_drives(1, n, seed=5)
+        st, ln = O.window_extents(spec_of(cfg), b.time[0])
+        rec, steps = c_oracle.search(cfg.to_c(), st, ln, np.zeros(len(st), np.int32), [b.dt], b.vo[0],
+                                     b.gps[0], b.imu[0], n_threads=2)
+        ref = oracle_windows(cfg, b.time[0], b.dt, b.vo[0], b.gps[0], b.imu[0])
+        np.testing.assert_array_equal(rec["best_idx"], [r.best_idx for r in ref])
+        np.testing.assert_array_equal(rec["n_steps"], [r.n_steps for r in ref])
+        np.testing.assert_allclose(rec["best_cost"], [r.best_cost for r in ref], rtol=1e-13)
+        np.testing.assert_allclose(rec["x1"], [r.poses[0, 0] for r in ref], rtol=0, atol=1e-14)
+        assert steps == cfg.grid_v * cfg.grid_s * sum(r.n_steps for r in ref)
