@@ -123,6 +123,16 @@ int vmvo_grid_search_f32(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n_wi
                          double* d_out_poses, double* d_out_steer, double* d_out_vel,
                          int32_t out_stride, void* stream);
 
+/* Test hook: the same search, additionally exporting the FP32 scan cost of EVERY hypothesis
+ * and the width of its error band, [n_windows][grid_v * grid_s] each, so tests can check
+ * |scan - float64| <= band against the oracle.  Not for production use.  */
+int vmvo_grid_search_debug_f32(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n_windows,
+                               const int64_t* d_win_start, const int32_t* d_win_len,
+                               const int32_t* d_win_drive, const double* d_dt_per_drive,
+                               const float* d_vo, const float* d_gps, const float* d_imu,
+                               const double* d_seeds, vmvo_window_result* d_results,
+                               float* d_scan_cost, float* d_scan_err, void* stream);
+
 /* ---- a12: write-back and blends -----------------------------------------------------
  * Replaces optimize_trajectory_v2.py:32-33,122-137: output columns start as the VO stream,
  * window i overwrites x,y[i : i+N_i] with its local-frame rollout (later windows win),

@@ -1,5 +1,5 @@
 // Fused window search: window staging (TMA bulk copy) -> local frame (a7) -> decimation (a9)
-// -> seeds -> hypothesis grid generated in registers -> batched bicycle integration (a1/a2)
+// -> seeds -> hypothesis grid generated on chip -> batched bicycle integration (a1/a2)
 // -> cost (a10) -> block argmin -> exact float64 re-score of every hypothesis whose FP32 cost
 // lies within a rigorous error band of the minimum -> per-window result record.
 //
@@ -7,9 +7,11 @@
 // optimize_trajectory (vmvo/scripts/optimize_trajectory_v2.py:49-96) of the reference.
 //
 // Work decomposition: one CTA works on one window at a time and pulls
-// windows from a global queue (persistent grid).  Inside a window a thread owns one steering
-// rate r_j and C consecutive accelerations a_i: tan(delta_k(j)) is computed once per step and
-// shared by the C hypotheses; each hypothesis costs 2 MUFU (sin, cos) + ~10 FP32 per step.
+// windows from a global queue (persistent grid).  Per window the CTA builds two small tables
+// in shared memory -- TL[k][j] = tan(delta_k(j))/L and VD[k][i] = V_k(i)*dt -- so the scan's
+// inner loop is, per hypothesis-step: 1 FFMA (heading), sin+cos on the SFU, 4 FP32 ops for
+// the position error recurrence and 2 FFMA for the cost.  A thread owns one steering rate j
+// and C = 8 consecutive accelerations.
 #include "vmvo_device.cuh"
 #include "vmvo_internal.h"
 
@@ -17,6 +19,7 @@
 
 namespace vmvo {
 
+constexpr int kC = 8;            // hypotheses (consecutive accelerations) per thread
 constexpr int kCandCap = 1024;   // candidate list entries per CTA (flushed when full)
 constexpr int kMaxWarps = 8;     // CTA size <= 256 threads
 
@@ -28,9 +31,10 @@ struct SearchParams {
   int maxp;              // pose capacity per window
   int use_vo, use_gps;   // position terms with non-zero weight
   int load_vo, load_gps; // streams staged into shared memory
+  int vd_cols;           // columns of the VD table (accelerations covered by one pass)
   double w_vo, w_gps, w_imu, k_steer;
   double L, ratio, max_steer, max_accel, max_rate;
-  double delta_max, tan_max;
+  double delta_max, kappa;     // kappa = 2*delta_max / sin(2*delta_max): tan's condition number
   const long long* win_start;
   const int* win_len;
   const int* win_drive;
@@ -46,30 +50,37 @@ struct SearchParams {
   int out_stride;
   long long n_windows;
   unsigned long long* work_counter;
+  float* dbg_cost;       // optional [n_windows][gv*gs] FP32 scan costs   (tests only)
+  float* dbg_err;        // optional [n_windows][gv*gs] error-band widths (tests only)
 };
 
 // per-window scalars shared by the CTA
 struct WinInfo {
   double v_seed, s_seed, dt;
-  long long start;
-  int len, n_targets, n_steps, status;
+  int n_targets, n_steps, status, pad;
 };
 
 // ---- shared-memory carve-up (same function on host and device) ---------------------------
 struct SmemLayout {
-  int off_raw, off_loc, off_loci, off_tgt, off_fa, off_fb, off_fi, off_keep, off_cand, total;
-  __host__ __device__ explicit SmemLayout(int P) {
-    int o = 1024;                       // fixed header: barriers, window ids, reductions
-    off_raw = o;  o += 2 * 2 * P * 16;  // float4 raw[2 buffers][2 streams][P]
-    off_loc = o;  o += 2 * 3 * P * 8;   // double loc[2 streams][3][P]  (lx, ly, lth)
-    off_loci = o; o += P * 8;           // double imu yaw relative to the window start
-    off_tgt = o;  o += 5 * P * 8;       // double tAx, tAy, tBx, tBy, tI
-    off_fa = o;   o += P * 8;           // float2 fA
-    off_fb = o;   o += P * 8;           // float2 fB
-    off_fi = o;   o += P * 4;           // float fI
-    off_keep = o; o += P * 4;           // int keep
+  int off_raw, off_loc, off_loci, off_tgt, off_df, off_dab, off_fi, off_keep, off_tl, off_js,
+      off_vd, off_cand, total;
+  __host__ __device__ SmemLayout(int P, int gs, int vd_cols) {
+    int o = 1024;                        // fixed header: barriers, window ids, reductions
+    off_raw = o;  o += 2 * 2 * P * 16;   // float4 raw[2 buffers][2 streams][P]
+    off_loc = o;  o += 2 * 3 * P * 8;    // double loc[2 streams][3][P]  (lx, ly, lth)
+    off_loci = o; o += P * 8;            // double imu yaw relative to the window start
+    off_tgt = o;  o += 5 * P * 8;        // double tAx, tAy, tBx, tBy, tI
+    off_df = o;   o += P * 8;            // float2 D[k]   = T_A[k-off] - T_A[k-1-off]
+    off_dab = o;  o += P * 8;            // float2 DAB[k] = T_A[k-off] - T_B[k-off]
+    off_fi = o;   o += P * 4;            // float  imu target per step
+    off_keep = o; o += P * 4;            // int keep
     o = (o + 15) & ~15;
-    off_cand = o; o += kCandCap * 8;    // uint2 (hypothesis, float cost bits)
+    off_tl = o;   o += P * gs * 4;       // float TL[k][j]
+    off_js = o;   o += ((gs + 3) & ~3) * 4;  // float sum_k S_k(j)^2 (steering penalty)
+    o = (o + 15) & ~15;
+    off_vd = o;   o += P * vd_cols * 4;  // float VD[k][m]
+    o = (o + 15) & ~15;
+    off_cand = o; o += kCandCap * 8;     // uint2 (hypothesis, float lower-bound bits)
     total = o;
   }
 };
@@ -88,44 +99,40 @@ struct SmemHeader {
 };
 static_assert(sizeof(SmemHeader) <= 1024, "header too large");
 
-// err(J) = c0 + c1*sqrt(J) + c2*J bounds |J_fp32 - J_fp64|
+// ---- FP32 error band ----------------------------------------------
+// |J_fp32 - J_fp64| <= c0 + c1*sqrt(J) + c2*J for every hypothesis of an item, from the item's
+// own step length, heading excursion and tan magnitude.
+struct BandWin {       // window-level inputs, identical in every thread
+  float n, s2, s4;     // N, sum k^2, bound on sum ((k^2+k)/2)^2
+  float dmax;          // max |target increment|
+  float dabmax;        // max |T_A - T_B|
+  float imax;          // max |imu target|
+  float eps_tl;        // relative error of TL
+  float wpos, wimu;    // weight sums
+  float c2;            // J-proportional coefficient (already includes the safety factor)
+};
 struct Band {
   float c0, c1, c2;
   __device__ __forceinline__ float err(float J) const { return fmaf(c1, sqrtf(J), fmaf(c2, J, c0)); }
-  __device__ __forceinline__ float upper(float J) const { return J + err(J); }
-  __device__ __forceinline__ float lower(float J) const { return J - err(J); }
 };
 
-__device__ Band make_band(const SearchParams& p, int N, double dt, double v_seed, double tmax,
-                          double imax) {
-  const double u = 5.9604644775390625e-8;  // 2^-24
-  const double n = (double)N;
-  double Vmax = (v_seed > 0 ? v_seed : 0) + p.max_accel * n * dt;
-  double vdtm = Vmax * dt;
-  double eps_d = 4 * u * p.delta_max;
-  double eps_T = (1 + p.tan_max * p.tan_max) * eps_d * 1.05 + 8 * u * p.tan_max;
-  double eps_v = 6 * u * vdtm;
-  double dth_max = vdtm * p.tan_max / p.L;
-  double th_max = n * dth_max;
-  double g = vdtm * eps_T / p.L + eps_v * p.tan_max / p.L + 2 * u * dth_max + 2 * u * th_max;
-  double eps_trig = 4.76837158203125e-7 /* 2^-21 */ + 4 * u * th_max;
-  double Xmax = n * vdtm;
-  double a = vdtm * eps_trig + eps_v + 2 * u * Xmax;  // pose error grows by <= a + b*k per step
-  double b = vdtm * g;
-  double e = u * tmax;
-  double s2 = n * (n + 1) * (2 * n + 1) / 6;                    // sum k^2
-  double s4 = n * n * n * n * n / 5 + n * n * n * n / 2 + n * n * n / 3;  // >= sum k^4
-  double E2pos = 3 * (a * a * s2 + b * b * s4 + n * e * e);
-  double ei = 8 * u * kPi * (1 + th_max / kTwoPi) + u * imax;
-  double E2imu = 2 * (g * g * s2 + n * ei * ei);
-  double E2w = (p.w_vo + p.w_gps) * E2pos + p.w_imu * E2imu;
-  double c2 = 2.8284271247461903 * u * sqrt(n) + 4 * u * u * n + 2 * (n + 2) * u + 16 * u;
-  const double SF = 2.0;  // safety factor on the whole bound
-  Band bd;
-  bd.c0 = __double2float_ru(SF * 4 * E2w);
-  bd.c1 = __double2float_ru(SF * 2.8284271247461903 * sqrt(E2w));
-  bd.c2 = __double2float_ru(SF * c2);
-  return bd;
+__device__ __forceinline__ Band make_band(const BandWin& w, float vmax, float theta_tv, float tlmax) {
+  const float u = 5.9604644775390625e-8f;           // 2^-24
+  const float SF = 2.0f;                            // safety factor on the whole bound
+  const float dth = vmax * tlmax;                   // largest heading step
+  const float g = (w.eps_tl + u) * dth + u * theta_tv;        // heading error grows <= g per step
+  const float eps_trig = 4.76837158203125e-7f + 4.f * u * theta_tv;  // MUFU sin/cos, |x| <= theta_tv
+  const float q1 = vmax * (eps_trig + u) + 2.f * u * w.dmax + 2.f * u * w.dabmax;
+  const float q2 = vmax * g;
+  const float e2pos = 3.f * (q1 * q1 * w.s2 + q2 * q2 * w.s4);
+  const float ei = u * (w.imax + 3.1415927f) + (theta_tv * 0.15915494f + 1.f) * 1.75e-7f;
+  const float e2imu = 2.f * (g * g * w.s2 + w.n * ei * ei);
+  const float e2 = w.wpos * e2pos + w.wimu * e2imu;
+  Band b;
+  b.c0 = SF * 2.f * e2;
+  b.c1 = SF * 2.f * sqrtf(2.f * e2);
+  b.c2 = w.c2;
+  return b;
 }
 
 // ---- float64 cost of one hypothesis, one warp, one step per lane ---------------------------
@@ -177,63 +184,54 @@ __device__ double warp_cost64(const SearchParams& p, const WinInfo& wi, const do
   return J;
 }
 
-// ---- FP32 scan of one item: steering rate j, accelerations ic*C .. ic*C+C-1 -----------------
-template <int C, bool DUAL, bool IMU>
-__device__ __forceinline__ void scan_item(const SearchParams& p, const WinInfo& wi, int ic, int j,
-                                          const float2* __restrict__ fA,
-                                          const float2* __restrict__ fB,
+// ---- FP32 scan of one item: steering rate j, accelerations m0 .. m0+C-1 of the VD table ------
+struct ScanOut {
+  float J[kC];
+  float vmax, theta_tv, tlmax;   // inputs of the item's error band
+};
+
+template <bool DUAL, bool IMU>
+__device__ __forceinline__ void scan_item(int N, int gs, int vd_cols, int j, int m0,
+                                          const float* __restrict__ TL,
+                                          const float* __restrict__ VD,
+                                          const float2* __restrict__ Df,
+                                          const float2* __restrict__ Dab,
                                           const float* __restrict__ fI, float wA, float wB,
-                                          float (&Jt)[C]) {
-  const double kd = kDegToRad / p.ratio;            // steering-wheel degrees -> road-wheel rad
-  const float rdd = (float)(grid_rate(p.max_rate, j, p.gs) * wi.dt * kd);
-  const float dw = (float)(wi.s_seed * kd);
-  const float dmaxf = (float)p.delta_max;
-  const float vwdt = (float)(wi.v_seed * wi.dt);
-  const float invL = (float)(1.0 / p.L);
-  const float rad2deg = (float)(1.0 / kd);
-  const float wI = (float)p.w_imu;
-  const bool ksteer = p.k_steer != 0.0;
-  float adt2[C], th[C], x[C], y[C], JA[C], JB[C], JI[C];
+                                          float wI, float kJS, ScanOut& out) {
+  float th[kC], ex[kC], ey[kC], JA[kC], JB[kC], JI[kC];
 #pragma unroll
-  for (int c = 0; c < C; ++c) {
-    int i = ic * C + c;
-    i = i < p.gv ? i : p.gv - 1;
-    adt2[c] = (float)(grid_rate(p.max_accel, i, p.gv) * wi.dt * wi.dt);
-    th[c] = x[c] = y[c] = JA[c] = JB[c] = JI[c] = 0.f;
-  }
-  float JS = 0.f;
-  const int N = wi.n_steps;
-  const int off = p.target_offset;
+  for (int c = 0; c < kC; ++c) th[c] = ex[c] = ey[c] = JA[c] = JB[c] = JI[c] = 0.f;
+  float vmax = 0.f, tv = 0.f, tlmax = 0.f;
+  const float* tl = TL + j;
+  const float* vd = VD + m0;
+#pragma unroll 1
   for (int k = 1; k <= N; ++k) {
-    const float kf = (float)k;
-    float d = fmaf(rdd, kf, dw);
-    d = fminf(fmaxf(d, -dmaxf), dmaxf);
-    const float TL = tanf(d) * invL;
-    const float2 ta = fA[k - off];
-    float2 tb = make_float2(0.f, 0.f);
+    const float tlk = tl[(k - 1) * gs];
+    const float4 va = *reinterpret_cast<const float4*>(vd + (k - 1) * vd_cols);
+    const float4 vb = *reinterpret_cast<const float4*>(vd + (k - 1) * vd_cols + 4);
+    const float v[kC] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+    const float2 d = Df[k];
+    float2 dab = make_float2(0.f, 0.f);
     float ti = 0.f;
-    if (DUAL) tb = fB[k - off];
-    if (IMU) ti = fI[k - off];
-    if (ksteer) {
-      float sd = d * rad2deg;
-      JS = fmaf(sd, sd, JS);
-    }
+    if (DUAL) dab = Dab[k];
+    if (IMU) ti = fI[k];
+    // band statistics from the item's fastest hypothesis (VD is non-decreasing in i)
+    tv = fmaf(v[kC - 1], fabsf(tlk), tv);
+    tlmax = fmaxf(tlmax, fabsf(tlk));
+    vmax = fmaxf(vmax, v[kC - 1]);
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const float vdt = fmaxf(fmaf(adt2[c], kf, vwdt), 0.f);
-      th[c] = fmaf(vdt, TL, th[c]);
+    for (int c = 0; c < kC; ++c) {
+      th[c] = fmaf(v[c], tlk, th[c]);
       float sn, cs;
       __sincosf(th[c], &sn, &cs);
-      x[c] = fmaf(vdt, cs, x[c]);
-      y[c] = fmaf(vdt, sn, y[c]);
-      float ex = x[c] - ta.x, ey = y[c] - ta.y;
-      JA[c] = fmaf(ex, ex, JA[c]);
-      JA[c] = fmaf(ey, ey, JA[c]);
+      ex[c] = fmaf(v[c], cs, ex[c] - d.x);   // error recurrence: e_k = e_{k-1} - dT_k + v*cos
+      ey[c] = fmaf(v[c], sn, ey[c] - d.y);
+      JA[c] = fmaf(ex[c], ex[c], JA[c]);
+      JA[c] = fmaf(ey[c], ey[c], JA[c]);
       if (DUAL) {
-        ex = x[c] - tb.x;
-        ey = y[c] - tb.y;
-        JB[c] = fmaf(ex, ex, JB[c]);
-        JB[c] = fmaf(ey, ey, JB[c]);
+        const float bx = ex[c] + dab.x, by = ey[c] + dab.y;
+        JB[c] = fmaf(bx, bx, JB[c]);
+        JB[c] = fmaf(by, by, JB[c]);
       }
       if (IMU) {
         float e = th[c] - ti;
@@ -242,32 +240,37 @@ __device__ __forceinline__ void scan_item(const SearchParams& p, const WinInfo& 
       }
     }
   }
-  const float kS = ksteer ? (float)p.k_steer * JS : 0.f;
 #pragma unroll
-  for (int c = 0; c < C; ++c) {
-    float t = wA * JA[c] + kS;
+  for (int c = 0; c < kC; ++c) {
+    float t = fmaf(wA, JA[c], kJS);
     if (DUAL) t = fmaf(wB, JB[c], t);
     if (IMU) t = fmaf(wI, JI[c], t);
-    Jt[c] = t;
+    out.J[c] = t;
   }
+  out.vmax = vmax;
+  out.theta_tv = tv;
+  out.tlmax = tlmax;
 }
 
 // ---- the kernel -----------------------------------------------------------------------------
-template <int C, bool DUAL, bool IMU>
-__global__ void __launch_bounds__(256)
+template <bool DUAL, bool IMU>
+__global__ void __launch_bounds__(256, 2)
 vmvo_window_search_kernel(const SearchParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int P = p.maxp;
-  const SmemLayout lay(P);
+  const SmemLayout lay(P, p.gs, p.vd_cols);
   SmemHeader* hd = reinterpret_cast<SmemHeader*>(smem);
   float4* raw = reinterpret_cast<float4*>(smem + lay.off_raw);
   double* loc = reinterpret_cast<double*>(smem + lay.off_loc);
   double* loci = reinterpret_cast<double*>(smem + lay.off_loci);
   double* tgt = reinterpret_cast<double*>(smem + lay.off_tgt);
-  float2* fA = reinterpret_cast<float2*>(smem + lay.off_fa);
-  float2* fB = reinterpret_cast<float2*>(smem + lay.off_fb);
+  float2* Df = reinterpret_cast<float2*>(smem + lay.off_df);
+  float2* Dab = reinterpret_cast<float2*>(smem + lay.off_dab);
   float* fI = reinterpret_cast<float*>(smem + lay.off_fi);
   int* keep = reinterpret_cast<int*>(smem + lay.off_keep);
+  float* TL = reinterpret_cast<float*>(smem + lay.off_tl);
+  float* JS = reinterpret_cast<float*>(smem + lay.off_js);
+  float* VD = reinterpret_cast<float*>(smem + lay.off_vd);
   uint2* cand = reinterpret_cast<uint2*>(smem + lay.off_cand);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -277,17 +280,22 @@ vmvo_window_search_kernel(const SearchParams p) {
   const int sA = p.use_vo ? 0 : 1;
   const double wA64 = p.use_vo ? p.w_vo : p.w_gps;
   const double wB64 = p.w_gps;
-  const float wA = (float)wA64, wB = (float)wB64;
+  const float wA = (float)wA64, wB = (float)wB64, wI = (float)p.w_imu;
+  const bool ksteer = p.k_steer != 0.0;
+  const double kd = kDegToRad / p.ratio;   // steering-wheel degrees -> road-wheel radians
 
   auto issue_load = [&](long long w, int buf) {  // thread 0 only
     const long long start = p.win_start[w];
     int len = p.win_len[w];
     len = len < P ? len : P;
+    len = len > 0 ? len : 0;
     const unsigned bytes = (unsigned)len * 16u;
     const unsigned total = bytes * (unsigned)(p.load_vo + p.load_gps);
     mbar_arrive_expect_tx(&hd->mbar[buf], total);
-    if (p.load_vo) bulk_g2s(raw + (buf * 2 + 0) * P, p.vo + start, bytes, &hd->mbar[buf]);
-    if (p.load_gps) bulk_g2s(raw + (buf * 2 + 1) * P, p.gps + start, bytes, &hd->mbar[buf]);
+    if (bytes) {
+      if (p.load_vo) bulk_g2s(raw + (buf * 2 + 0) * P, p.vo + start, bytes, &hd->mbar[buf]);
+      if (p.load_gps) bulk_g2s(raw + (buf * 2 + 1) * P, p.gps + start, bytes, &hd->mbar[buf]);
+    }
   };
 
   if (tid == 0) {
@@ -331,24 +339,26 @@ vmvo_window_search_kernel(const SearchParams p) {
       continue;
     }
 
-    // ---- phase A: local frames (a7), seeds, decimation (a9), targets ----------------------
-    for (int s = 0; s < 2; ++s) {
-      if (!(s == 0 ? p.load_vo : p.load_gps)) continue;
-      const float4* rs = raw + (cur * 2 + s) * P;
-      const float4 p0 = rs[0];
-      const double th0 = (double)p0.z;
-      double sn, cs;
-      sincos(th0, &sn, &cs);
-      double* lx = loc + (s * 3 + 0) * P;
-      double* ly = loc + (s * 3 + 1) * P;
-      double* lt = loc + (s * 3 + 2) * P;
-      for (int m = tid; m < len; m += T) {
-        const float4 q = rs[m];
-        const double dx = dsub((double)q.x, (double)p0.x);
-        const double dy = dsub((double)q.y, (double)p0.y);
-        lx[m] = dadd(dmul(dx, cs), dmul(dy, sn));
-        ly[m] = dadd(dmul(-dx, sn), dmul(dy, cs));
-        lt[m] = dsub((double)q.z, th0);
+    // ---- phase A1: local frames (a7), one pose per thread ---------------------------------
+    if (tid < ((len + 31) & ~31)) {  // only the warps that own poses pay for sincos
+      for (int s = 0; s < 2; ++s) {
+        if (!(s == 0 ? p.load_vo : p.load_gps)) continue;
+        const float4* rs = raw + (cur * 2 + s) * P;
+        const float4 p0 = rs[0];
+        const double th0 = (double)p0.z;
+        double sn, cs;
+        sincos(th0, &sn, &cs);
+        double* lx = loc + (s * 3 + 0) * P;
+        double* ly = loc + (s * 3 + 1) * P;
+        double* lt = loc + (s * 3 + 2) * P;
+        for (int m = tid; m < len; m += T) {
+          const float4 q = rs[m];
+          const double dx = dsub((double)q.x, (double)p0.x);
+          const double dy = dsub((double)q.y, (double)p0.y);
+          lx[m] = dadd(dmul(dx, cs), dmul(dy, sn));
+          ly[m] = dadd(dmul(-dx, sn), dmul(dy, cs));
+          lt[m] = dsub((double)q.z, th0);
+        }
       }
     }
     if (IMU) {
@@ -357,124 +367,164 @@ vmvo_window_search_kernel(const SearchParams p) {
     }
     __syncthreads();
 
-    const float4* rp = raw + (cur * 2 + p.primary) * P;
+    // ---- phase A2 (warp 0): seeds, decimation (a9) ----------------------------------------
     const double* plx = loc + (p.primary * 3 + 0) * P;
     const double* ply = loc + (p.primary * 3 + 1) * P;
     const double* plt = loc + (p.primary * 3 + 2) * P;
-    double v_seed, s_seed;
-    if (p.seed_mode == VMVO_SEED_GIVEN) {
-      v_seed = p.seeds[2 * w];
-      s_seed = p.seeds[2 * w + 1];
-    } else {
-      v_seed = ddiv(dadd((double)rp[0].w, (double)rp[len - 1].w), 2.0);
-      s_seed = 0.0;
-      if (len >= 2 && dmul(v_seed, dt) > 1e-6) {
-        const double dth = remainder(dsub(plt[1], plt[0]), kTwoPi);
-        const double ang = atan(ddiv(dmul(p.L, dth), dmul(v_seed, dt)));
-        s_seed = dmul(dmul(ang, kRadToDeg), p.ratio);
-        s_seed = s_seed < -p.max_steer ? -p.max_steer : s_seed;
-        s_seed = s_seed > p.max_steer ? p.max_steer : s_seed;
-      }
-    }
-
-    if (p.target_mode == VMVO_TARGET_TRAVERSE) {
-      if (tid == 0) {  // sequential by definition (distance accumulator with reset)
-        const double D = dmul(v_seed, dt);
-        int cnt = 1;
-        keep[0] = 0;
-        double dist = 0.0;
-        for (int i = 1; i < len; ++i) {
-          const double ddx = dsub(plx[i], plx[i - 1]), ddy = dsub(ply[i], ply[i - 1]);
-          const double seg = sqrt(dadd(dmul(ddx, ddx), dmul(ddy, ddy)));
-          if (dadd(dist, seg) > D) {
-            keep[cnt++] = i - 1;
-            dist = seg;
-          } else {
-            dist = dadd(dist, seg);
-          }
+    if (warp == 0) {
+      const float4* rp = raw + (cur * 2 + p.primary) * P;
+      double v_seed, s_seed;
+      if (p.seed_mode == VMVO_SEED_GIVEN) {
+        v_seed = p.seeds[2 * w];
+        s_seed = p.seeds[2 * w + 1];
+      } else {
+        v_seed = ddiv(dadd((double)rp[0].w, (double)rp[len - 1].w), 2.0);
+        s_seed = 0.0;
+        if (len >= 2 && dmul(v_seed, dt) > 1e-6) {
+          const double dth = remainder(dsub(plt[1], plt[0]), kTwoPi);
+          const double ang = atan(ddiv(dmul(p.L, dth), dmul(v_seed, dt)));
+          s_seed = dmul(dmul(ang, kRadToDeg), p.ratio);
+          s_seed = s_seed < -p.max_steer ? -p.max_steer : s_seed;
+          s_seed = s_seed > p.max_steer ? p.max_steer : s_seed;
         }
-        hd->wi.n_targets = cnt;
       }
-    } else {
-      for (int m = tid; m < len; m += T) keep[m] = m;
-      if (tid == 0) hd->wi.n_targets = len;
+      int n_targets = len;
+      if (p.target_mode == VMVO_TARGET_TRAVERSE) {
+        if (lane == 0) {  // sequential by definition (distance accumulator with reset)
+          const double D = dmul(v_seed, dt);
+          int cnt = 1;
+          keep[0] = 0;
+          double dist = 0.0;
+          for (int i = 1; i < len; ++i) {
+            const double ddx = dsub(plx[i], plx[i - 1]), ddy = dsub(ply[i], ply[i - 1]);
+            const double seg = sqrt(dadd(dmul(ddx, ddx), dmul(ddy, ddy)));
+            if (dadd(dist, seg) > D) {
+              keep[cnt++] = i - 1;
+              dist = seg;
+            } else {
+              dist = dadd(dist, seg);
+            }
+          }
+          n_targets = cnt;
+        }
+        n_targets = __shfl_sync(FULL, n_targets, 0);
+      }
+      if (lane == 0) {
+        hd->wi.v_seed = v_seed;
+        hd->wi.s_seed = s_seed;
+        hd->wi.dt = dt;
+        hd->wi.n_targets = n_targets;
+        hd->wi.n_steps = n_targets > 1 ? n_targets - 1 : 0;
+      }
     }
     __syncthreads();
 
     const int n_targets = hd->wi.n_targets;
-    const int N = n_targets - 1;
+    const int N = hd->wi.n_steps;
+    const double v_seed = hd->wi.v_seed, s_seed = hd->wi.s_seed;
+    const int off = p.target_offset;
+    const bool traverse = p.target_mode == VMVO_TARGET_TRAVERSE;
+
+    // ---- phase A3: targets in float64, FP32 increments for the scan, finiteness -------------
     bool finite = isfinite(v_seed) && isfinite(s_seed) && isfinite(dt);
-    float tmax = 0.f, imax = 0.f;
+    float dmax = 0.f, dabmax = 0.f, imax = 0.f;
     {
       const double* aX = loc + (sA * 3 + 0) * P;
       const double* aY = loc + (sA * 3 + 1) * P;
       const double* bX = loc + (1 * 3 + 0) * P;
       const double* bY = loc + (1 * 3 + 1) * P;
       for (int q = tid; q < n_targets; q += T) {
-        const int m = keep[q];
+        const int m = traverse ? keep[q] : q;
         const double ax = aX[m], ay = aY[m];
         tgt[q] = ax;
         tgt[P + q] = ay;
-        fA[q] = make_float2((float)ax, (float)ay);
         finite = finite && isfinite(ax) && isfinite(ay);
-        tmax = fmaxf(tmax, fmaxf(fabsf((float)ax), fabsf((float)ay)));
         if (DUAL) {
           const double bx = bX[m], by = bY[m];
           tgt[2 * P + q] = bx;
           tgt[3 * P + q] = by;
-          fB[q] = make_float2((float)bx, (float)by);
           finite = finite && isfinite(bx) && isfinite(by);
-          tmax = fmaxf(tmax, fmaxf(fabsf((float)bx), fabsf((float)by)));
         }
         if (IMU) {
           const double yi = loci[m];
           tgt[4 * P + q] = yi;
-          fI[q] = (float)yi;
           finite = finite && isfinite(yi);
-          imax = fmaxf(imax, fabsf((float)yi));
+        }
+        // step k = q + off compares against target q; its increment needs target q - 1
+        const int k = q + off;
+        if (k >= 1 && k <= N) {
+          const int mp = (q >= 1) ? (traverse ? keep[q - 1] : q - 1) : -1;
+          const double px = (k >= 2) ? aX[mp] : 0.0, py = (k >= 2) ? aY[mp] : 0.0;
+          const float dx = (float)dsub(ax, px), dy = (float)dsub(ay, py);
+          Df[k] = make_float2(dx, dy);
+          dmax = fmaxf(dmax, fmaxf(fabsf(dx), fabsf(dy)));
+          if (DUAL) {
+            const float ex = (float)dsub(ax, bX[m]), ey = (float)dsub(ay, bY[m]);
+            Dab[k] = make_float2(ex, ey);
+            dabmax = fmaxf(dabmax, fmaxf(fabsf(ex), fabsf(ey)));
+          }
+          if (IMU) {
+            const float yi = (float)loci[m];
+            fI[k] = yi;
+            imax = fmaxf(imax, fabsf(yi));
+          }
+        }
+      }
+    }
+    // ---- phase A4: TL[k][j] = tan(delta_k(j)) / L and the steering penalty per j -------------
+    if (N > 0) {
+      const float invL = (float)(1.0 / p.L);
+      for (int e = tid; e < N * p.gs; e += T) {
+        const int k = e / p.gs + 1, j = e - (k - 1) * p.gs;
+        double s = dadd(s_seed, dmul(grid_rate(p.max_rate, j, p.gs), dmul((double)k, dt)));
+        s = s < -p.max_steer ? -p.max_steer : s;
+        s = s > p.max_steer ? p.max_steer : s;
+        TL[e] = tanf((float)(s * kd)) * invL;
+      }
+      if (ksteer) {
+        for (int j = tid; j < p.gs; j += T) {
+          const double r = grid_rate(p.max_rate, j, p.gs);
+          double acc = 0.0;
+          for (int k = 1; k <= N; ++k) {
+            double s = dadd(s_seed, dmul(r, dmul((double)k, dt)));
+            s = s < -p.max_steer ? -p.max_steer : s;
+            s = s > p.max_steer ? p.max_steer : s;
+            acc += s * s;
+          }
+          JS[j] = (float)(p.k_steer * acc);
         }
       }
     }
     {
-      // block max of |target| (for the band) and the non-finite flag
-      float wm = tmax, wi_ = imax;
+      // block max of the band inputs
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
-        wm = fmaxf(wm, __shfl_xor_sync(FULL, wm, o));
-        wi_ = fmaxf(wi_, __shfl_xor_sync(FULL, wi_, o));
+        dmax = fmaxf(dmax, __shfl_xor_sync(FULL, dmax, o));
+        dabmax = fmaxf(dabmax, __shfl_xor_sync(FULL, dabmax, o));
+        imax = fmaxf(imax, __shfl_xor_sync(FULL, imax, o));
       }
       if (lane == 0) {
-        hd->red[warp] = wm;
-        hd->red[16 + warp] = wi_;
+        hd->red[warp] = dmax;
+        hd->red[8 + warp] = dabmax;
+        hd->red[16 + warp] = imax;
       }
     }
     const int bad = __syncthreads_or(finite ? 0 : 1);
-    {
-      float wm = 0.f, wi_ = 0.f;
-      for (int q = 0; q < NW; ++q) {
-        wm = fmaxf(wm, hd->red[q]);
-        wi_ = fmaxf(wi_, hd->red[16 + q]);
-      }
-      tmax = wm;
-      imax = wi_;
+    dmax = dabmax = imax = 0.f;
+    for (int q = 0; q < NW; ++q) {
+      dmax = fmaxf(dmax, hd->red[q]);
+      dabmax = fmaxf(dabmax, hd->red[8 + q]);
+      imax = fmaxf(imax, hd->red[16 + q]);
     }
-    if (tid == 0) {
-      hd->wi.v_seed = v_seed;
-      hd->wi.s_seed = s_seed;
-      hd->wi.dt = dt;
-      hd->wi.start = start;
-      hd->wi.len = len;
-      hd->wi.n_steps = N > 0 ? N : 0;
-      hd->wi.status = (N <= 0 ? VMVO_WIN_EMPTY : 0) | (bad ? VMVO_WIN_NONFINITE : 0);
-    }
-    __syncthreads();  // wi visible; red[] free for reuse
-    const WinInfo wi = hd->wi;
-    res.n_steps = wi.n_steps;
-    res.status = wi.status;
+    const int status = (N <= 0 ? VMVO_WIN_EMPTY : 0) | (bad ? VMVO_WIN_NONFINITE : 0);
+    WinInfo wi = hd->wi;
+    wi.status = status;
+    res.n_steps = N;
+    res.status = status;
     res.v_seed = v_seed;
     res.s_seed = s_seed;
 
-    if (wi.status & VMVO_WIN_EMPTY) {
+    if (status & VMVO_WIN_EMPTY) {
       if (tid == 0) p.results[w] = res;
       __syncthreads();
       continue;
@@ -485,13 +535,28 @@ vmvo_window_search_kernel(const SearchParams p) {
     Pose<double> best_first{CUDART_NAN, CUDART_NAN, CUDART_NAN};
     int n_rescored = 0;
 
-    if (wi.status & VMVO_WIN_NONFINITE) {
+    if (status & VMVO_WIN_NONFINITE) {
       // every hypothesis costs NaN or Inf alike: np.argmin returns index 0
       best_h = 0;
       best_cost = CUDART_NAN;
     } else {
       // ---- phase B: FP32 scan of the whole grid, candidates within the error band -------
-      const Band band = make_band(p, N, dt, v_seed, (double)tmax, (double)imax);
+      BandWin bw;
+      {
+        const float u = 5.9604644775390625e-8f;
+        const float n = (float)N;
+        bw.n = n;
+        bw.s2 = n * (n + 1.f) * (2.f * n + 1.f) * (1.f / 6.f);
+        const float n2 = n + 2.f;
+        bw.s4 = 0.05f * n2 * n2 * n2 * n2 * n2;
+        bw.dmax = dmax;
+        bw.dabmax = dabmax;
+        bw.imax = imax;
+        bw.eps_tl = (10.f + (float)p.kappa) * u;
+        bw.wpos = wA + (DUAL ? wB : 0.f);
+        bw.wimu = IMU ? wI : 0.f;
+        bw.c2 = 2.0f * (2.f * u * sqrtf(24.f * bw.s2) + 24.f * u * u * bw.s2 + 2.f * (n + 2.f) * u + 16.f * u);
+      }
       float U = CUDART_INF_F;          // upper bound on the true minimum cost
       float Uw = CUDART_INF_F;         // this warp's tightened copy (after float64 re-scores)
 
@@ -499,8 +564,7 @@ vmvo_window_search_kernel(const SearchParams p) {
         const int count = hd->count < kCandCap ? hd->count : kCandCap;
         for (int e = warp; e < count; e += NW) {
           const uint2 ce = cand[e];
-          const float j32 = __uint_as_float(ce.y);
-          if (band.lower(j32) > fminf(U, Uw)) continue;  // warp-uniform
+          if (__uint_as_float(ce.y) > fminf(U, Uw)) continue;  // warp-uniform; NaN stays in
           const int h = (int)ce.x;
           Pose<double> first;
           const double c64 = warp_cost64<DUAL, IMU>(p, wi, tgt, P, h, lane, wA64, wB64, &first);
@@ -520,39 +584,62 @@ vmvo_window_search_kernel(const SearchParams p) {
 
       const int n_pass = (p.n_items + T - 1) / T;
       for (int pass = 0; pass < n_pass; ++pass) {
+        // VD[k][m] = V_k(ic0*C + m) * dt for the accelerations this pass touches
+        const int ic0 = (pass * T) / p.gs;
+        for (int e = tid; e < N * p.vd_cols; e += T) {
+          const int k = e / p.vd_cols + 1, m = e - (k - 1) * p.vd_cols;
+          int i = ic0 * kC + m;
+          i = i < p.gv ? i : p.gv - 1;
+          const double vv = dadd(v_seed, dmul(grid_rate(p.max_accel, i, p.gv), dmul((double)k, dt)));
+          VD[e] = (float)((vv > 0.0 ? vv : 0.0) * dt);
+        }
+        __syncthreads();
         const int q = pass * T + tid;
-        float Jt[C];
+        ScanOut so;
         int ic = 0, j = 0;
         unsigned valid = 0;
+        Band band{0.f, 0.f, 0.f};
         if (q < p.n_items) {
           ic = q / p.gs;
           j = q - ic * p.gs;
-          scan_item<C, DUAL, IMU>(p, wi, ic, j, fA, fB, fI, wA, wB, Jt);
+          scan_item<DUAL, IMU>(N, p.gs, p.vd_cols, j, (ic - ic0) * kC, TL, VD, Df, Dab, fI, wA, wB, wI,
+                               ksteer ? JS[j] : 0.f, so);
+          band = make_band(bw, so.vmax, so.theta_tv, so.tlmax);
 #pragma unroll
-          for (int c = 0; c < C; ++c)
-            if (ic * C + c < p.gv) valid |= 1u << c;
+          for (int c = 0; c < kC; ++c)
+            if (ic * kC + c < p.gv) valid |= 1u << c;
+          if (p.dbg_cost) {
+#pragma unroll
+            for (int c = 0; c < kC; ++c)
+              if ((valid >> c) & 1u) {
+                const long long o = w * (long long)p.gv * p.gs + (long long)(ic * kC + c) * p.gs + j;
+                p.dbg_cost[o] = so.J[c];
+                p.dbg_err[o] = band.err(so.J[c]);
+              }
+          }
         }
         float m = CUDART_INF_F;
 #pragma unroll
-        for (int c = 0; c < C; ++c)
-          if ((valid >> c) & 1u) m = fminf(m, Jt[c]);  // fminf drops NaN; NaN stays a candidate below
-        m = warp_min_f32_nonneg(m);
+        for (int c = 0; c < kC; ++c)
+          if ((valid >> c) & 1u) m = fminf(m, so.J[c] + band.err(so.J[c]));  // fminf drops NaN
+        m = warp_min_f32_nonneg(fmaxf(m, 0.f));
         if (lane == 0) hd->red[warp] = m;
         __syncthreads();
         float bm = lane < NW ? hd->red[lane] : CUDART_INF_F;
         bm = warp_min_f32_nonneg(bm);
-        U = fminf(U, band.upper(bm));
+        U = fminf(U, bm);
         unsigned pend = 0;
 #pragma unroll
-        for (int c = 0; c < C; ++c)
-          if (((valid >> c) & 1u) && !(band.lower(Jt[c]) > U)) pend |= 1u << c;
+        for (int c = 0; c < kC; ++c)
+          if (((valid >> c) & 1u) && !(so.J[c] - band.err(so.J[c]) > U)) pend |= 1u << c;
         for (;;) {
 #pragma unroll
-          for (int c = 0; c < C; ++c) {
+          for (int c = 0; c < kC; ++c) {
             if ((pend >> c) & 1u) {
               const int slot = atomicAdd(&hd->count, 1);
               if (slot < kCandCap) {
-                cand[slot] = make_uint2((unsigned)((ic * C + c) * p.gs + j), __float_as_uint(Jt[c]));
+                cand[slot] = make_uint2((unsigned)((ic * kC + c) * p.gs + j),
+                                        __float_as_uint(so.J[c] - band.err(so.J[c])));
                 pend &= ~(1u << c);
               }
             }
@@ -576,23 +663,23 @@ vmvo_window_search_kernel(const SearchParams p) {
     }
     __syncthreads();
     if (tid == 0) {
-      int bw = -1;
+      int bwi = -1;
       int total = 0;
       for (int q = 0; q < NW; ++q) {
         total += hd->nres[q];
         if (hd->bh[q] < 0) continue;
-        if (bw < 0 || hd->bcost[q] < hd->bcost[bw] ||
-            (hd->bcost[q] == hd->bcost[bw] && hd->bh[q] < hd->bh[bw]))
-          bw = q;
+        if (bwi < 0 || hd->bcost[q] < hd->bcost[bwi] ||
+            (hd->bcost[q] == hd->bcost[bwi] && hd->bh[q] < hd->bh[bwi]))
+          bwi = q;
       }
-      if (wi.status & VMVO_WIN_NONFINITE) bw = 0;
+      if (status & VMVO_WIN_NONFINITE) bwi = 0;
       res.n_rescored = total;
-      if (bw >= 0) {
-        res.best_idx = hd->bh[bw];
-        res.best_cost = hd->bcost[bw];
-        res.x1 = hd->bpose[bw][0];
-        res.y1 = hd->bpose[bw][1];
-        res.theta1 = hd->bpose[bw][2];
+      if (bwi >= 0) {
+        res.best_idx = hd->bh[bwi];
+        res.best_cost = hd->bcost[bwi];
+        res.x1 = hd->bpose[bwi][0];
+        res.y1 = hd->bpose[bwi][1];
+        res.theta1 = hd->bpose[bwi][2];
       }
       hd->winner = res.best_idx;
       p.results[w] = res;
@@ -605,7 +692,7 @@ vmvo_window_search_kernel(const SearchParams p) {
         GridCtl g{wi.v_seed, wi.s_seed, wi.dt, grid_rate(p.max_accel, i, p.gv),
                   grid_rate(p.max_rate, j, p.gs), p.max_steer};
         Pose<double> carry{0.0, 0.0, 0.0};
-        const bool nonfinite = (wi.status & VMVO_WIN_NONFINITE) != 0;
+        const bool nonfinite = (status & VMVO_WIN_NONFINITE) != 0;
         for (int base = 0; base < N; base += 32) {
           const int k = base + lane + 1;
           const bool active = k <= N;
@@ -630,10 +717,14 @@ vmvo_window_search_kernel(const SearchParams p) {
   }
 }
 
-template <int C, bool DUAL, bool IMU>
+template <bool DUAL, bool IMU>
 static int launch_search(vmvo_ctx* ctx, const SearchParams& p, int threads, cudaStream_t st) {
-  auto kern = vmvo_window_search_kernel<C, DUAL, IMU>;
-  const SmemLayout lay(p.maxp);
+  auto kern = vmvo_window_search_kernel<DUAL, IMU>;
+  const SmemLayout lay(p.maxp, p.gs, p.vd_cols);
+  if (lay.total > 200 * 1024)
+    return fail(ctx, VMVO_ERR_UNSUPPORTED,
+                "window tables need %d bytes of shared memory (max_window_poses %d x grid_s %d): "
+                "reduce max_window_poses or grid_s", lay.total, p.maxp, p.gs);
   VMVO_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total));
   int per_sm = 0;
   VMVO_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, lay.total));
@@ -644,17 +735,13 @@ static int launch_search(vmvo_ctx* ctx, const SearchParams& p, int threads, cuda
   return check_launch(ctx, "vmvo_window_search_kernel");
 }
 
-}  // namespace vmvo
-
-using namespace vmvo;
-
-extern "C" int vmvo_grid_search_f32(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n_windows,
-                                    const int64_t* d_win_start, const int32_t* d_win_len,
-                                    const int32_t* d_win_drive, const double* d_dt_per_drive,
-                                    const float* d_vo, const float* d_gps, const float* d_imu,
-                                    const double* d_seeds, vmvo_window_result* d_results,
-                                    double* d_out_poses, double* d_out_steer, double* d_out_vel,
-                                    int32_t out_stride, void* stream) {
+static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n_windows,
+                            const int64_t* d_win_start, const int32_t* d_win_len,
+                            const int32_t* d_win_drive, const double* d_dt_per_drive,
+                            const float* d_vo, const float* d_gps, const float* d_imu,
+                            const double* d_seeds, vmvo_window_result* d_results,
+                            double* d_out_poses, double* d_out_steer, double* d_out_vel,
+                            int32_t out_stride, float* d_dbg_cost, float* d_dbg_err, void* stream) {
   if (!ctx) return VMVO_ERR_BAD_ARG;
   int rc = validate_cfg(ctx, cfg);
   if (rc) return rc;
@@ -664,7 +751,7 @@ extern "C" int vmvo_grid_search_f32(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, i
     return fail(ctx, VMVO_ERR_BAD_ARG, "NULL window plan / dt / result pointer");
   if (cfg->seed_mode == VMVO_SEED_CHAINED)
     return fail(ctx, VMVO_ERR_UNSUPPORTED,
-                "seed_mode chained serialises the windows of a drive; use vmvo_grid_search_chained_f32");
+                "seed_mode chained serialises the windows of a drive and is not built yet");
   if (cfg->seed_mode == VMVO_SEED_GIVEN && !d_seeds)
     return fail(ctx, VMVO_ERR_BAD_ARG, "seed_mode given needs d_seeds");
   const bool use_vo = cfg->w_vo != 0, use_gps = cfg->w_gps != 0, use_imu = cfg->w_imu != 0;
@@ -679,13 +766,20 @@ extern "C" int vmvo_grid_search_f32(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, i
     return fail(ctx, VMVO_ERR_BAD_ARG, "pose streams must be 16-byte aligned");
   if ((d_out_poses || d_out_steer || d_out_vel) && out_stride < 1)
     return fail(ctx, VMVO_ERR_BAD_ARG, "out_stride < 1");
+  if ((d_dbg_cost == nullptr) != (d_dbg_err == nullptr))
+    return fail(ctx, VMVO_ERR_BAD_ARG, "debug outputs come in pairs");
 
-  const int C = cfg->grid_v >= 8 ? 8 : 4;
   SearchParams p;
   p.gv = cfg->grid_v;
   p.gs = cfg->grid_s;
-  p.n_ic = (p.gv + C - 1) / C;
+  p.n_ic = (p.gv + kC - 1) / kC;
   p.n_items = p.n_ic * p.gs;
+  int threads = ((p.n_items + 31) / 32) * 32;
+  threads = threads < 64 ? 64 : (threads > 256 ? 256 : threads);
+  // accelerations one pass can touch: items [pass*T, pass*T + T) span at most this many chunks
+  int chunks = (threads + p.gs - 1) / p.gs + 1;
+  if (chunks > p.n_ic) chunks = p.n_ic;
+  p.vd_cols = chunks * kC;
   p.target_mode = cfg->target_mode;
   p.target_offset = cfg->target_offset;
   p.seed_mode = cfg->seed_mode;
@@ -705,7 +799,8 @@ extern "C" int vmvo_grid_search_f32(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, i
   p.max_accel = cfg->max_accel;
   p.max_rate = cfg->max_steer_rate;
   p.delta_max = cfg->max_steer * kDegToRad / cfg->steering_ratio;
-  p.tan_max = tan(p.delta_max);
+  p.kappa = 2 * p.delta_max / sin(2 * p.delta_max);
+  if (!(p.kappa > 0) || p.kappa > 64) p.kappa = 64;
   p.win_start = (const long long*)d_win_start;
   p.win_len = d_win_len;
   p.win_drive = d_win_drive;
@@ -720,6 +815,8 @@ extern "C" int vmvo_grid_search_f32(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, i
   p.out_vel = d_out_vel;
   p.out_stride = out_stride;
   p.n_windows = n_windows;
+  p.dbg_cost = d_dbg_cost;
+  p.dbg_err = d_dbg_err;
 
   cudaStream_t st = (cudaStream_t)stream;
   VMVO_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -728,14 +825,37 @@ extern "C" int vmvo_grid_search_f32(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, i
   VMVO_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
   p.work_counter = counter;
 
-  int threads = ((p.n_items + 31) / 32) * 32;
-  threads = threads < 64 ? 64 : (threads > 256 ? 256 : threads);
   const bool dual = use_vo && use_gps;
-#define VMVO_LAUNCH(CC)                                                                   \
-  (dual ? (use_imu ? launch_search<CC, true, true>(ctx, p, threads, st)                   \
-                   : launch_search<CC, true, false>(ctx, p, threads, st))                 \
-        : (use_imu ? launch_search<CC, false, true>(ctx, p, threads, st)                  \
-                   : launch_search<CC, false, false>(ctx, p, threads, st)))
-  return C == 8 ? VMVO_LAUNCH(8) : VMVO_LAUNCH(4);
-#undef VMVO_LAUNCH
+  if (dual) return use_imu ? launch_search<true, true>(ctx, p, threads, st)
+                           : launch_search<true, false>(ctx, p, threads, st);
+  return use_imu ? launch_search<false, true>(ctx, p, threads, st)
+                 : launch_search<false, false>(ctx, p, threads, st);
+}
+
+}  // namespace vmvo
+
+using namespace vmvo;
+
+extern "C" int vmvo_grid_search_f32(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n_windows,
+                                    const int64_t* d_win_start, const int32_t* d_win_len,
+                                    const int32_t* d_win_drive, const double* d_dt_per_drive,
+                                    const float* d_vo, const float* d_gps, const float* d_imu,
+                                    const double* d_seeds, vmvo_window_result* d_results,
+                                    double* d_out_poses, double* d_out_steer, double* d_out_vel,
+                                    int32_t out_stride, void* stream) {
+  return grid_search_impl(ctx, cfg, n_windows, d_win_start, d_win_len, d_win_drive, d_dt_per_drive,
+                          d_vo, d_gps, d_imu, d_seeds, d_results, d_out_poses, d_out_steer, d_out_vel,
+                          out_stride, nullptr, nullptr, stream);
+}
+
+extern "C" int vmvo_grid_search_debug_f32(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n_windows,
+                                          const int64_t* d_win_start, const int32_t* d_win_len,
+                                          const int32_t* d_win_drive, const double* d_dt_per_drive,
+                                          const float* d_vo, const float* d_gps, const float* d_imu,
+                                          const double* d_seeds, vmvo_window_result* d_results,
+                                          float* d_scan_cost, float* d_scan_err, void* stream) {
+  if (!d_scan_cost || !d_scan_err) return fail(ctx, VMVO_ERR_BAD_ARG, "debug outputs are NULL");
+  return grid_search_impl(ctx, cfg, n_windows, d_win_start, d_win_len, d_win_drive, d_dt_per_drive,
+                          d_vo, d_gps, d_imu, d_seeds, d_results, nullptr, nullptr, nullptr, 0,
+                          d_scan_cost, d_scan_err, stream);
 }

@@ -232,6 +232,25 @@ def grid_search(cfg: SearchConfig, drives: DriveSet, plan: WindowPlan,
     return so
 
 
+def grid_search_debug(cfg: SearchConfig, drives: DriveSet, plan: WindowPlan,
+                      seeds: Optional[torch.Tensor] = None):
+    """Test hook (``vmvo_grid_search_debug_f32``): records plus, for EVERY hypothesis, the FP32
+    scan cost and the width of its error band, each float32 [n_windows, grid_v * grid_s]."""
+    ctx = _lib.context(drives.device.index)
+    c = cfg.to_c()
+    n, dev = plan.n_windows, drives.device
+    results = torch.empty((n, 64), dtype=torch.uint8, device=dev)
+    cost = torch.full((n, cfg.grid_v * cfg.grid_s), float("nan"), dtype=torch.float32, device=dev)
+    err = torch.full_like(cost, float("nan"))
+    d_seeds = None if seeds is None else _as_dev(seeds, torch.float64, dev)
+    ctx.check(ctx.lib.vmvo_grid_search_debug_f32(
+        ctx.handle, C.byref(c), n, _lib.ptr(plan.win_start), _lib.ptr(plan.win_len),
+        _lib.ptr(plan.win_drive), _lib.ptr(drives.dt), _lib.ptr(drives.vo), _lib.ptr(drives.gps),
+        _lib.ptr(drives.imu), _lib.ptr(d_seeds), _lib.ptr(results), _lib.ptr(cost), _lib.ptr(err),
+        _lib.stream_ptr(dev)), "vmvo_grid_search_debug_f32")
+    return SearchOutput(results=results), cost, err
+
+
 def write_back(cfg: SearchConfig, drives: DriveSet, plan: WindowPlan, results: torch.Tensor,
                blend_gps: bool = True) -> torch.Tensor:
     """a12: float64 [4, F] = x, y, theta, velocity (optimize_trajectory_v2.py:32-33,122-137)."""
