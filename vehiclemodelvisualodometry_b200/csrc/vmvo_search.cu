@@ -6,12 +6,14 @@
 // Replaces mpc_run (vmvo/utils/mpc.py:14-122) and the per-window preparation of
 // optimize_trajectory (vmvo/scripts/optimize_trajectory_v2.py:49-96) of the reference.
 //
-// Work decomposition: one CTA works on one window at a time and pulls
-// windows from a global queue (persistent grid).  Per window the CTA builds two small tables
-// in shared memory -- TL[k][j] = tan(delta_k(j))/L and VD[k][i] = V_k(i)*dt -- so the scan's
-// inner loop is, per hypothesis-step: 1 FFMA (heading), sin+cos on the SFU, 4 FP32 ops for
-// the position error recurrence and 2 FFMA for the cost.  A thread owns one steering rate j
-// and C = 8 consecutive accelerations.
+// Work decomposition: a TEAM of 1, 2, 4 or 8 warps works on one window
+// at a time and pulls windows from a global queue (persistent grid, 8 warps per CTA, teams
+// synchronise on their own named barrier -- a one-warp team needs no barrier at all, so small
+// grids run one window per warp).  Per window the team builds two small tables in shared
+// memory -- TL[k][j] = tan(delta_k(j))/L and VD[k][i] = V_k(i)*dt -- so the scan's inner loop
+// is, per hypothesis-step: 1 FFMA (heading), sin+cos on the SFU, 4 FP32 ops for the position
+// error recurrence and 2 FFMA for the cost.  A thread owns one steering rate j and C = 8
+// consecutive accelerations per pass.
 #include "vmvo_device.cuh"
 #include "vmvo_internal.h"
 
@@ -20,8 +22,10 @@
 namespace vmvo {
 
 constexpr int kC = 8;            // hypotheses (consecutive accelerations) per thread
-constexpr int kCandCap = 1024;   // candidate list entries per CTA (flushed when full)
-constexpr int kMaxWarps = 8;     // CTA size <= 256 threads
+constexpr int kCandPerWarp = 128;  // candidate list entries per team warp (flushed when full)
+constexpr int kMaxWarps = 8;       // warps per CTA and largest team
+constexpr int kCtaThreads = 32 * kMaxWarps;
+constexpr int kHeaderBytes = 640;
 
 struct SearchParams {
   int gv, gs;
@@ -32,6 +36,7 @@ struct SearchParams {
   int use_vo, use_gps;   // position terms with non-zero weight
   int load_vo, load_gps; // streams staged into shared memory
   int vd_cols;           // columns of the VD table (accelerations covered by one pass)
+  int team_warps;        // warps per team (1, 2, 4 or 8)
   double w_vo, w_gps, w_imu, k_steer;
   double L, ratio, max_steer, max_accel, max_rate;
   double delta_max, kappa;     // kappa = 2*delta_max / sin(2*delta_max): tan's condition number
@@ -64,24 +69,26 @@ struct WinInfo {
 struct SmemLayout {
   int off_raw, off_loc, off_loci, off_tgt, off_df, off_dab, off_fi, off_keep, off_tl, off_js,
       off_vd, off_cand, total;
-  __host__ __device__ SmemLayout(int P, int gs, int vd_cols) {
-    int o = 1024;                        // fixed header: barriers, window ids, reductions
-    off_raw = o;  o += 2 * 2 * P * 16;   // float4 raw[2 buffers][2 streams][P]
-    off_loc = o;  o += 2 * 3 * P * 8;    // double loc[2 streams][3][P]  (lx, ly, lth)
-    off_loci = o; o += P * 8;            // double imu yaw relative to the window start
-    off_tgt = o;  o += 5 * P * 8;        // double tAx, tAy, tBx, tBy, tI
-    off_df = o;   o += P * 8;            // float2 D[k]   = T_A[k-off] - T_A[k-1-off]
-    off_dab = o;  o += P * 8;            // float2 DAB[k] = T_A[k-off] - T_B[k-off]
-    off_fi = o;   o += P * 4;            // float  imu target per step
-    off_keep = o; o += P * 4;            // int keep
+  // P poses per window, n_streams pose streams staged, optional terms only when configured
+  __host__ __device__ SmemLayout(int P, int gs, int vd_cols, int team_warps, int n_streams,
+                                 bool dual, bool imu, bool traverse) {
+    int o = kHeaderBytes;                       // barriers, window ids, reductions
+    off_raw = o;  o += 2 * n_streams * P * 16;  // float4 raw[2 buffers][streams][P]
+    off_loc = o;  o += n_streams * 3 * P * 8;   // double loc[streams][3][P]  (lx, ly, lth)
+    off_loci = o; o += imu ? P * 8 : 0;         // double imu yaw relative to the window start
+    off_tgt = o;  o += (2 + (dual ? 2 : 0) + (imu ? 1 : 0)) * P * 8;  // tAx, tAy, [tBx, tBy], [tI]
+    off_df = o;   o += P * 8;                   // float2 D[k]   = T_A[k-off] - T_A[k-1-off]
+    off_dab = o;  o += dual ? P * 8 : 0;        // float2 DAB[k] = T_A[k-off] - T_B[k-off]
+    off_fi = o;   o += imu ? P * 4 : 0;         // float  imu target per step
+    off_keep = o; o += traverse ? P * 4 : 0;    // int keep
     o = (o + 15) & ~15;
-    off_tl = o;   o += P * gs * 4;       // float TL[k][j]
-    off_js = o;   o += ((gs + 3) & ~3) * 4;  // float sum_k S_k(j)^2 (steering penalty)
+    off_tl = o;   o += P * gs * 4;              // float TL[k][j]
+    off_js = o;   o += ((gs + 3) & ~3) * 4;     // float K * sum_k S_k(j)^2 (steering penalty)
     o = (o + 15) & ~15;
-    off_vd = o;   o += P * vd_cols * 4;  // float VD[k][m]
+    off_vd = o;   o += P * vd_cols * 4;         // float VD[k][m]
     o = (o + 15) & ~15;
-    off_cand = o; o += kCandCap * 8;     // uint2 (hypothesis, float lower-bound bits)
-    total = o;
+    off_cand = o; o += kCandPerWarp * team_warps * 8;  // uint2 (hypothesis, lower-bound bits)
+    total = (o + 127) & ~127;
   }
 };
 
@@ -97,7 +104,31 @@ struct SmemHeader {
   int count;
   int winner;
 };
-static_assert(sizeof(SmemHeader) <= 1024, "header too large");
+static_assert(sizeof(SmemHeader) <= kHeaderBytes, "header too large");
+
+// ---- team barriers: named barrier 1 + team index; a one-warp team only needs __syncwarp ------
+struct Team {
+  int warps, threads, id;
+  __device__ __forceinline__ void sync() const {
+    if (warps == 1) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(id + 1), "r"(threads) : "memory");
+  }
+  __device__ __forceinline__ int any(int pred) const {
+    if (warps == 1) return __any_sync(FULL, pred);
+    int r;
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        "setp.ne.u32 q, %3, 0;\n"
+        "bar.red.or.pred p, %1, %2, q;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(r)
+        : "r"(id + 1), "r"(threads), "r"(pred)
+        : "memory");
+    return r;
+  }
+};
 
 // ---- FP32 error band ----------------------------------------------
 // |J_fp32 - J_fp64| <= c0 + c1*sqrt(J) + c2*J for every hypothesis of an item, from the item's
@@ -146,7 +177,7 @@ __device__ double warp_cost64(const SearchParams& p, const WinInfo& wi, const do
   const double* tAy = tgt + P;
   const double* tBx = tgt + 2 * P;
   const double* tBy = tgt + 3 * P;
-  const double* tI = tgt + 4 * P;
+  const double* tI = tgt + (DUAL ? 4 : 2) * P;
   Pose<double> carry{0.0, 0.0, 0.0};
   double J = 0.0;
   const int N = wi.n_steps;
@@ -254,11 +285,17 @@ __device__ __forceinline__ void scan_item(int N, int gs, int vd_cols, int j, int
 
 // ---- the kernel -----------------------------------------------------------------------------
 template <bool DUAL, bool IMU>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(kCtaThreads, 2)
 vmvo_window_search_kernel(const SearchParams p) {
-  extern __shared__ __align__(1024) unsigned char smem[];
+  extern __shared__ __align__(1024) unsigned char smem_cta[];
   const int P = p.maxp;
-  const SmemLayout lay(P, p.gs, p.vd_cols);
+  const int n_streams = p.load_vo + p.load_gps;
+  const SmemLayout lay(P, p.gs, p.vd_cols, p.team_warps, n_streams, DUAL, IMU,
+                       p.target_mode == VMVO_TARGET_TRAVERSE);
+  // stream s (0 = VO, 1 = GPS) lives in slot s when both are staged, else in slot 0
+  const int slot_vo = 0, slot_gps = p.load_vo ? 1 : 0;
+  const Team team{p.team_warps, p.team_warps * 32, (int)threadIdx.x / (p.team_warps * 32)};
+  unsigned char* smem = smem_cta + (size_t)team.id * lay.total;
   SmemHeader* hd = reinterpret_cast<SmemHeader*>(smem);
   float4* raw = reinterpret_cast<float4*>(smem + lay.off_raw);
   double* loc = reinterpret_cast<double*>(smem + lay.off_loc);
@@ -273,8 +310,10 @@ vmvo_window_search_kernel(const SearchParams p) {
   float* VD = reinterpret_cast<float*>(smem + lay.off_vd);
   uint2* cand = reinterpret_cast<uint2*>(smem + lay.off_cand);
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int T = blockDim.x, NW = T >> 5;
+  const int tid = threadIdx.x - team.id * team.threads;   // thread index within the team
+  const int lane = tid & 31, warp = tid >> 5;              // warp index within the team
+  const int T = team.threads, NW = team.warps;
+  const int cand_cap = kCandPerWarp * NW;
 
   // A = first position stream with a weight, B = the second one (DUAL only)
   const int sA = p.use_vo ? 0 : 1;
@@ -293,8 +332,10 @@ vmvo_window_search_kernel(const SearchParams p) {
     const unsigned total = bytes * (unsigned)(p.load_vo + p.load_gps);
     mbar_arrive_expect_tx(&hd->mbar[buf], total);
     if (bytes) {
-      if (p.load_vo) bulk_g2s(raw + (buf * 2 + 0) * P, p.vo + start, bytes, &hd->mbar[buf]);
-      if (p.load_gps) bulk_g2s(raw + (buf * 2 + 1) * P, p.gps + start, bytes, &hd->mbar[buf]);
+      if (p.load_vo)
+        bulk_g2s(raw + (buf * n_streams + slot_vo) * P, p.vo + start, bytes, &hd->mbar[buf]);
+      if (p.load_gps)
+        bulk_g2s(raw + (buf * n_streams + slot_gps) * P, p.gps + start, bytes, &hd->mbar[buf]);
     }
   };
 
@@ -307,7 +348,7 @@ vmvo_window_search_kernel(const SearchParams p) {
     hd->wid[0] = w;
     if (w < p.n_windows) issue_load(w, 0);
   }
-  __syncthreads();
+  team.sync();
 
   for (int it = 0;; ++it) {
     const int cur = it & 1;
@@ -335,7 +376,7 @@ vmvo_window_search_kernel(const SearchParams p) {
     if (len > P || len < 1) {  // uniform branch
       res.status = VMVO_WIN_TOO_LONG;
       if (tid == 0) p.results[w] = res;
-      __syncthreads();
+      team.sync();
       continue;
     }
 
@@ -343,14 +384,15 @@ vmvo_window_search_kernel(const SearchParams p) {
     if (tid < ((len + 31) & ~31)) {  // only the warps that own poses pay for sincos
       for (int s = 0; s < 2; ++s) {
         if (!(s == 0 ? p.load_vo : p.load_gps)) continue;
-        const float4* rs = raw + (cur * 2 + s) * P;
+        const int slot = s == 0 ? slot_vo : slot_gps;
+        const float4* rs = raw + (cur * n_streams + slot) * P;
         const float4 p0 = rs[0];
         const double th0 = (double)p0.z;
         double sn, cs;
         sincos(th0, &sn, &cs);
-        double* lx = loc + (s * 3 + 0) * P;
-        double* ly = loc + (s * 3 + 1) * P;
-        double* lt = loc + (s * 3 + 2) * P;
+        double* lx = loc + (slot * 3 + 0) * P;
+        double* ly = loc + (slot * 3 + 1) * P;
+        double* lt = loc + (slot * 3 + 2) * P;
         for (int m = tid; m < len; m += T) {
           const float4 q = rs[m];
           const double dx = dsub((double)q.x, (double)p0.x);
@@ -365,14 +407,15 @@ vmvo_window_search_kernel(const SearchParams p) {
       const double y0 = (double)p.imu[start];
       for (int m = tid; m < len; m += T) loci[m] = dsub((double)p.imu[start + m], y0);
     }
-    __syncthreads();
+    team.sync();
 
     // ---- phase A2 (warp 0): seeds, decimation (a9) ----------------------------------------
-    const double* plx = loc + (p.primary * 3 + 0) * P;
-    const double* ply = loc + (p.primary * 3 + 1) * P;
-    const double* plt = loc + (p.primary * 3 + 2) * P;
+    const int slot_prim = p.primary == VMVO_PRIMARY_VO ? slot_vo : slot_gps;
+    const double* plx = loc + (slot_prim * 3 + 0) * P;
+    const double* ply = loc + (slot_prim * 3 + 1) * P;
+    const double* plt = loc + (slot_prim * 3 + 2) * P;
     if (warp == 0) {
-      const float4* rp = raw + (cur * 2 + p.primary) * P;
+      const float4* rp = raw + (cur * n_streams + slot_prim) * P;
       double v_seed, s_seed;
       if (p.seed_mode == VMVO_SEED_GIVEN) {
         v_seed = p.seeds[2 * w];
@@ -417,7 +460,7 @@ vmvo_window_search_kernel(const SearchParams p) {
         hd->wi.n_steps = n_targets > 1 ? n_targets - 1 : 0;
       }
     }
-    __syncthreads();
+    team.sync();
 
     const int n_targets = hd->wi.n_targets;
     const int N = hd->wi.n_steps;
@@ -429,10 +472,11 @@ vmvo_window_search_kernel(const SearchParams p) {
     bool finite = isfinite(v_seed) && isfinite(s_seed) && isfinite(dt);
     float dmax = 0.f, dabmax = 0.f, imax = 0.f;
     {
-      const double* aX = loc + (sA * 3 + 0) * P;
-      const double* aY = loc + (sA * 3 + 1) * P;
-      const double* bX = loc + (1 * 3 + 0) * P;
-      const double* bY = loc + (1 * 3 + 1) * P;
+      const int slot_a = sA == 0 ? slot_vo : slot_gps;
+      const double* aX = loc + (slot_a * 3 + 0) * P;
+      const double* aY = loc + (slot_a * 3 + 1) * P;
+      const double* bX = loc + (slot_gps * 3 + 0) * P;   // B is GPS (DUAL only)
+      const double* bY = loc + (slot_gps * 3 + 1) * P;
       for (int q = tid; q < n_targets; q += T) {
         const int m = traverse ? keep[q] : q;
         const double ax = aX[m], ay = aY[m];
@@ -447,7 +491,7 @@ vmvo_window_search_kernel(const SearchParams p) {
         }
         if (IMU) {
           const double yi = loci[m];
-          tgt[4 * P + q] = yi;
+          tgt[(DUAL ? 4 : 2) * P + q] = yi;
           finite = finite && isfinite(yi);
         }
         // step k = q + off compares against target q; its increment needs target q - 1
@@ -473,13 +517,18 @@ vmvo_window_search_kernel(const SearchParams p) {
     }
     // ---- phase A4: TL[k][j] = tan(delta_k(j)) / L and the steering penalty per j -------------
     if (N > 0) {
+      // one steering rate per thread (one division), steps strided over the threads that share it
       const float invL = (float)(1.0 / p.L);
-      for (int e = tid; e < N * p.gs; e += T) {
-        const int k = e / p.gs + 1, j = e - (k - 1) * p.gs;
-        double s = dadd(s_seed, dmul(grid_rate(p.max_rate, j, p.gs), dmul((double)k, dt)));
-        s = s < -p.max_steer ? -p.max_steer : s;
-        s = s > p.max_steer ? p.max_steer : s;
-        TL[e] = tanf((float)(s * kd)) * invL;
+      const int kpar = T >= p.gs ? T / p.gs : 1;
+      for (int c = tid; c < p.gs * kpar; c += T) {
+        const int j = c % p.gs;
+        const double rdt = dmul(grid_rate(p.max_rate, j, p.gs), dt);
+        for (int k = 1 + c / p.gs; k <= N; k += kpar) {
+          double s = dadd(s_seed, dmul(rdt, (double)k));
+          s = s < -p.max_steer ? -p.max_steer : s;
+          s = s > p.max_steer ? p.max_steer : s;
+          TL[(k - 1) * p.gs + j] = tanf((float)(s * kd)) * invL;
+        }
       }
       if (ksteer) {
         for (int j = tid; j < p.gs; j += T) {
@@ -509,7 +558,8 @@ vmvo_window_search_kernel(const SearchParams p) {
         hd->red[16 + warp] = imax;
       }
     }
-    const int bad = __syncthreads_or(finite ? 0 : 1);
+    team.sync();   // red[] complete
+    const int bad = team.any(finite ? 0 : 1);
     dmax = dabmax = imax = 0.f;
     for (int q = 0; q < NW; ++q) {
       dmax = fmaxf(dmax, hd->red[q]);
@@ -526,7 +576,7 @@ vmvo_window_search_kernel(const SearchParams p) {
 
     if (status & VMVO_WIN_EMPTY) {
       if (tid == 0) p.results[w] = res;
-      __syncthreads();
+      team.sync();
       continue;
     }
 
@@ -561,7 +611,7 @@ vmvo_window_search_kernel(const SearchParams p) {
       float Uw = CUDART_INF_F;         // this warp's tightened copy (after float64 re-scores)
 
       auto process_list = [&]() {
-        const int count = hd->count < kCandCap ? hd->count : kCandCap;
+        const int count = hd->count < cand_cap ? hd->count : cand_cap;
         for (int e = warp; e < count; e += NW) {
           const uint2 ce = cand[e];
           if (__uint_as_float(ce.y) > fminf(U, Uw)) continue;  // warp-uniform; NaN stays in
@@ -577,23 +627,29 @@ vmvo_window_search_kernel(const SearchParams p) {
           // a float64 cost is itself an upper bound on the minimum (rounded up to float)
           Uw = fminf(Uw, __double2float_ru(c64));
         }
-        __syncthreads();
+        team.sync();
         if (tid == 0) hd->count = 0;
-        __syncthreads();
+        team.sync();
       };
 
       const int n_pass = (p.n_items + T - 1) / T;
       for (int pass = 0; pass < n_pass; ++pass) {
         // VD[k][m] = V_k(ic0*C + m) * dt for the accelerations this pass touches
         const int ic0 = (pass * T) / p.gs;
-        for (int e = tid; e < N * p.vd_cols; e += T) {
-          const int k = e / p.vd_cols + 1, m = e - (k - 1) * p.vd_cols;
-          int i = ic0 * kC + m;
-          i = i < p.gv ? i : p.gv - 1;
-          const double vv = dadd(v_seed, dmul(grid_rate(p.max_accel, i, p.gv), dmul((double)k, dt)));
-          VD[e] = (float)((vv > 0.0 ? vv : 0.0) * dt);
+        {
+          const int kpar = T >= p.vd_cols ? T / p.vd_cols : 1;
+          for (int c = tid; c < p.vd_cols * kpar; c += T) {
+            const int m = c % p.vd_cols;
+            int i = ic0 * kC + m;
+            i = i < p.gv ? i : p.gv - 1;
+            const double adt = dmul(grid_rate(p.max_accel, i, p.gv), dt);
+            for (int k = 1 + c / p.vd_cols; k <= N; k += kpar) {
+              const double vv = dadd(v_seed, dmul(adt, (double)k));
+              VD[(k - 1) * p.vd_cols + m] = (float)((vv > 0.0 ? vv : 0.0) * dt);
+            }
+          }
         }
-        __syncthreads();
+        team.sync();
         const int q = pass * T + tid;
         ScanOut so;
         int ic = 0, j = 0;
@@ -624,7 +680,7 @@ vmvo_window_search_kernel(const SearchParams p) {
           if ((valid >> c) & 1u) m = fminf(m, so.J[c] + band.err(so.J[c]));  // fminf drops NaN
         m = warp_min_f32_nonneg(fmaxf(m, 0.f));
         if (lane == 0) hd->red[warp] = m;
-        __syncthreads();
+        team.sync();
         float bm = lane < NW ? hd->red[lane] : CUDART_INF_F;
         bm = warp_min_f32_nonneg(bm);
         U = fminf(U, bm);
@@ -637,14 +693,14 @@ vmvo_window_search_kernel(const SearchParams p) {
           for (int c = 0; c < kC; ++c) {
             if ((pend >> c) & 1u) {
               const int slot = atomicAdd(&hd->count, 1);
-              if (slot < kCandCap) {
+              if (slot < cand_cap) {
                 cand[slot] = make_uint2((unsigned)((ic * kC + c) * p.gs + j),
                                         __float_as_uint(so.J[c] - band.err(so.J[c])));
                 pend &= ~(1u << c);
               }
             }
           }
-          const int overflow = __syncthreads_or(pend != 0);
+          const int overflow = team.any(pend != 0);
           if (!overflow) break;
           process_list();
         }
@@ -661,7 +717,7 @@ vmvo_window_search_kernel(const SearchParams p) {
       hd->bpose[warp][2] = best_first.th;
       hd->nres[warp] = n_rescored;
     }
-    __syncthreads();
+    team.sync();
     if (tid == 0) {
       int bwi = -1;
       int total = 0;
@@ -685,7 +741,7 @@ vmvo_window_search_kernel(const SearchParams p) {
       p.results[w] = res;
     }
     if (p.out_poses || p.out_steer || p.out_vel) {
-      __syncthreads();
+      team.sync();
       const int h = hd->winner;
       if (warp == 0 && h >= 0) {
         const int i = h / p.gs, j = h - i * p.gs;
@@ -713,25 +769,29 @@ vmvo_window_search_kernel(const SearchParams p) {
         }
       }
     }
-    __syncthreads();
+    team.sync();
   }
 }
 
 template <bool DUAL, bool IMU>
-static int launch_search(vmvo_ctx* ctx, const SearchParams& p, int threads, cudaStream_t st) {
+static int launch_search(vmvo_ctx* ctx, const SearchParams& p, cudaStream_t st) {
   auto kern = vmvo_window_search_kernel<DUAL, IMU>;
-  const SmemLayout lay(p.maxp, p.gs, p.vd_cols);
-  if (lay.total > 200 * 1024)
+  const SmemLayout lay(p.maxp, p.gs, p.vd_cols, p.team_warps, p.load_vo + p.load_gps, DUAL, IMU,
+                       p.target_mode == VMVO_TARGET_TRAVERSE);
+  const int teams = kMaxWarps / p.team_warps;
+  const int smem = lay.total * teams;
+  if (smem > 200 * 1024)
     return fail(ctx, VMVO_ERR_UNSUPPORTED,
                 "window tables need %d bytes of shared memory (max_window_poses %d x grid_s %d): "
-                "reduce max_window_poses or grid_s", lay.total, p.maxp, p.gs);
-  VMVO_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total));
+                "reduce max_window_poses or grid_s", smem, p.maxp, p.gs);
+  VMVO_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int per_sm = 0;
-  VMVO_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, lay.total));
+  VMVO_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kCtaThreads, smem));
   if (per_sm < 1) return fail(ctx, VMVO_ERR_CUDA, "search kernel does not fit on an SM");
   long long grid = (long long)ctx->sm_count * per_sm;
-  if (grid > p.n_windows) grid = p.n_windows;
-  kern<<<(unsigned)grid, threads, lay.total, st>>>(p);
+  const long long need = (p.n_windows + teams - 1) / teams;
+  if (grid > need) grid = need;
+  kern<<<(unsigned)grid, kCtaThreads, smem, st>>>(p);
   return check_launch(ctx, "vmvo_window_search_kernel");
 }
 
@@ -774,8 +834,21 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
   p.gs = cfg->grid_s;
   p.n_ic = (p.gv + kC - 1) / kC;
   p.n_items = p.n_ic * p.gs;
-  int threads = ((p.n_items + 31) / 32) * 32;
-  threads = threads < 64 ? 64 : (threads > 256 ? 256 : threads);
+  // team size: about eight passes of 32 items per warp, so small grids run one window per warp
+  int tw = 1;
+  while (tw < kMaxWarps && p.n_items > tw * 32 * 8) tw *= 2;
+  // ... unless the per-team tables would not leave room for two CTAs per SM
+  for (;;) {
+    const int th = tw * 32;
+    int ch = (th + p.gs - 1) / p.gs + 1;
+    if (ch > p.n_ic) ch = p.n_ic;
+    const SmemLayout probe(cfg->max_window_poses, p.gs, ch * kC, tw, (int)load_vo + (int)load_gps,
+                           use_vo && use_gps, use_imu, cfg->target_mode == VMVO_TARGET_TRAVERSE);
+    if (tw == kMaxWarps || probe.total * (kMaxWarps / tw) <= 110 * 1024) break;
+    tw *= 2;
+  }
+  p.team_warps = tw;
+  const int threads = tw * 32;
   // accelerations one pass can touch: items [pass*T, pass*T + T) span at most this many chunks
   int chunks = (threads + p.gs - 1) / p.gs + 1;
   if (chunks > p.n_ic) chunks = p.n_ic;
@@ -826,10 +899,9 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
   p.work_counter = counter;
 
   const bool dual = use_vo && use_gps;
-  if (dual) return use_imu ? launch_search<true, true>(ctx, p, threads, st)
-                           : launch_search<true, false>(ctx, p, threads, st);
-  return use_imu ? launch_search<false, true>(ctx, p, threads, st)
-                 : launch_search<false, false>(ctx, p, threads, st);
+  if (dual) return use_imu ? launch_search<true, true>(ctx, p, st)
+                           : launch_search<true, false>(ctx, p, st);
+  return use_imu ? launch_search<false, true>(ctx, p, st) : launch_search<false, false>(ctx, p, st);
 }
 
 }  // namespace vmvo
