@@ -18,6 +18,7 @@
 #include "vmvo_internal.h"
 
 #include <math_constants.h>
+#include <stdlib.h>
 
 namespace vmvo {
 
@@ -62,7 +63,11 @@ struct SearchParams {
 // per-window scalars shared by the CTA
 struct WinInfo {
   double v_seed, s_seed, dt;
-  int n_targets, n_steps, status, pad;
+  int n_targets, n_steps, status;
+  // structural duplicates: rows i < n_dead never move (V_k = 0 for every k) and
+  // share one cost for every j; with the seed at a steering bound, rates j in [sat_lo, sat_hi]
+  // all clamp to the same sequence.  Only the lowest index of a class can be the argmin.
+  int n_dead, sat_lo, sat_hi;
 };
 
 // ---- shared-memory carve-up (same function on host and device) ---------------------------
@@ -452,12 +457,49 @@ vmvo_window_search_kernel(const SearchParams p) {
         }
         n_targets = __shfl_sync(FULL, n_targets, 0);
       }
+      // rows that never move: a_i <= 0 and V_w + a_i*t_1 <= 0 (a_i grows with i: a prefix)
+      int n_dead = 0;
+      for (int i0 = 0; i0 < p.gv; i0 += 32) {
+        const int i = i0 + lane;
+        bool dead = false;
+        if (i < p.gv) {
+          const double a = grid_rate(p.max_accel, i, p.gv);
+          dead = a <= 0.0 && !(dadd(v_seed, dmul(a, dmul(1.0, dt))) > 0.0) && v_seed == v_seed;
+        }
+        const unsigned b = __ballot_sync(FULL, dead);
+        n_dead += __popc(b);
+        if (b != FULL) break;
+      }
+      // steering rates that clamp to the seed's bound for every step
+      int sat_lo = 0, sat_hi = -1;
+      if (s_seed == p.max_steer || s_seed == -p.max_steer) {
+        const bool hi = s_seed > 0;
+        int first = p.gs, last = -1;
+        for (int j0 = 0; j0 < p.gs; j0 += 32) {
+          const int j = j0 + lane;
+          bool in = false;
+          if (j < p.gs) {
+            const double r = grid_rate(p.max_rate, j, p.gs);
+            in = hi ? (r >= 0.0) : (r <= 0.0);
+          }
+          const unsigned b = __ballot_sync(FULL, in);
+          if (b) {
+            first = min(first, j0 + __ffs(b) - 1);
+            last = max(last, j0 + 31 - __clz(b));
+          }
+        }
+        sat_lo = first;
+        sat_hi = last;
+      }
       if (lane == 0) {
         hd->wi.v_seed = v_seed;
         hd->wi.s_seed = s_seed;
         hd->wi.dt = dt;
         hd->wi.n_targets = n_targets;
         hd->wi.n_steps = n_targets > 1 ? n_targets - 1 : 0;
+        hd->wi.n_dead = n_dead;
+        hd->wi.sat_lo = sat_lo;
+        hd->wi.sat_hi = sat_hi;
       }
     }
     team.sync();
@@ -688,6 +730,14 @@ vmvo_window_search_kernel(const SearchParams p) {
 #pragma unroll
         for (int c = 0; c < kC; ++c)
           if (((valid >> c) & 1u) && !(so.J[c] - band.err(so.J[c]) > U)) pend |= 1u << c;
+        // drop structural duplicates: only the lowest index of a class can win (np.argmin)
+        if (j > wi.sat_lo && j <= wi.sat_hi) pend = 0;
+#pragma unroll
+        for (int c = 0; c < kC; ++c) {
+          const int i = ic * kC + c;
+          // (with a steering penalty the cost of a motionless row still depends on j)
+          if (i < wi.n_dead && (i > 0 || (j > 0 && !ksteer))) pend &= ~(1u << c);
+        }
         for (;;) {
 #pragma unroll
           for (int c = 0; c < kC; ++c) {
@@ -846,6 +896,10 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
                            use_vo && use_gps, use_imu, cfg->target_mode == VMVO_TARGET_TRAVERSE);
     if (tw == kMaxWarps || probe.total * (kMaxWarps / tw) <= 110 * 1024) break;
     tw *= 2;
+  }
+  if (const char* ov = getenv("VMVO_TEAM_WARPS")) {  // tuning knob, not part of the ABI
+    const int v = atoi(ov);
+    if (v == 1 || v == 2 || v == 4 || v == 8) tw = v;
   }
   p.team_warps = tw;
   const int threads = tw * 32;
