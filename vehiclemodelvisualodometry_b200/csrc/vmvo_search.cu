@@ -38,6 +38,7 @@ struct SearchParams {
   int load_vo, load_gps; // streams staged into shared memory
   int vd_cols;           // columns of the VD table (accelerations covered by one pass)
   int team_warps;        // warps per team (1, 2, 4 or 8)
+  int cand_cap;          // candidate list entries per team (<= kCandPerWarp * team_warps)
   double w_vo, w_gps, w_imu, k_steer;
   double L, ratio, max_steer, max_accel, max_rate;
   double delta_max, kappa;     // kappa = 2*delta_max / sin(2*delta_max): tan's condition number
@@ -318,7 +319,7 @@ vmvo_window_search_kernel(const SearchParams p) {
   const int tid = threadIdx.x - team.id * team.threads;   // thread index within the team
   const int lane = tid & 31, warp = tid >> 5;              // warp index within the team
   const int T = team.threads, NW = team.warps;
-  const int cand_cap = kCandPerWarp * NW;
+  const int cand_cap = p.cand_cap;
 
   // A = first position stream with a weight, B = the second one (DUAL only)
   const int sA = p.use_vo ? 0 : 1;
@@ -884,9 +885,9 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
   p.gs = cfg->grid_s;
   p.n_ic = (p.gv + kC - 1) / kC;
   p.n_items = p.n_ic * p.gs;
-  // team size: about eight passes of 32 items per warp, so small grids run one window per warp
+  // team size: about two passes of 32 items per warp (measured best on 32x32: two warps)
   int tw = 1;
-  while (tw < kMaxWarps && p.n_items > tw * 32 * 8) tw *= 2;
+  while (tw < kMaxWarps && p.n_items > tw * 32 * 2) tw *= 2;
   // ... unless the per-team tables would not leave room for two CTAs per SM
   for (;;) {
     const int th = tw * 32;
@@ -902,6 +903,11 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
     if (v == 1 || v == 2 || v == 4 || v == 8) tw = v;
   }
   p.team_warps = tw;
+  p.cand_cap = kCandPerWarp * tw;
+  if (const char* ov = getenv("VMVO_CAND_CAP")) {  // test knob: forces the list-flush path
+    const int v = atoi(ov);
+    if (v >= 1 && v < p.cand_cap) p.cand_cap = v;
+  }
   const int threads = tw * 32;
   // accelerations one pass can touch: items [pass*T, pass*T + T) span at most this many chunks
   int chunks = (threads + p.gs - 1) / p.gs + 1;
