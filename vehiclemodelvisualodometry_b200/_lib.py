@@ -88,7 +88,8 @@ class VmvoError(RuntimeError):
 
 
 def library_path() -> str:
-    return _build.LIB_PATH
+    # VMVO_B200_LIBRARY: development override used to A/B kernel variants
+    return os.environ.get("VMVO_B200_LIBRARY") or _build.LIB_PATH
 
 
 def load() -> C.CDLL:
