@@ -167,9 +167,13 @@ def run_b200(args):
     def step():
         p = plan_windows(cfg, drives)
         so = grid_search(cfg, drives, p, out=local)
+        work = None
+        if world > 1:  # the only exchange of the path: per-window records to every rank;
+            # it runs on NCCL's stream while the write-back (local records only) proceeds
+            work = dist.all_gather_into_tensor(gathered, local, async_op=True)
         traj = write_back(cfg, drives, p, so.results, blend_gps=False)
-        if world > 1:  # the only exchange of the path: per-window records to every rank
-            dist.all_gather_into_tensor(gathered, local)
+        if work is not None:
+            work.wait()
         return so, traj
 
     def timed(fn, k, w):
@@ -381,10 +385,16 @@ def cpu_pass(workload, seed, max_windows=None, threads=0):
     return steps, time.perf_counter() - t0, len(starts)
 
 
-def cpu_baseline(workload, budget_s=12.0):
-    from oracle import c_oracle
+def host_threads():
+    """All host threads this process may use (torchrun pins OMP_NUM_THREADS=1; ignore that)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
-    cores = c_oracle.max_threads()
+
+def cpu_baseline(workload, budget_s=12.0):
+    cores = host_threads()
     cpu_pass(workload, BASE_SEED, max_windows=256, threads=cores)  # warm the library and the threads
     n_frames, cfg = make_cfg(workload)
     total_win = n_frames - 2 * cfg.window_frames
@@ -408,9 +418,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import c_oracle
-
-    cores = c_oracle.max_threads()
+    cores = host_threads()
     n_frames, cfg = make_cfg(args.workload)
     total_win = n_frames - 2 * cfg.window_frames
     per_win = cfg.grid_v * cfg.grid_s * cfg.window_frames
