@@ -22,7 +22,6 @@
 
 namespace vmvo {
 
-constexpr int kC = 8;            // hypotheses (consecutive accelerations) per thread
 constexpr int kCandPerWarp = 128;  // candidate list entries per team warp (flushed when full)
 constexpr int kMaxWarps = 8;       // warps per CTA and largest team
 constexpr int kCtaThreads = 32 * kMaxWarps;
@@ -222,42 +221,46 @@ __device__ double warp_cost64(const SearchParams& p, const WinInfo& wi, const do
 }
 
 // ---- FP32 scan of one item: steering rate j, accelerations m0 .. m0+C-1 of the VD table ------
+template <int C>
 struct ScanOut {
-  float J[kC];
+  float J[C];
   float vmax, theta_tv, tlmax;   // inputs of the item's error band
 };
 
-template <bool DUAL, bool IMU>
+template <int C, bool DUAL, bool IMU>
 __device__ __forceinline__ void scan_item(int N, int gs, int vd_cols, int j, int m0,
                                           const float* __restrict__ TL,
                                           const float* __restrict__ VD,
                                           const float2* __restrict__ Df,
                                           const float2* __restrict__ Dab,
                                           const float* __restrict__ fI, float wA, float wB,
-                                          float wI, float kJS, ScanOut& out) {
-  float th[kC], ex[kC], ey[kC], JA[kC], JB[kC], JI[kC];
+                                          float wI, float kJS, ScanOut<C>& out) {
+  float th[C], ex[C], ey[C], JA[C], JB[C], JI[C];
 #pragma unroll
-  for (int c = 0; c < kC; ++c) th[c] = ex[c] = ey[c] = JA[c] = JB[c] = JI[c] = 0.f;
+  for (int c = 0; c < C; ++c) th[c] = ex[c] = ey[c] = JA[c] = JB[c] = JI[c] = 0.f;
   float vmax = 0.f, tv = 0.f, tlmax = 0.f;
   const float* tl = TL + j;
   const float* vd = VD + m0;
 #pragma unroll 1
   for (int k = 1; k <= N; ++k) {
     const float tlk = tl[(k - 1) * gs];
-    const float4 va = *reinterpret_cast<const float4*>(vd + (k - 1) * vd_cols);
-    const float4 vb = *reinterpret_cast<const float4*>(vd + (k - 1) * vd_cols + 4);
-    const float v[kC] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+    float v[C];
+#pragma unroll
+    for (int c4 = 0; c4 < C; c4 += 4) {
+      const float4 q = *reinterpret_cast<const float4*>(vd + (k - 1) * vd_cols + c4);
+      v[c4] = q.x; v[c4 + 1] = q.y; v[c4 + 2] = q.z; v[c4 + 3] = q.w;
+    }
     const float2 d = Df[k];
     float2 dab = make_float2(0.f, 0.f);
     float ti = 0.f;
     if (DUAL) dab = Dab[k];
     if (IMU) ti = fI[k];
     // band statistics from the item's fastest hypothesis (VD is non-decreasing in i)
-    tv = fmaf(v[kC - 1], fabsf(tlk), tv);
+    tv = fmaf(v[C - 1], fabsf(tlk), tv);
     tlmax = fmaxf(tlmax, fabsf(tlk));
-    vmax = fmaxf(vmax, v[kC - 1]);
+    vmax = fmaxf(vmax, v[C - 1]);
 #pragma unroll
-    for (int c = 0; c < kC; ++c) {
+    for (int c = 0; c < C; ++c) {
       th[c] = fmaf(v[c], tlk, th[c]);
       float sn, cs;
       __sincosf(th[c], &sn, &cs);
@@ -278,7 +281,7 @@ __device__ __forceinline__ void scan_item(int N, int gs, int vd_cols, int j, int
     }
   }
 #pragma unroll
-  for (int c = 0; c < kC; ++c) {
+  for (int c = 0; c < C; ++c) {
     float t = fmaf(wA, JA[c], kJS);
     if (DUAL) t = fmaf(wB, JB[c], t);
     if (IMU) t = fmaf(wI, JI[c], t);
@@ -290,9 +293,10 @@ __device__ __forceinline__ void scan_item(int N, int gs, int vd_cols, int j, int
 }
 
 // ---- the kernel -----------------------------------------------------------------------------
-template <bool DUAL, bool IMU>
-__global__ void __launch_bounds__(kCtaThreads, 2)
+template <int C, int MINB, bool DUAL, bool IMU>
+__global__ void __launch_bounds__(kCtaThreads, MINB)
 vmvo_window_search_kernel(const SearchParams p) {
+  constexpr int kC = C;
   extern __shared__ __align__(1024) unsigned char smem_cta[];
   const int P = p.maxp;
   const int n_streams = p.load_vo + p.load_gps;
@@ -694,14 +698,14 @@ vmvo_window_search_kernel(const SearchParams p) {
         }
         team.sync();
         const int q = pass * T + tid;
-        ScanOut so;
+        ScanOut<C> so;
         int ic = 0, j = 0;
         unsigned valid = 0;
         Band band{0.f, 0.f, 0.f};
         if (q < p.n_items) {
           ic = q / p.gs;
           j = q - ic * p.gs;
-          scan_item<DUAL, IMU>(N, p.gs, p.vd_cols, j, (ic - ic0) * kC, TL, VD, Df, Dab, fI, wA, wB, wI,
+          scan_item<C, DUAL, IMU>(N, p.gs, p.vd_cols, j, (ic - ic0) * kC, TL, VD, Df, Dab, fI, wA, wB, wI,
                                ksteer ? JS[j] : 0.f, so);
           band = make_band(bw, so.vmax, so.theta_tv, so.tlmax);
 #pragma unroll
@@ -824,9 +828,9 @@ vmvo_window_search_kernel(const SearchParams p) {
   }
 }
 
-template <bool DUAL, bool IMU>
+template <int C, int MINB, bool DUAL, bool IMU>
 static int launch_search(vmvo_ctx* ctx, const SearchParams& p, cudaStream_t st) {
-  auto kern = vmvo_window_search_kernel<DUAL, IMU>;
+  auto kern = vmvo_window_search_kernel<C, MINB, DUAL, IMU>;
   const SmemLayout lay(p.maxp, p.gs, p.vd_cols, p.team_warps, p.load_vo + p.load_gps, DUAL, IMU,
                        p.target_mode == VMVO_TARGET_TRAVERSE);
   const int teams = kMaxWarps / p.team_warps;
@@ -880,9 +884,17 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
   if ((d_dbg_cost == nullptr) != (d_dbg_err == nullptr))
     return fail(ctx, VMVO_ERR_BAD_ARG, "debug outputs come in pairs");
 
+  // hypotheses per thread: 4 (64 registers, four CTAs per SM: the window setup and the float64
+  // re-score of one team overlap with other teams' scans) when the tables are small enough for
+  // four CTAs per SM, else 8 (128 registers, two CTAs per SM)
+  int kC = 4;
+  if (const char* ov = getenv("VMVO_HYP_PER_THREAD")) {  // tuning knob
+    if (atoi(ov) == 8) kC = 8;
+  }
   SearchParams p;
   p.gv = cfg->grid_v;
   p.gs = cfg->grid_s;
+retry_c:
   p.n_ic = (p.gv + kC - 1) / kC;
   p.n_items = p.n_ic * p.gs;
   // team size: about two passes of 32 items per warp (measured best on 32x32: two warps)
@@ -895,7 +907,12 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
     if (ch > p.n_ic) ch = p.n_ic;
     const SmemLayout probe(cfg->max_window_poses, p.gs, ch * kC, tw, (int)load_vo + (int)load_gps,
                            use_vo && use_gps, use_imu, cfg->target_mode == VMVO_TARGET_TRAVERSE);
-    if (tw == kMaxWarps || probe.total * (kMaxWarps / tw) <= 110 * 1024) break;
+    const int budget = kC == 4 ? 54 * 1024 : 110 * 1024;
+    if (probe.total * (kMaxWarps / tw) <= budget) break;
+    if (tw == kMaxWarps) {
+      if (kC == 4) { kC = 8; goto retry_c; }   // tables too large for four CTAs per SM
+      break;
+    }
     tw *= 2;
   }
   if (const char* ov = getenv("VMVO_TEAM_WARPS")) {  // tuning knob, not part of the ABI
@@ -959,9 +976,13 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
   p.work_counter = counter;
 
   const bool dual = use_vo && use_gps;
-  if (dual) return use_imu ? launch_search<true, true>(ctx, p, st)
-                           : launch_search<true, false>(ctx, p, st);
-  return use_imu ? launch_search<false, true>(ctx, p, st) : launch_search<false, false>(ctx, p, st);
+#define VMVO_LAUNCH(CC, MB)                                                              \
+  (dual ? (use_imu ? launch_search<CC, MB, true, true>(ctx, p, st)                       \
+                   : launch_search<CC, MB, true, false>(ctx, p, st))                     \
+        : (use_imu ? launch_search<CC, MB, false, true>(ctx, p, st)                      \
+                   : launch_search<CC, MB, false, false>(ctx, p, st)))
+  return kC == 4 ? VMVO_LAUNCH(4, 4) : VMVO_LAUNCH(8, 2);
+#undef VMVO_LAUNCH
 }
 
 }  // namespace vmvo
