@@ -123,6 +123,20 @@ int vmvo_grid_search_f32(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n_wi
                          double* d_out_poses, double* d_out_steer, double* d_out_vel,
                          int32_t out_stride, void* stream);
 
+/* seed_mode = VMVO_SEED_CHAINED (optimize_trajectory_v2.py:46,72,146): the steering seed of a
+ * window is the last steering angle of the previous window's optimum, 0 for the first window
+ * of a drive.  Windows of a drive are therefore searched in order by one team; drives run in
+ * parallel.  d_run_offsets[n_runs + 1] delimits, in window indices of this call, the runs
+ * (normally one per drive: the d_window_offsets of vmvo_plan_windows).                     */
+int vmvo_grid_search_chained_f32(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n_windows,
+                                 const int64_t* d_win_start, const int32_t* d_win_len,
+                                 const int32_t* d_win_drive, const double* d_dt_per_drive,
+                                 const float* d_vo, const float* d_gps, const float* d_imu,
+                                 int64_t n_runs, const int64_t* d_run_offsets,
+                                 vmvo_window_result* d_results, double* d_out_poses,
+                                 double* d_out_steer, double* d_out_vel, int32_t out_stride,
+                                 void* stream);
+
 /* Test hook: the same search, additionally exporting the FP32 scan cost of EVERY hypothesis
  * and the width of its error band, [n_windows][grid_v * grid_s] each, so tests can check
  * |scan - float64| <= band against the oracle.  Not for production use.  */

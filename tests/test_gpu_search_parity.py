@@ -88,3 +88,32 @@ def test_window_range_and_out_buffer(cuda_device):
     got = buf.cpu().numpy().view(_lib.RESULT_DTYPE).reshape(-1)
     for f in ("best_idx", "n_steps", "status", "best_cost", "x1", "y1", "theta1"):
         np.testing.assert_array_equal(got[f], full[f])
+
+
+@pytest.mark.parametrize("target_mode", ["time", "traverse"])
+def test_chained_seed_mode(cuda_device, target_mode):
+    """seed_mode chained (optimize_trajectory_v2.py:46,72,146): S_w of window w+1 is the last
+    steering angle of window w's optimum; drives are independent runs."""
+    cfg = SearchConfig(grid_v=8, grid_s=16, window_frames=20, seed_mode="chained", target_mode=target_mode)
+    lengths = [75, 40, 120]           # the middle drive has no windows at all
+    batch = synthetic_drives(3, 120, seed=17)
+    time = [batch.time[d][:n] for d, n in enumerate(lengths)]
+    vo = [batch.vo[d][:n] for d, n in enumerate(lengths)]
+    drives = DriveSet.from_arrays(time, [batch.dt] * 3, vo=vo)
+    so, traj, plan = optimize_drives(cfg, drives)
+    rec = so.records()
+    assert plan.window_offsets == [0, 35, 35, 115]
+    spec = spec_of(cfg)
+    ref_windows = []
+    for d in range(3):
+        ref = O.optimize_drive(spec, time[d], batch.dt, vo[d])
+        ref_windows += ref.windows
+        lo, hi = drives.drive_offsets[d], drives.drive_offsets[d + 1]
+        np.testing.assert_allclose(traj[0, lo:hi].cpu().numpy(), ref.x, rtol=0, atol=1e-9)
+        np.testing.assert_allclose(traj[1, lo:hi].cpu().numpy(), ref.y, rtol=0, atol=1e-9)
+    assert_records_match(rec, ref_windows)
+    # the chain itself is pure IEEE arithmetic on the selected index: bit-exact
+    np.testing.assert_array_equal(rec["s_seed"], [r.s_seed for r in ref_windows])
+    assert rec["s_seed"][0] == 0.0 and rec["s_seed"][35] == 0.0 and np.any(rec["s_seed"] != 0.0)
+    with pytest.raises(ValueError, match="whole drives"):
+        grid_search(cfg, drives, plan, window_range=(0, 20))

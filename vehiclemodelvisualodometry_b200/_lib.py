@@ -58,6 +58,9 @@ _SIGNATURES = {
     "vmvo_grid_search_f32": (C.c_int, [_c_vp, C.POINTER(SearchCfg), _c_i64, _c_vp, _c_vp, _c_vp, _c_vp,
                                        _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i32,
                                        _c_vp]),
+    "vmvo_grid_search_chained_f32": (C.c_int, [_c_vp, C.POINTER(SearchCfg), _c_i64, _c_vp, _c_vp, _c_vp,
+                                               _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp,
+                                               _c_vp, _c_vp, _c_i32, _c_vp]),
     "vmvo_grid_search_debug_f32": (C.c_int, [_c_vp, C.POINTER(SearchCfg), _c_i64, _c_vp, _c_vp, _c_vp,
                                              _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp,
                                              _c_vp]),

@@ -25,7 +25,7 @@ namespace vmvo {
 constexpr int kCandPerWarp = 128;  // candidate list entries per team warp (flushed when full)
 constexpr int kMaxWarps = 8;       // warps per CTA and largest team
 constexpr int kCtaThreads = 32 * kMaxWarps;
-constexpr int kHeaderBytes = 640;
+constexpr int kHeaderBytes = 704;
 
 struct SearchParams {
   int gv, gs;
@@ -56,6 +56,10 @@ struct SearchParams {
   int out_stride;
   long long n_windows;
   unsigned long long* work_counter;
+  // seed_mode chained: the queue hands out RUNS (the windows of one drive, in order) and the
+  // steering seed of a window is the last steering angle of the previous window's optimum
+  const long long* run_offsets;   // [n_runs + 1] window index ranges, or NULL
+  long long n_runs;
   float* dbg_cost;       // optional [n_windows][gv*gs] FP32 scan costs   (tests only)
   float* dbg_err;        // optional [n_windows][gv*gs] error-band widths (tests only)
 };
@@ -108,6 +112,7 @@ struct SmemHeader {
   int nres[kMaxWarps];
   int count;
   int winner;
+  int first[2];      // chained mode: the window is the first of its run
 };
 static_assert(sizeof(SmemHeader) <= kHeaderBytes, "header too large");
 
@@ -349,12 +354,31 @@ vmvo_window_search_kernel(const SearchParams p) {
     }
   };
 
+  const bool chained = p.run_offsets != nullptr;
+  long long run_end = 0;     // thread 0: end of the run being walked (chained mode)
+  double s_chain = 0.0;      // all threads: steering seed handed from window to window
+  // thread 0: the window after `w` -- the next one of the same run, else a fresh queue item
+  auto next_window = [&](long long w, int slot) -> long long {
+    if (chained && w >= 0 && w + 1 < run_end) {
+      hd->first[slot] = 0;
+      return w + 1;
+    }
+    hd->first[slot] = 1;
+    for (;;) {
+      const long long r = (long long)atomicAdd(p.work_counter, 1ULL);
+      if (!chained) return r;
+      if (r >= p.n_runs) return p.n_windows;
+      run_end = p.run_offsets[r + 1];
+      if (p.run_offsets[r] < run_end) return p.run_offsets[r];
+    }
+  };
+
   if (tid == 0) {
     mbar_init(&hd->mbar[0], 1);
     mbar_init(&hd->mbar[1], 1);
     mbar_fence_init();
     hd->count = 0;
-    long long w = (long long)atomicAdd(p.work_counter, 1ULL);
+    const long long w = next_window(-1, 0);
     hd->wid[0] = w;
     if (w < p.n_windows) issue_load(w, 0);
   }
@@ -365,10 +389,11 @@ vmvo_window_search_kernel(const SearchParams p) {
     const long long w = hd->wid[cur];
     if (w >= p.n_windows) break;
     if (tid == 0) {  // prefetch the next window's poses while this one is searched
-      long long wn = (long long)atomicAdd(p.work_counter, 1ULL);
+      const long long wn = next_window(w, cur ^ 1);
       hd->wid[cur ^ 1] = wn;
       if (wn < p.n_windows) issue_load(wn, cur ^ 1);
     }
+    if (chained && hd->first[cur]) s_chain = 0.0;   // optimize_trajectory_v2.py:46
     const long long start = p.win_start[w];
     const int len = p.win_len[w];
     const double dt = p.dt_drive[p.win_drive[w]];
@@ -441,6 +466,7 @@ vmvo_window_search_kernel(const SearchParams p) {
           s_seed = s_seed > p.max_steer ? p.max_steer : s_seed;
         }
       }
+      if (chained) s_seed = s_chain;
       int n_targets = len;
       if (p.target_mode == VMVO_TARGET_TRAVERSE) {
         if (lane == 0) {  // sequential by definition (distance accumulator with reset)
@@ -795,6 +821,17 @@ vmvo_window_search_kernel(const SearchParams p) {
       hd->winner = res.best_idx;
       p.results[w] = res;
     }
+    if (chained) {  // last steering angle of the optimum (optimize_trajectory_v2.py:146)
+      team.sync();
+      const int h = hd->winner;
+      if (h >= 0) {
+        const int j = h % p.gs;
+        GridCtl g{wi.v_seed, wi.s_seed, wi.dt, 0.0, grid_rate(p.max_rate, j, p.gs), p.max_steer};
+        double v_unused, s_last;
+        g.at(N, &v_unused, &s_last);
+        s_chain = s_last;
+      }
+    }
     if (p.out_poses || p.out_steer || p.out_vel) {
       team.sync();
       const int h = hd->winner;
@@ -844,7 +881,8 @@ static int launch_search(vmvo_ctx* ctx, const SearchParams& p, cudaStream_t st) 
   VMVO_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kCtaThreads, smem));
   if (per_sm < 1) return fail(ctx, VMVO_ERR_CUDA, "search kernel does not fit on an SM");
   long long grid = (long long)ctx->sm_count * per_sm;
-  const long long need = (p.n_windows + teams - 1) / teams;
+  const long long items = p.run_offsets ? p.n_runs : p.n_windows;
+  const long long need = (items + teams - 1) / teams;
   if (grid > need) grid = need;
   kern<<<(unsigned)grid, kCtaThreads, smem, st>>>(p);
   return check_launch(ctx, "vmvo_window_search_kernel");
@@ -856,7 +894,8 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
                             const float* d_vo, const float* d_gps, const float* d_imu,
                             const double* d_seeds, vmvo_window_result* d_results,
                             double* d_out_poses, double* d_out_steer, double* d_out_vel,
-                            int32_t out_stride, float* d_dbg_cost, float* d_dbg_err, void* stream) {
+                            int32_t out_stride, float* d_dbg_cost, float* d_dbg_err,
+                            int64_t n_runs, const int64_t* d_run_offsets, void* stream) {
   if (!ctx) return VMVO_ERR_BAD_ARG;
   int rc = validate_cfg(ctx, cfg);
   if (rc) return rc;
@@ -864,9 +903,12 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
   if (n_windows == 0) return VMVO_OK;
   if (!d_win_start || !d_win_len || !d_win_drive || !d_dt_per_drive || !d_results)
     return fail(ctx, VMVO_ERR_BAD_ARG, "NULL window plan / dt / result pointer");
-  if (cfg->seed_mode == VMVO_SEED_CHAINED)
+  if (cfg->seed_mode == VMVO_SEED_CHAINED && !d_run_offsets)
     return fail(ctx, VMVO_ERR_UNSUPPORTED,
-                "seed_mode chained serialises the windows of a drive and is not built yet");
+                "seed_mode chained walks the windows of a drive in order: call "
+                "vmvo_grid_search_chained_f32 with the per-drive window ranges");
+  if (d_run_offsets && (cfg->seed_mode != VMVO_SEED_CHAINED || n_runs < 1))
+    return fail(ctx, VMVO_ERR_BAD_ARG, "run offsets are for seed_mode chained with n_runs >= 1");
   if (cfg->seed_mode == VMVO_SEED_GIVEN && !d_seeds)
     return fail(ctx, VMVO_ERR_BAD_ARG, "seed_mode given needs d_seeds");
   const bool use_vo = cfg->w_vo != 0, use_gps = cfg->w_gps != 0, use_imu = cfg->w_imu != 0;
@@ -884,12 +926,12 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
   if ((d_dbg_cost == nullptr) != (d_dbg_err == nullptr))
     return fail(ctx, VMVO_ERR_BAD_ARG, "debug outputs come in pairs");
 
-  // hypotheses per thread: 4 (64 registers, four CTAs per SM: the window setup and the float64
-  // re-score of one team overlap with other teams' scans) when the tables are small enough for
-  // four CTAs per SM, else 8 (128 registers, two CTAs per SM)
-  int kC = 4;
-  if (const char* ov = getenv("VMVO_HYP_PER_THREAD")) {  // tuning knob
-    if (atoi(ov) == 8) kC = 8;
+  // hypotheses per thread: 8 (128 registers, two CTAs per SM).  The 4-per-thread variant (64
+  // registers, four CTAs per SM) measured 10 % slower on the 32x32 grid (profiles/README.md)
+  // and stays behind a tuning knob.
+  int kC = 8;
+  if (const char* ov = getenv("VMVO_HYP_PER_THREAD")) {
+    if (atoi(ov) == 4) kC = 4;
   }
   SearchParams p;
   p.gv = cfg->grid_v;
@@ -967,6 +1009,8 @@ retry_c:
   p.n_windows = n_windows;
   p.dbg_cost = d_dbg_cost;
   p.dbg_err = d_dbg_err;
+  p.run_offsets = (const long long*)d_run_offsets;
+  p.n_runs = d_run_offsets ? n_runs : 0;
 
   cudaStream_t st = (cudaStream_t)stream;
   VMVO_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -998,7 +1042,22 @@ extern "C" int vmvo_grid_search_f32(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, i
                                     int32_t out_stride, void* stream) {
   return grid_search_impl(ctx, cfg, n_windows, d_win_start, d_win_len, d_win_drive, d_dt_per_drive,
                           d_vo, d_gps, d_imu, d_seeds, d_results, d_out_poses, d_out_steer, d_out_vel,
-                          out_stride, nullptr, nullptr, stream);
+                          out_stride, nullptr, nullptr, 0, nullptr, stream);
+}
+
+extern "C" int vmvo_grid_search_chained_f32(vmvo_ctx* ctx, const vmvo_search_cfg* cfg,
+                                            int64_t n_windows, const int64_t* d_win_start,
+                                            const int32_t* d_win_len, const int32_t* d_win_drive,
+                                            const double* d_dt_per_drive, const float* d_vo,
+                                            const float* d_gps, const float* d_imu, int64_t n_runs,
+                                            const int64_t* d_run_offsets,
+                                            vmvo_window_result* d_results, double* d_out_poses,
+                                            double* d_out_steer, double* d_out_vel,
+                                            int32_t out_stride, void* stream) {
+  if (!d_run_offsets) return fail(ctx, VMVO_ERR_BAD_ARG, "d_run_offsets is NULL");
+  return grid_search_impl(ctx, cfg, n_windows, d_win_start, d_win_len, d_win_drive, d_dt_per_drive,
+                          d_vo, d_gps, d_imu, nullptr, d_results, d_out_poses, d_out_steer, d_out_vel,
+                          out_stride, nullptr, nullptr, n_runs, d_run_offsets, stream);
 }
 
 extern "C" int vmvo_grid_search_debug_f32(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n_windows,
@@ -1010,5 +1069,5 @@ extern "C" int vmvo_grid_search_debug_f32(vmvo_ctx* ctx, const vmvo_search_cfg* 
   if (!d_scan_cost || !d_scan_err) return fail(ctx, VMVO_ERR_BAD_ARG, "debug outputs are NULL");
   return grid_search_impl(ctx, cfg, n_windows, d_win_start, d_win_len, d_win_drive, d_dt_per_drive,
                           d_vo, d_gps, d_imu, d_seeds, d_results, nullptr, nullptr, nullptr, 0,
-                          d_scan_cost, d_scan_err, stream);
+                          d_scan_cost, d_scan_err, 0, nullptr, stream);
 }

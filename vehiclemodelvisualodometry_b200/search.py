@@ -222,7 +222,19 @@ def grid_search(cfg: SearchConfig, drives: DriveSet, plan: WindowPlan,
         if d_seeds.shape != (plan.n_windows, 2):
             raise ValueError("seeds must be [n_windows, 2]")
         d_seeds = d_seeds[lo:hi].contiguous()
-    if n:
+    if n and cfg.seed_mode == "chained":
+        # runs = the drives whose windows fall in [lo, hi); the range must not cut a drive
+        offs = [o for o in plan.window_offsets if lo <= o <= hi]
+        if not offs or offs[0] != lo or offs[-1] != hi:
+            raise ValueError("seed_mode 'chained' needs a window range aligned to whole drives")
+        runs = torch.tensor([o - lo for o in offs], dtype=torch.int64, device=dev)
+        ctx.check(ctx.lib.vmvo_grid_search_chained_f32(
+            ctx.handle, C.byref(c), n, _lib.ptr(plan.win_start[lo:hi]), _lib.ptr(plan.win_len[lo:hi]),
+            _lib.ptr(plan.win_drive[lo:hi]), _lib.ptr(drives.dt), _lib.ptr(drives.vo),
+            _lib.ptr(drives.gps), _lib.ptr(drives.imu), len(offs) - 1, _lib.ptr(runs),
+            _lib.ptr(results), _lib.ptr(so.poses), _lib.ptr(so.steer), _lib.ptr(so.vel), stride,
+            _lib.stream_ptr(dev)), "vmvo_grid_search_chained_f32")
+    elif n:
         ctx.check(ctx.lib.vmvo_grid_search_f32(
             ctx.handle, C.byref(c), n, _lib.ptr(plan.win_start[lo:hi]), _lib.ptr(plan.win_len[lo:hi]),
             _lib.ptr(plan.win_drive[lo:hi]), _lib.ptr(drives.dt), _lib.ptr(drives.vo),
