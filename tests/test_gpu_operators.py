@@ -173,3 +173,28 @@ def test_write_back_golden_reference_loop(cuda_device):
     np.testing.assert_allclose(traj[1], unhex(g["y"]), rtol=0, atol=1e-9)
     np.testing.assert_array_equal(traj[2], unhex(g["theta"]))
     np.testing.assert_array_equal(traj[3], unhex(g["velocity"]))
+
+
+@pytest.mark.parametrize("split", [False, True])
+def test_drive_pipeline_graph_replay(cuda_device, split):
+    """DrivePipeline (CUDA-graph replay of plan + search + write-back) equals the eager calls and
+    follows new data copied into the resident streams."""
+    from vehiclemodelvisualodometry_b200 import DrivePipeline
+
+    cfg = SearchConfig(grid_v=8, grid_s=8, window_frames=15)
+    a, b = synthetic_drives(2, 120, seed=61), synthetic_drives(2, 120, seed=62)
+    drives = DriveSet.from_arrays(list(a.time), [a.dt] * 2, vo=list(a.vo), gps=list(a.gps))
+    pipe = DrivePipeline(cfg, drives, split=split)
+    for batch in (a, b, a):
+        drives.vo.copy_(torch.from_numpy(batch.vo.reshape(-1, 4)))
+        drives.gps.copy_(torch.from_numpy(batch.gps.reshape(-1, 4)))
+        if split:
+            pipe.run_search()
+            pipe.run_write_back()
+        else:
+            pipe.run()
+        got_rec, got_traj = pipe.records.clone(), pipe.trajectory.clone()
+        so, traj, _ = optimize_drives(cfg, drives)
+        assert torch.equal(got_rec.view(torch.int32)[:, :3], so.results.view(torch.int32)[:, :3])
+        assert torch.equal(got_rec[:, 16:], so.results[:, 16:])     # costs, seeds, first pose
+        assert torch.equal(got_traj, traj)

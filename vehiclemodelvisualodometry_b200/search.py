@@ -158,10 +158,23 @@ class WindowPlan:
         return self.window_offsets[-1]
 
 
-def plan_windows(cfg: SearchConfig, drives: DriveSet) -> WindowPlan:
-    """a8 for every window of every drive (vmvo/schema.py:117-127, …v2.py:48)."""
+def plan_windows(cfg: SearchConfig, drives: DriveSet, into: Optional[WindowPlan] = None) -> WindowPlan:
+    """a8 for every window of every drive (vmvo/schema.py:117-127, …v2.py:48).
+
+    ``into``: a plan allocated by an earlier call for the same drive lengths; only the kernel
+    is launched (no allocation, no host-to-device copy), e.g. under CUDA-graph capture.
+    """
     ctx = _lib.context(drives.device.index)
     c = cfg.to_c()
+    if into is not None:
+        plan, n = into, into.n_windows
+        if n:
+            ctx.check(ctx.lib.vmvo_plan_windows(
+                ctx.handle, C.byref(c), drives.n_drives, _lib.ptr(drives.d_drive_offsets),
+                _lib.ptr(plan.d_window_offsets), n, _lib.ptr(drives.time), _lib.ptr(plan.win_start),
+                _lib.ptr(plan.win_len), _lib.ptr(plan.win_drive), _lib.stream_ptr(drives.device)),
+                "vmvo_plan_windows")
+        return plan
     woffs = [0]
     for d in range(drives.n_drives):
         woffs.append(woffs[-1] + cfg.window_count(drives.drive_offsets[d + 1] - drives.drive_offsets[d]))
@@ -227,7 +240,10 @@ def grid_search(cfg: SearchConfig, drives: DriveSet, plan: WindowPlan,
         offs = [o for o in plan.window_offsets if lo <= o <= hi]
         if not offs or offs[0] != lo or offs[-1] != hi:
             raise ValueError("seed_mode 'chained' needs a window range aligned to whole drives")
-        runs = torch.tensor([o - lo for o in offs], dtype=torch.int64, device=dev)
+        if lo == 0 and hi == plan.n_windows:
+            runs = plan.d_window_offsets          # no allocation: usable under graph capture
+        else:
+            runs = torch.tensor([o - lo for o in offs], dtype=torch.int64, device=dev)
         ctx.check(ctx.lib.vmvo_grid_search_chained_f32(
             ctx.handle, C.byref(c), n, _lib.ptr(plan.win_start[lo:hi]), _lib.ptr(plan.win_len[lo:hi]),
             _lib.ptr(plan.win_drive[lo:hi]), _lib.ptr(drives.dt), _lib.ptr(drives.vo),
@@ -264,7 +280,7 @@ def grid_search_debug(cfg: SearchConfig, drives: DriveSet, plan: WindowPlan,
 
 
 def write_back(cfg: SearchConfig, drives: DriveSet, plan: WindowPlan, results: torch.Tensor,
-               blend_gps: bool = True) -> torch.Tensor:
+               blend_gps: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """a12: float64 [4, F] = x, y, theta, velocity (optimize_trajectory_v2.py:32-33,122-137)."""
     ctx = _lib.context(drives.device.index)
     c = cfg.to_c()
@@ -272,7 +288,10 @@ def write_back(cfg: SearchConfig, drives: DriveSet, plan: WindowPlan, results: t
         raise ValueError("write_back copies the VO stream: drives.vo is required")
     if results.shape != (plan.n_windows, 64):
         raise ValueError("results must hold one record per planned window")
-    out = torch.empty((4, drives.n_frames), dtype=torch.float64, device=drives.device)
+    if out is None:
+        out = torch.empty((4, drives.n_frames), dtype=torch.float64, device=drives.device)
+    elif out.shape != (4, drives.n_frames) or out.dtype != torch.float64 or not out.is_contiguous():
+        raise ValueError("out must be a contiguous float64 [4, n_frames] tensor")
     gps = drives.gps if blend_gps else None
     ctx.check(ctx.lib.vmvo_write_back_f32(
         ctx.handle, C.byref(c), drives.n_drives, drives.n_frames, _lib.ptr(drives.d_drive_offsets),
@@ -290,6 +309,85 @@ def optimize_drives(cfg: SearchConfig, drives: DriveSet, plan: Optional[WindowPl
     so = grid_search(cfg, drives, plan, seeds=seeds)
     traj = write_back(cfg, drives, plan, so.results)
     return so, traj, plan
+
+
+class DrivePipeline:
+    """plan -> search -> write-back for one resident batch of drives, captured once as a CUDA
+    graph and replayed: three kernel launches and a memset per pass, no per-pass host work.
+
+    The pose streams and stamps are read from ``drives`` at replay time, so new data of the
+    same shape can be copied into ``drives.vo`` / ``.gps`` / ``.imu`` / ``.time`` between passes.
+    ``records`` (uint8 [n_windows, 64]) may be a slice of a larger gather buffer.
+    """
+
+    KERNELS_PER_PASS = 3
+
+    def __init__(self, cfg: SearchConfig, drives: DriveSet, blend_gps: bool = True,
+                 records: Optional[torch.Tensor] = None, use_graph: bool = True,
+                 split: bool = False):
+        if cfg.seed_mode == "given":
+            raise ValueError("DrivePipeline derives seeds from the data (seed_mode data / chained)")
+        self.cfg, self.drives, self.blend_gps = cfg, drives, blend_gps
+        self.plan = plan_windows(cfg, drives)
+        dev = drives.device
+        n = self.plan.n_windows
+        self.records = records if records is not None else torch.empty((n, 64), dtype=torch.uint8, device=dev)
+        self.trajectory = torch.empty((4, drives.n_frames), dtype=torch.float64, device=dev)
+        self.graphs = None
+        self._search()                                # eager warm-up: sets kernel attributes
+        self._write_back()
+        torch.cuda.synchronize(dev)
+        if use_graph:
+            # split: the search and the write-back are separate graphs so that a caller can put
+            # the record gather between them (bench.py, N > 1)
+            parts = [[self._search], [self._write_back]] if split else [[self._search, self._write_back]]
+            self.graphs = []
+            for fns in parts:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    for fn in fns:
+                        fn()
+                self.graphs.append(g)
+        self.split = split
+
+    def _search(self):
+        plan_windows(self.cfg, self.drives, into=self.plan)
+        grid_search(self.cfg, self.drives, self.plan, out=self.records)
+
+    def _write_back(self):
+        write_back(self.cfg, self.drives, self.plan, self.records, blend_gps=self.blend_gps,
+                   out=self.trajectory)
+
+    def run_search(self) -> torch.Tensor:
+        if self.graphs is None:
+            self._search()
+        elif self.split:
+            self.graphs[0].replay()
+        else:
+            raise RuntimeError("run_search needs split=True (or use_graph=False)")
+        return self.records
+
+    def run_write_back(self) -> torch.Tensor:
+        if self.graphs is None:
+            self._write_back()
+        elif self.split:
+            self.graphs[1].replay()
+        else:
+            raise RuntimeError("run_write_back needs split=True (or use_graph=False)")
+        return self.trajectory
+
+    def run(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        """One pass on the current stream; returns (records, trajectory) -- reused buffers."""
+        if self.graphs is None:
+            self._search()
+            self._write_back()
+        else:
+            for g in self.graphs:
+                g.replay()
+        return self.records, self.trajectory
+
+    def result_records(self) -> np.ndarray:
+        return self.records.cpu().numpy().view(_lib.RESULT_DTYPE).reshape(-1)
 
 
 def hypothesis_steps(cfg: SearchConfig, records: np.ndarray) -> int:
