@@ -23,8 +23,13 @@ CASES = {
 }
 
 
+@pytest.mark.parametrize("scan", ["fast", "generic"])
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_band_contains_float64_cost(cuda_device, name):
+def test_band_contains_float64_cost(cuda_device, name, scan, monkeypatch):
+    """scan = fast: the packed FP32x2 / rotation scan (used when there is no IMU term and
+    V_w >= 0); generic: the one-hypothesis-per-lane-slot scan (forced by a test knob)."""
+    if scan == "generic":
+        monkeypatch.setenv("VMVO_NO_FAST_SCAN", "1")
     cfg = CASES[name]
     spec = spec_of(cfg)
     n = 2 * cfg.horizon() + 12
@@ -51,5 +56,5 @@ def test_band_contains_float64_cost(cuda_device, name):
     assert worst <= 0.5, f"FP32 scan error reaches {worst:.3f} of the band"
     # ... and is not vacuous: few re-scores per window on ordinary data
     assert np.median(rec["n_rescored"]) <= 8, np.percentile(rec["n_rescored"], [50, 90, 100])
-    print(name, "worst |c32-c64|/band", worst, "rescored median/max", np.median(rec["n_rescored"]),
+    print(name, scan, "worst |c32-c64|/band", worst, "rescored median/max", np.median(rec["n_rescored"]),
           rec["n_rescored"].max())

@@ -38,6 +38,7 @@ struct SearchParams {
   int vd_cols;           // columns of the VD table (accelerations covered by one pass)
   int team_warps;        // warps per team (1, 2, 4 or 8)
   int cand_cap;          // candidate list entries per team (<= kCandPerWarp * team_warps)
+  int allow_fast;        // use the packed / rotation scan where its preconditions hold
   double w_vo, w_gps, w_imu, k_steer;
   double L, ratio, max_steer, max_accel, max_rate;
   double delta_max, kappa;     // kappa = 2*delta_max / sin(2*delta_max): tan's condition number
@@ -157,13 +158,20 @@ struct Band {
   __device__ __forceinline__ float err(float J) const { return fmaf(c1, sqrtf(J), fmaf(c2, J, c0)); }
 };
 
-__device__ __forceinline__ Band make_band(const BandWin& w, float vmax, float theta_tv, float tlmax) {
+// fast = the packed / rotation scan (scan_item_fast): headings are the affine form A_k + a_i*B_k
+// (error <= (eps_TL + 5u + k*u) * Theta', Theta' = sum (V_w*dt + |a|max*t*dt)*|TL|), half of the
+// sin/cos pairs come from one rotation of a MUFU pair by a MUFU angle.
+__device__ __forceinline__ Band make_band(const BandWin& w, float vmax, float theta_tv, float tlmax,
+                                          bool fast) {
   const float u = 5.9604644775390625e-8f;           // 2^-24
   const float SF = 2.0f;                            // safety factor on the whole bound
   const float dth = vmax * tlmax;                   // largest heading step
-  const float g = (w.eps_tl + u) * dth + u * theta_tv;        // heading error grows <= g per step
-  const float eps_trig = 4.76837158203125e-7f + 4.f * u * theta_tv;  // MUFU sin/cos, |x| <= theta_tv
-  const float q1 = vmax * (eps_trig + u) + 2.f * u * w.dmax + 2.f * u * w.dabmax;
+  // heading error grows <= g per step
+  const float g = fast ? u * theta_tv : (w.eps_tl + u) * dth + u * theta_tv;
+  const float mufu = 4.76837158203125e-7f + 4.f * u * theta_tv;  // MUFU sin/cos, |x| <= theta_tv
+  const float eps_trig = fast ? 2.f * mufu + 4.f * u : mufu;
+  const float head = fast ? vmax * (w.eps_tl + 5.f * u) * theta_tv : 0.f;
+  const float q1 = vmax * (eps_trig + u) + 2.f * u * w.dmax + 2.f * u * w.dabmax + head;
   const float q2 = vmax * g;
   const float e2pos = 3.f * (q1 * q1 * w.s2 + q2 * q2 * w.s4);
   const float ei = u * (w.imax + 3.1415927f) + (theta_tv * 0.15915494f + 1.f) * 1.75e-7f;
@@ -291,6 +299,93 @@ __device__ __forceinline__ void scan_item(int N, int gs, int vd_cols, int j, int
     if (DUAL) t = fmaf(wB, JB[c], t);
     if (IMU) t = fmaf(wI, JI[c], t);
     out.J[c] = t;
+  }
+  out.vmax = vmax;
+  out.theta_tv = tv;
+  out.tlmax = tlmax;
+}
+
+// ---- packed FP32x2 + rotation scan (C = 8, no IMU term, V_w >= 0) --------------------------------
+// Blackwell's FFMA2 / FADD2 / FMUL2 process two hypotheses per instruction.  While a hypothesis
+// is still moving its heading is affine in its acceleration, theta_k(i) = A_k(j) + a_i * B_k(j)
+// (after V clamps to zero the step length is zero and the heading no longer matters), so the
+// sin/cos of accelerations {0,1,4,5} of the chunk come from the SFU and those of {2,3,6,7} from one
+// rotation by 2*da*B_k: 10 MUFU and ~64 FP32-pipe instructions per 8 hypothesis-steps.
+__device__ __forceinline__ float2 pk(float a, float b) { return make_float2(a, b); }
+
+__device__ __forceinline__ void rot_pair(float2 c2, float2 s2, float cr, float sr, float2& co,
+                                         float2& so) {
+  co = __ffma2_rn(c2, pk(cr, cr), __fmul2_rn(s2, pk(-sr, -sr)));
+  so = __ffma2_rn(s2, pk(cr, cr), __fmul2_rn(c2, pk(sr, sr)));
+}
+
+template <bool DUAL>
+__device__ __forceinline__ void scan_item_fast(int N, int gs, int vd_cols, int j, int m0,
+                                               const float* __restrict__ TL,
+                                               const float* __restrict__ VD,
+                                               const float2* __restrict__ Df,
+                                               const float2* __restrict__ Dab, float wA, float wB,
+                                               float kJS, float vwdt, float dt2, float a0, float da,
+                                               float amax, ScanOut<8>& out) {
+  float2 ex[4], ey[4], JAx[4], JAy[4], JBx[4], JBy[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) ex[q] = ey[q] = JAx[q] = JAy[q] = JBx[q] = JBy[q] = pk(0.f, 0.f);
+  float A = 0.f, B = 0.f, vmax = 0.f, tv = 0.f, tlmax = 0.f;
+  const float a1 = a0 + da, a4 = fmaf(4.f, da, a0), a5 = fmaf(5.f, da, a0), da2 = da + da;
+  const float* tl = TL + j;
+  const float* vd = VD + m0;
+#pragma unroll 1
+  for (int k = 1; k <= N; ++k) {
+    const float tlk = tl[(k - 1) * gs];
+    const float4 va = *reinterpret_cast<const float4*>(vd + (k - 1) * vd_cols);
+    const float4 vb = *reinterpret_cast<const float4*>(vd + (k - 1) * vd_cols + 4);
+    const float2 d = Df[k];
+    float2 dab = pk(0.f, 0.f);
+    if (DUAL) dab = Dab[k];
+    const float kdt2 = (float)k * dt2;
+    A = fmaf(vwdt, tlk, A);
+    B = fmaf(kdt2, tlk, B);
+    // band statistics: heading bound of the fastest-changing hypothesis, largest step
+    tv = fmaf(fmaf(amax, kdt2, vwdt), fabsf(tlk), tv);
+    tlmax = fmaxf(tlmax, fabsf(tlk));
+    vmax = fmaxf(vmax, vb.w);
+    float s0, c0, s1, c1, s4, c4, s5, c5, sr, cr;
+    __sincosf(fmaf(a0, B, A), &s0, &c0);
+    __sincosf(fmaf(a1, B, A), &s1, &c1);
+    __sincosf(fmaf(a4, B, A), &s4, &c4);
+    __sincosf(fmaf(a5, B, A), &s5, &c5);
+    __sincosf(da2 * B, &sr, &cr);
+    float2 c2[4], s2[4];
+    c2[0] = pk(c0, c1);
+    s2[0] = pk(s0, s1);
+    c2[2] = pk(c4, c5);
+    s2[2] = pk(s4, s5);
+    rot_pair(c2[0], s2[0], cr, sr, c2[1], s2[1]);
+    rot_pair(c2[2], s2[2], cr, sr, c2[3], s2[3]);
+    const float2 v2[4] = {pk(va.x, va.y), pk(va.z, va.w), pk(vb.x, vb.y), pk(vb.z, vb.w)};
+    const float2 ndx = pk(-d.x, -d.x), ndy = pk(-d.y, -d.y);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      ex[q] = __ffma2_rn(v2[q], c2[q], __fadd2_rn(ex[q], ndx));
+      ey[q] = __ffma2_rn(v2[q], s2[q], __fadd2_rn(ey[q], ndy));
+      JAx[q] = __ffma2_rn(ex[q], ex[q], JAx[q]);
+      JAy[q] = __ffma2_rn(ey[q], ey[q], JAy[q]);
+      if (DUAL) {
+        const float2 bx = __fadd2_rn(ex[q], pk(dab.x, dab.x)), by = __fadd2_rn(ey[q], pk(dab.y, dab.y));
+        JBx[q] = __ffma2_rn(bx, bx, JBx[q]);
+        JBy[q] = __ffma2_rn(by, by, JBy[q]);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float t0 = fmaf(wA, JAx[q].x + JAy[q].x, kJS), t1 = fmaf(wA, JAx[q].y + JAy[q].y, kJS);
+    if (DUAL) {
+      t0 = fmaf(wB, JBx[q].x + JBy[q].x, t0);
+      t1 = fmaf(wB, JBx[q].y + JBy[q].y, t1);
+    }
+    out.J[2 * q] = t0;
+    out.J[2 * q + 1] = t1;
   }
   out.vmax = vmax;
   out.theta_tv = tv;
@@ -731,9 +826,27 @@ vmvo_window_search_kernel(const SearchParams p) {
         if (q < p.n_items) {
           ic = q / p.gs;
           j = q - ic * p.gs;
-          scan_item<C, DUAL, IMU>(N, p.gs, p.vd_cols, j, (ic - ic0) * kC, TL, VD, Df, Dab, fI, wA, wB, wI,
-                               ksteer ? JS[j] : 0.f, so);
-          band = make_band(bw, so.vmax, so.theta_tv, so.tlmax);
+          bool fast = false;
+          if constexpr (C == 8 && !IMU) {
+            fast = p.allow_fast && v_seed >= 0.0;   // affine headings need V to clamp only once
+            if (fast) {
+              // a_i by multiplication with 1/(G-1): last-bit differences from the spec's
+              // division are far below the FP32 resolution this scan works at
+              const double inv = p.gv > 1 ? p.max_accel / (double)(p.gv - 1) : 0.0;
+              const int i0 = ic * kC;
+              const double a0d = inv * (double)(2 * i0 - (p.gv - 1));
+              const double a7d = inv * (double)(2 * (i0 + 7) - (p.gv - 1));
+              const double dtd = dt * dt;
+              scan_item_fast<DUAL>(N, p.gs, p.vd_cols, j, (ic - ic0) * kC, TL, VD, Df, Dab, wA, wB,
+                                   ksteer ? JS[j] : 0.f, (float)(v_seed * dt), (float)dtd,
+                                   (float)a0d, (float)(2.0 * inv),
+                                   (float)fmax(fabs(a0d), fabs(a7d)), so);
+            }
+          }
+          if (!fast)
+            scan_item<C, DUAL, IMU>(N, p.gs, p.vd_cols, j, (ic - ic0) * kC, TL, VD, Df, Dab, fI, wA, wB,
+                                    wI, ksteer ? JS[j] : 0.f, so);
+          band = make_band(bw, so.vmax, so.theta_tv, so.tlmax, fast);
 #pragma unroll
           for (int c = 0; c < kC; ++c)
             if (ic * kC + c < p.gv) valid |= 1u << c;
@@ -963,6 +1076,7 @@ retry_c:
   }
   p.team_warps = tw;
   p.cand_cap = kCandPerWarp * tw;
+  p.allow_fast = getenv("VMVO_NO_FAST_SCAN") ? 0 : 1;   // test knob: force the generic scan
   if (const char* ov = getenv("VMVO_CAND_CAP")) {  // test knob: forces the list-flush path
     const int v = atoi(ov);
     if (v >= 1 && v < p.cand_cap) p.cand_cap = v;
