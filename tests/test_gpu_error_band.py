@@ -28,8 +28,7 @@ CASES = {
 def test_band_contains_float64_cost(cuda_device, name, scan, monkeypatch):
     """scan = fast: the packed FP32x2 / rotation scan (used when there is no IMU term and
     V_w >= 0); generic: the one-hypothesis-per-lane-slot scan (forced by a test knob)."""
-    if scan == "generic":
-        monkeypatch.setenv("VMVO_NO_FAST_SCAN", "1")
+    monkeypatch.setenv("VMVO_FAST_SCAN", "1" if scan == "fast" else "0")
     cfg = CASES[name]
     spec = spec_of(cfg)
     n = 2 * cfg.horizon() + 12

@@ -63,9 +63,11 @@ def test_search_matches_oracle(cuda_device, name):
         np.testing.assert_allclose(vel[w, :N], r.vel, rtol=1e-13, atol=1e-13)
 
 
-def test_generic_scan_path_matches_oracle(cuda_device, monkeypatch):
-    """The generic scan (IMU term, negative seeds, or the test knob) on a plain VO search."""
-    monkeypatch.setenv("VMVO_NO_FAST_SCAN", "1")
+@pytest.mark.parametrize("fast", ["0", "1"])
+def test_both_scan_paths_match_oracle(cuda_device, monkeypatch, fast):
+    """Both scans (the packed / rotation one is the default on large grids only) on a 32x32 VO
+    search."""
+    monkeypatch.setenv("VMVO_FAST_SCAN", fast)
     cfg = SearchConfig(grid_v=32, grid_s=32, window_frames=30)
     batch = synthetic_drives(1, 110, seed=71)
     drives = DriveSet.from_arrays([batch.time[0]], [batch.dt], vo=[batch.vo[0]])
@@ -73,9 +75,10 @@ def test_generic_scan_path_matches_oracle(cuda_device, monkeypatch):
     assert_records_match(rec, oracle_windows(cfg, batch.time[0], batch.dt, batch.vo[0]))
 
 
-def test_negative_speed_seed_uses_generic_scan(cuda_device):
-    """V_w < 0 (a caller-supplied seed): hypotheses start clamped and move later, so the
-    affine-heading scan does not apply; results must still match."""
+def test_negative_speed_seed_uses_generic_scan(cuda_device, monkeypatch):
+    monkeypatch.setenv("VMVO_FAST_SCAN", "1")
+    # V_w < 0 (a caller-supplied seed): hypotheses start clamped and move later, so the
+    # affine-heading scan does not apply; results must still match
     cfg = SearchConfig(grid_v=16, grid_s=16, window_frames=20, seed_mode="given")
     batch = synthetic_drives(1, 70, seed=72)
     seeds = np.tile([[-2.0, 15.0]], (30, 1))

@@ -23,9 +23,8 @@
 namespace vmvo {
 
 constexpr int kCandPerWarp = 128;  // candidate list entries per team warp (flushed when full)
-constexpr int kMaxWarps = 8;       // warps per CTA and largest team
-constexpr int kCtaThreads = 32 * kMaxWarps;
-constexpr int kHeaderBytes = 704;
+constexpr int kMaxWarps = 16;      // most warps per CTA (and per team) of any kernel variant
+constexpr int kHeaderBytes = 1152;
 
 struct SearchParams {
   int gv, gs;
@@ -106,7 +105,7 @@ struct SmemHeader {
   uint64_t mbar[2];
   long long wid[2];
   WinInfo wi;
-  float red[32];
+  float red[3 * kMaxWarps];
   double bcost[kMaxWarps];
   double bpose[kMaxWarps][3];
   int bh[kMaxWarps];
@@ -393,8 +392,11 @@ __device__ __forceinline__ void scan_item_fast(int N, int gs, int vd_cols, int j
 }
 
 // ---- the kernel -----------------------------------------------------------------------------
-template <int C, int MINB, bool DUAL, bool IMU>
-__global__ void __launch_bounds__(kCtaThreads, MINB)
+// WARPS warps per CTA, MINB CTAs per SM.  Only <8, 2> (128 registers per thread, 16 warps/SM) is
+// instantiated: at 80 or 64 registers (24 / 32 warps/SM) both scan loops spill inside the loop and
+// every such variant measured slower (profiles/README.md).
+template <int C, int WARPS, int MINB, bool DUAL, bool IMU>
+__global__ void __launch_bounds__(32 * WARPS, MINB)
 vmvo_window_search_kernel(const SearchParams p) {
   constexpr int kC = C;
   extern __shared__ __align__(1024) unsigned char smem_cta[];
@@ -722,8 +724,8 @@ vmvo_window_search_kernel(const SearchParams p) {
       }
       if (lane == 0) {
         hd->red[warp] = dmax;
-        hd->red[8 + warp] = dabmax;
-        hd->red[16 + warp] = imax;
+        hd->red[kMaxWarps + warp] = dabmax;
+        hd->red[2 * kMaxWarps + warp] = imax;
       }
     }
     team.sync();   // red[] complete
@@ -731,8 +733,8 @@ vmvo_window_search_kernel(const SearchParams p) {
     dmax = dabmax = imax = 0.f;
     for (int q = 0; q < NW; ++q) {
       dmax = fmaxf(dmax, hd->red[q]);
-      dabmax = fmaxf(dabmax, hd->red[8 + q]);
-      imax = fmaxf(imax, hd->red[16 + q]);
+      dabmax = fmaxf(dabmax, hd->red[kMaxWarps + q]);
+      imax = fmaxf(imax, hd->red[2 * kMaxWarps + q]);
     }
     const int status = (N <= 0 ? VMVO_WIN_EMPTY : 0) | (bad ? VMVO_WIN_NONFINITE : 0);
     WinInfo wi = hd->wi;
@@ -978,12 +980,13 @@ vmvo_window_search_kernel(const SearchParams p) {
   }
 }
 
-template <int C, int MINB, bool DUAL, bool IMU>
+template <int C, int WARPS, int MINB, bool DUAL, bool IMU>
 static int launch_search(vmvo_ctx* ctx, const SearchParams& p, cudaStream_t st) {
-  auto kern = vmvo_window_search_kernel<C, MINB, DUAL, IMU>;
+  auto kern = vmvo_window_search_kernel<C, WARPS, MINB, DUAL, IMU>;
+  constexpr int kCtaThreads = 32 * WARPS;
   const SmemLayout lay(p.maxp, p.gs, p.vd_cols, p.team_warps, p.load_vo + p.load_gps, DUAL, IMU,
                        p.target_mode == VMVO_TARGET_TRAVERSE);
-  const int teams = kMaxWarps / p.team_warps;
+  const int teams = WARPS / p.team_warps;
   const int smem = lay.total * teams;
   if (smem > 200 * 1024)
     return fail(ctx, VMVO_ERR_UNSUPPORTED,
@@ -1039,22 +1042,16 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
   if ((d_dbg_cost == nullptr) != (d_dbg_err == nullptr))
     return fail(ctx, VMVO_ERR_BAD_ARG, "debug outputs come in pairs");
 
-  // hypotheses per thread: 8 (128 registers, two CTAs per SM).  The 4-per-thread variant (64
-  // registers, four CTAs per SM) measured 10 % slower on the 32x32 grid (profiles/README.md)
-  // and stays behind a tuning knob.
-  int kC = 8;
-  if (const char* ov = getenv("VMVO_HYP_PER_THREAD")) {
-    if (atoi(ov) == 4) kC = 4;
-  }
+  constexpr int kC = 8;
+  const int cta_warps = 8;
   SearchParams p;
   p.gv = cfg->grid_v;
   p.gs = cfg->grid_s;
-retry_c:
   p.n_ic = (p.gv + kC - 1) / kC;
   p.n_items = p.n_ic * p.gs;
   // team size: about two passes of 32 items per warp (measured best on 32x32: two warps)
   int tw = 1;
-  while (tw < kMaxWarps && p.n_items > tw * 32 * 2) tw *= 2;
+  while (tw < cta_warps && p.n_items > tw * 32 * 2) tw *= 2;
   // ... unless the per-team tables would not leave room for two CTAs per SM
   for (;;) {
     const int th = tw * 32;
@@ -1062,21 +1059,19 @@ retry_c:
     if (ch > p.n_ic) ch = p.n_ic;
     const SmemLayout probe(cfg->max_window_poses, p.gs, ch * kC, tw, (int)load_vo + (int)load_gps,
                            use_vo && use_gps, use_imu, cfg->target_mode == VMVO_TARGET_TRAVERSE);
-    const int budget = kC == 4 ? 54 * 1024 : 110 * 1024;
-    if (probe.total * (kMaxWarps / tw) <= budget) break;
-    if (tw == kMaxWarps) {
-      if (kC == 4) { kC = 8; goto retry_c; }   // tables too large for four CTAs per SM
-      break;
-    }
+    if (tw == cta_warps || probe.total * (cta_warps / tw) <= 110 * 1024) break;
     tw *= 2;
   }
   if (const char* ov = getenv("VMVO_TEAM_WARPS")) {  // tuning knob, not part of the ABI
     const int v = atoi(ov);
-    if (v == 1 || v == 2 || v == 4 || v == 8) tw = v;
+    if ((v == 1 || v == 2 || v == 4 || v == 8 || v == 16) && v <= cta_warps) tw = v;
   }
   p.team_warps = tw;
   p.cand_cap = kCandPerWarp * tw;
-  p.allow_fast = getenv("VMVO_NO_FAST_SCAN") ? 0 : 1;   // test knob: force the generic scan
+  // the packed / rotation scan pays on large grids (+11 % on 256x256) and not on small ones
+  // (-2 % on 32x32, where its wider band costs more float64 re-scores than the loop saves)
+  p.allow_fast = p.n_items >= 1024;
+  if (const char* ov = getenv("VMVO_FAST_SCAN")) p.allow_fast = atoi(ov) != 0;   // test knob
   if (const char* ov = getenv("VMVO_CAND_CAP")) {  // test knob: forces the list-flush path
     const int v = atoi(ov);
     if (v >= 1 && v < p.cand_cap) p.cand_cap = v;
@@ -1134,12 +1129,12 @@ retry_c:
   p.work_counter = counter;
 
   const bool dual = use_vo && use_gps;
-#define VMVO_LAUNCH(CC, MB)                                                              \
-  (dual ? (use_imu ? launch_search<CC, MB, true, true>(ctx, p, st)                       \
-                   : launch_search<CC, MB, true, false>(ctx, p, st))                     \
-        : (use_imu ? launch_search<CC, MB, false, true>(ctx, p, st)                      \
-                   : launch_search<CC, MB, false, false>(ctx, p, st)))
-  return kC == 4 ? VMVO_LAUNCH(4, 4) : VMVO_LAUNCH(8, 2);
+#define VMVO_LAUNCH(W)                                                                   \
+  (dual ? (use_imu ? launch_search<8, W, 2, true, true>(ctx, p, st)                      \
+                   : launch_search<8, W, 2, true, false>(ctx, p, st))                    \
+        : (use_imu ? launch_search<8, W, 2, false, true>(ctx, p, st)                     \
+                   : launch_search<8, W, 2, false, false>(ctx, p, st)))
+  return VMVO_LAUNCH(8);
 #undef VMVO_LAUNCH
 }
 
