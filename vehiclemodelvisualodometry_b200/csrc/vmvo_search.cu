@@ -996,6 +996,10 @@ static int launch_search(vmvo_ctx* ctx, const SearchParams& p, cudaStream_t st) 
   int per_sm = 0;
   VMVO_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kCtaThreads, smem));
   if (per_sm < 1) return fail(ctx, VMVO_ERR_CUDA, "search kernel does not fit on an SM");
+  if (const char* ov = getenv("VMVO_MAX_CTAS_PER_SM")) {  // experiment knob
+    const int v = atoi(ov);
+    if (v >= 1 && v < per_sm) per_sm = v;
+  }
   long long grid = (long long)ctx->sm_count * per_sm;
   const long long items = p.run_offsets ? p.n_runs : p.n_windows;
   const long long need = (items + teams - 1) / teams;
