@@ -161,27 +161,41 @@ def run_b200(args):
     plan = plan_windows(cfg, drives)
     n_win = plan.n_windows
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # 2x the 126 MB L2
-    gathered = torch.empty((world * n_win, 64), dtype=torch.uint8, device=dev)
-    local = gathered[rank * n_win:(rank + 1) * n_win]
-
+    # record buffers double as the send buffers of the gather; two sets so that the gather of
+    # pass s can still be in flight while pass s+1 is searched
+    n_buf = 2 if world > 1 else 1
+    gathered = [torch.empty((world * n_win, 64), dtype=torch.uint8, device=dev) for _ in range(n_buf)]
+    local = [g[rank * n_win:(rank + 1) * n_win] for g in gathered]
     # the public batched API: plan + search + write-back captured once as CUDA graphs
-    pipe = DrivePipeline(cfg, drives, blend_gps=False, records=local, split=world > 1)
+    pipes = [DrivePipeline(cfg, drives, blend_gps=False, records=local[b], split=world > 1)
+             for b in range(n_buf)]
+    pipe = pipes[0]
+    state = {"n": 0, "work": None}
 
     def step():
         if world == 1:
             return pipe.run()
-        pipe.run_search()
-        # the only exchange of the path: per-window records to every rank; it runs on NCCL's
-        # stream while the write-back (which needs the local records only) proceeds
-        work = dist.all_gather_into_tensor(gathered, local, async_op=True)
-        traj = pipe.run_write_back()
-        work.wait()
-        return local, traj
+        b = state["n"] & 1
+        state["n"] += 1
+        pipes[b].run_search()
+        if state["work"] is not None:      # the previous pass's gather had this search to hide behind
+            state["work"].wait()
+        # the only exchange of the path: per-window records to every rank, on NCCL's stream,
+        # while the write-back (which needs the local records only) and the next search proceed
+        state["work"] = dist.all_gather_into_tensor(gathered[b], local[b], async_op=True)
+        traj = pipes[b].run_write_back()
+        return local[b], traj
+
+    def drain():
+        if state["work"] is not None:
+            state["work"].wait()
+            state["work"] = None
 
     def timed(fn, k, w):
         for _ in range(w):
             flush.zero_()
             fn()
+        drain()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -194,6 +208,11 @@ def run_b200(args):
             fn()
             b.record()
             evs.append((a, b))
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        drain()          # the last gather completes inside the timed total
+        b.record()
+        evs.append((a, b))
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -212,6 +231,7 @@ def run_b200(args):
     # graph replays do not pass through the library's launch counter: count the captured kernels
     launches = DrivePipeline.KERNELS_PER_PASS * args.steps
     step()
+    drain()
     torch.cuda.synchronize()
     rec = pipe.result_records()
     hsteps = int(cfg.grid_v) * int(cfg.grid_s) * int(rec["n_steps"].astype(np.int64).sum())
@@ -219,7 +239,7 @@ def run_b200(args):
     value = hsteps * world / (ms_per_step * 1e-3)
 
     # search kernel alone (the dominant kernel): average launch duration for the roofline
-    kern_ms = timed(lambda: grid_search(cfg, drives, plan, out=local), args.steps, 2) / args.steps
+    kern_ms = timed(lambda: grid_search(cfg, drives, plan, out=local[0]), args.steps, 2) / args.steps
 
     # end to end through the public API with HOST buffers: H2D of the pose stream and stamps,
     # plan + search + write-back, D2H of the records and the written-back trajectory
