@@ -194,6 +194,31 @@ int vmvo_time_extent_f64(vmvo_ctx* ctx, int64_t n, const double* d_time, double 
 int vmvo_traverse_f64(vmvo_ctx* ctx, int32_t n, const double* d_xy, double D, int32_t* d_keep,
                       int32_t* d_count, void* stream);
 
+/* ---- next row: trajectory pre-processing, batched over drives ---------------
+ * All arrays float64, drives concatenated, d_offsets[n_drives + 1] in frames.                */
+/* smoothen_traj (vmvo/utils/trajectory.py:68-99): trailing moving average, per drive.       */
+int vmvo_smooth_f64(vmvo_ctx* ctx, int32_t n_drives, int64_t total_frames, const int64_t* d_offsets,
+                    const double* d_x, const double* d_y, int32_t window, double* d_out_x,
+                    double* d_out_y, void* stream);
+/* process_vo_trajectory (vmvo/utils/trajectory.py:13-65): d_rot [frames][9] row-major 3x3,
+ * d_stamp_ms the Timestamp column.  Outputs [frames] each.                                   */
+int vmvo_vo_prepare_f64(vmvo_ctx* ctx, int32_t n_drives, int64_t total_frames,
+                        const int64_t* d_offsets, const double* d_x, const double* d_y,
+                        const double* d_rot, const double* d_stamp_ms, double scale, int32_t window,
+                        double* d_out_x, double* d_out_y, double* d_out_theta, double* d_out_vel,
+                        double* d_out_time, void* stream);
+/* process_gps_trajectory (vmvo/utils/trajectory.py:177-335, with geodetic_to_euclidean
+ * :120-174).  A drive of n fixes yields n + 1 points (the reference's leading duplicate of the
+ * origin): outputs are [total_frames + n_drives], drive d starting at d_offsets[d] + d; theta has
+ * n valid entries per drive (NaN in the last slot).  d_status[d] = 1 where the reference would
+ * raise IndexError (log ending on a fresh fix).  d_scratch: vmvo_gps_prepare_scratch_bytes.   */
+int64_t vmvo_gps_prepare_scratch_bytes(int64_t total_frames, int32_t n_drives);
+int vmvo_gps_prepare_f64(vmvo_ctx* ctx, int32_t n_drives, int64_t total_frames,
+                         const int64_t* d_offsets, const double* d_lat, const double* d_lon,
+                         const double* d_speed, const double* d_stamp_ms, int32_t window,
+                         void* d_scratch, double* d_out_x, double* d_out_y, double* d_out_theta,
+                         double* d_out_vel, double* d_out_time, int32_t* d_status, void* stream);
+
 /* ---- measurement helpers ------------------------------------------------------------ */
 /* Issue-rate microbenchmarks used for the roofline denominators (bench.py): each thread
  * runs `iters` dependent-free MUFU (kind 0: sin+cos pairs), FFMA (kind 1) or DFMA (kind 2)

@@ -75,6 +75,12 @@ _SIGNATURES = {
     "vmvo_extract_window_f64": (C.c_int, [_c_vp, _c_i32, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),
     "vmvo_time_extent_f64": (C.c_int, [_c_vp, _c_i64, _c_vp, _c_f64, _c_f64, _c_vp, _c_vp]),
     "vmvo_traverse_f64": (C.c_int, [_c_vp, _c_i32, _c_vp, _c_f64, _c_vp, _c_vp, _c_vp]),
+    "vmvo_smooth_f64": (C.c_int, [_c_vp, _c_i32, _c_i64, _c_vp, _c_vp, _c_vp, _c_i32, _c_vp, _c_vp, _c_vp]),
+    "vmvo_vo_prepare_f64": (C.c_int, [_c_vp, _c_i32, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_f64,
+                                      _c_i32, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),
+    "vmvo_gps_prepare_scratch_bytes": (_c_i64, [_c_i64, _c_i32]),
+    "vmvo_gps_prepare_f64": (C.c_int, [_c_vp, _c_i32, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i32,
+                                       _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),
     "vmvo_peak_probe": (C.c_int, [_c_vp, _c_i32, _c_i32, _c_i32, _c_i32, _c_vp, _c_vp]),
     "vmvo_launch_count": (_c_i64, [_c_vp]),
 }

@@ -9,7 +9,7 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libvmvo_b200.so")
-SOURCES = ["vmvo_search.cu", "vmvo_aux.cu"]
+SOURCES = ["vmvo_search.cu", "vmvo_aux.cu", "vmvo_prep.cu"]
 HEADERS = ["vmvo_device.cuh", "vmvo_internal.h", os.path.join("..", "..", "include", "vmvo_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
