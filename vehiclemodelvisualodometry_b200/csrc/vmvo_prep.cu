@@ -96,39 +96,59 @@ __global__ void gps_delta_kernel(int n_drives, const long long* off, long long t
 }
 
 // per drive, sequential by definition: the cumulative path (n+1 points, a leading duplicate of
-// the origin) and the de-duplication state machine (vmvo/utils/trajectory.py:206-216, 243-300)
+// the origin) and the de-duplication state machine (vmvo/utils/trajectory.py:206-216, 243-300).
+// One warp per drive: 32 deltas are loaded coalesced, every lane walks the same dependent chain of
+// additions (values broadcast by shuffle), lane l keeps point l of the batch and the stores are
+// coalesced again; the segment table of a finished run of repeated fixes is filled by all lanes.
 __global__ void gps_scan_kernel(int n_drives, const long long* off, long long total, const double* dxy,
                                 double* X, double* Y, int* seg_lo, int* seg_hi, int* status) {
-  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (d >= n_drives) return;
   const long long f0 = off[d], n = off[d + 1] - f0;
   const long long o0 = f0 + d;          // outputs hold n + 1 points per drive
   const long long m = n + 1;
-  X[o0] = 0.0;
-  Y[o0] = 0.0;
-  for (long long i = 0; i < n; ++i) {
-    X[o0 + i + 1] = dadd(dxy[f0 + i], X[o0 + i]);
-    Y[o0 + i + 1] = dadd(dxy[total + f0 + i], Y[o0 + i]);
+  if (lane == 0) {
+    X[o0] = 0.0;
+    Y[o0] = 0.0;
+    seg_lo[o0] = 0;
+    seg_hi[o0] = 0;
   }
-  int st = 0;
+  double xc = 0.0, yc = 0.0;            // point i (replicated in every lane)
+  double xl = 0.0, yl = 0.0;            // point `last`
   long long last = 0;
-  seg_lo[o0] = 0;
-  seg_hi[o0] = 0;
-  for (long long i = 1; i < m; ++i) {
-    if (X[o0 + last] != X[o0 + i] || Y[o0 + last] != Y[o0 + i]) {
-      if (i == n) st = 1;   // the reference indexes velocity[n] here: IndexError
-      for (long long j = last + 1; j <= i; ++j) {
-        seg_lo[o0 + j] = (int)last;
-        seg_hi[o0 + j] = (int)i;
+  int st = 0;
+  for (long long base = 0; base < n; base += 32) {
+    const long long i0 = base + lane;
+    const double ddx = i0 < n ? dxy[f0 + i0] : 0.0, ddy = i0 < n ? dxy[total + f0 + i0] : 0.0;
+    double mx = 0.0, my = 0.0;
+    const int cnt = (int)(n - base < 32 ? n - base : 32);
+    for (int l = 0; l < cnt; ++l) {
+      xc = dadd(__shfl_sync(FULL, ddx, l), xc);      // x[i+1] = dx_i + x[i]
+      yc = dadd(__shfl_sync(FULL, ddy, l), yc);
+      if (l == lane) { mx = xc; my = yc; }
+      const long long i = base + l + 1;              // index of the point just produced
+      if (xl != xc || yl != yc) {                    // warp-uniform
+        if (i == n) st = 1;   // the reference indexes velocity[n] here: IndexError
+        for (long long j = last + 1 + lane; j <= i; j += 32) {
+          seg_lo[o0 + j] = (int)last;
+          seg_hi[o0 + j] = (int)i;
+        }
+        last = i;
+        xl = xc;
+        yl = yc;
       }
-      last = i;
+    }
+    if (i0 < n) {
+      X[o0 + i0 + 1] = mx;
+      Y[o0 + i0 + 1] = my;
     }
   }
-  for (long long j = last + 1; j < m; ++j) {   // "interpolate the last few points"
+  for (long long j = last + 1 + lane; j < m; j += 32) {   // "interpolate the last few points"
     seg_lo[o0 + j] = (int)last;
     seg_hi[o0 + j] = -1;
   }
-  status[d] = st;
+  if (lane == 0) status[d] = st;
 }
 
 __global__ void gps_interp_kernel(int n_drives, const long long* off, long long total_out,
@@ -286,8 +306,8 @@ extern "C" int vmvo_gps_prepare_f64(vmvo_ctx* ctx, int32_t n_drives, int64_t tot
                                                            dxy, time);
   int rc = check_launch(ctx, "gps_delta_kernel");
   if (rc) return rc;
-  gps_scan_kernel<<<blocks_for(n_drives, 32, 65535), 32, 0, st>>>(n_drives, off, F, dxy, X, Y, seg_lo,
-                                                                 seg_hi, d_status);
+  gps_scan_kernel<<<blocks_for((long long)n_drives * 32, 128, 1 << 30), 128, 0, st>>>(
+      n_drives, off, F, dxy, X, Y, seg_lo, seg_hi, d_status);
   rc = check_launch(ctx, "gps_scan_kernel");
   if (rc) return rc;
   gps_interp_kernel<<<blocks_for(M, 256, cap), 256, 0, st>>>(n_drives, off, M, X, Y, d_speed, time,

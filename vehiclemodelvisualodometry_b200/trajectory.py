@@ -58,17 +58,49 @@ def smoothen_traj(trajectory, window_size=3):
     return np.stack([sx, sy], axis=1)
 
 
+def vo_prepare_device(d_off: torch.Tensor, n_drives: int, total: int, dx, dy, drot, dstamp,
+                      scale: float = 0.25, window: int = 20, out: Optional[torch.Tensor] = None):
+    """Device-resident process_vo_trajectory: float64 CUDA tensors in, float64 [5, total] out
+    (rows x, y, theta, velocity, time)."""
+    dev = dx.device
+    ctx = _lib.context(dev.index)
+    if out is None:
+        out = torch.empty((5, total), dtype=torch.float64, device=dev)
+    ctx.check(ctx.lib.vmvo_vo_prepare_f64(
+        ctx.handle, n_drives, total, _lib.ptr(d_off), _lib.ptr(dx), _lib.ptr(dy), _lib.ptr(drot),
+        _lib.ptr(dstamp), float(scale), int(window), _lib.ptr(out[0]), _lib.ptr(out[1]), _lib.ptr(out[2]),
+        _lib.ptr(out[3]), _lib.ptr(out[4]), _lib.stream_ptr(dev)), "vmvo_vo_prepare_f64")
+    return out
+
+
+def gps_prepare_device(d_off: torch.Tensor, n_drives: int, total: int, dlat, dlon, dspeed, dstamp,
+                       window: int = 20, out: Optional[torch.Tensor] = None,
+                       scratch: Optional[torch.Tensor] = None, status: Optional[torch.Tensor] = None):
+    """Device-resident process_gps_trajectory: float64 [5, total + n_drives] out (drive d starts at
+    offset[d] + d) and int32 status [n_drives]."""
+    dev = dlat.device
+    ctx = _lib.context(dev.index)
+    if out is None:
+        out = torch.empty((5, total + n_drives), dtype=torch.float64, device=dev)
+    if status is None:
+        status = torch.zeros(n_drives, dtype=torch.int32, device=dev)
+    if scratch is None:
+        scratch = torch.empty(int(ctx.lib.vmvo_gps_prepare_scratch_bytes(total, n_drives)),
+                              dtype=torch.uint8, device=dev)
+    ctx.check(ctx.lib.vmvo_gps_prepare_f64(
+        ctx.handle, n_drives, total, _lib.ptr(d_off), _lib.ptr(dlat), _lib.ptr(dlon), _lib.ptr(dspeed),
+        _lib.ptr(dstamp), int(window), _lib.ptr(scratch), _lib.ptr(out[0]), _lib.ptr(out[1]),
+        _lib.ptr(out[2]), _lib.ptr(out[3]), _lib.ptr(out[4]), _lib.ptr(status), _lib.stream_ptr(dev)),
+        "vmvo_gps_prepare_f64")
+    return out, status, scratch
+
+
 def vo_prepare_batch(x, y, rot, stamp_ms, scale: float = 0.25, window: int = 20):
     """Batched process_vo_trajectory: lists of per-drive arrays -> list of dicts of columns."""
     dev = _device()
-    ctx = _lib.context(dev.index)
     offs, d_off = _offsets([len(a) for a in x], dev)
     dx, dy, dr, dt = _cat(x, dev), _cat(y, dev), _cat(rot, dev, 9), _cat(stamp_ms, dev)
-    out = torch.empty((5, offs[-1]), dtype=torch.float64, device=dev)
-    ctx.check(ctx.lib.vmvo_vo_prepare_f64(
-        ctx.handle, len(offs) - 1, offs[-1], _lib.ptr(d_off), _lib.ptr(dx), _lib.ptr(dy), _lib.ptr(dr),
-        _lib.ptr(dt), float(scale), int(window), _lib.ptr(out[0]), _lib.ptr(out[1]), _lib.ptr(out[2]),
-        _lib.ptr(out[3]), _lib.ptr(out[4]), _lib.stream_ptr(dev)), "vmvo_vo_prepare_f64")
+    out = vo_prepare_device(d_off, len(offs) - 1, offs[-1], dx, dy, dr, dt, scale, window)
     o = out.cpu().numpy()
     names = ("x", "y", "theta", "velocity", "time")
     return [{k: o[c, a:b] for c, k in enumerate(names)} for a, b in zip(offs, offs[1:])]
@@ -77,18 +109,11 @@ def vo_prepare_batch(x, y, rot, stamp_ms, scale: float = 0.25, window: int = 20)
 def gps_prepare_batch(lat, lon, speed, stamp_ms, window: int = 20):
     """Batched process_gps_trajectory; a drive of n fixes yields n + 1 points and n headings."""
     dev = _device()
-    ctx = _lib.context(dev.index)
     lens = [len(a) for a in lat]
     offs, d_off = _offsets(lens, dev)
     D, F = len(lens), offs[-1]
     dla, dlo, dsp, dst = _cat(lat, dev), _cat(lon, dev), _cat(speed, dev), _cat(stamp_ms, dev)
-    out = torch.empty((5, F + D), dtype=torch.float64, device=dev)
-    status = torch.zeros(D, dtype=torch.int32, device=dev)
-    scratch = torch.empty(int(ctx.lib.vmvo_gps_prepare_scratch_bytes(F, D)), dtype=torch.uint8, device=dev)
-    ctx.check(ctx.lib.vmvo_gps_prepare_f64(
-        ctx.handle, D, F, _lib.ptr(d_off), _lib.ptr(dla), _lib.ptr(dlo), _lib.ptr(dsp), _lib.ptr(dst),
-        int(window), _lib.ptr(scratch), _lib.ptr(out[0]), _lib.ptr(out[1]), _lib.ptr(out[2]),
-        _lib.ptr(out[3]), _lib.ptr(out[4]), _lib.ptr(status), _lib.stream_ptr(dev)), "vmvo_gps_prepare_f64")
+    out, status, _ = gps_prepare_device(d_off, D, F, dla, dlo, dsp, dst, window)
     o, st = out.cpu().numpy(), status.cpu().numpy()
     res = []
     for d in range(D):
