@@ -95,11 +95,14 @@ __global__ void gps_delta_kernel(int n_drives, const long long* off, long long t
   }
 }
 
-// per drive, sequential by definition: the cumulative path (n+1 points, a leading duplicate of
-// the origin) and the de-duplication state machine (vmvo/utils/trajectory.py:206-216, 243-300).
-// One warp per drive: 32 deltas are loaded coalesced, every lane walks the same dependent chain of
-// additions (values broadcast by shuffle), lane l keeps point l of the batch and the stores are
-// coalesced again; the segment table of a finished run of repeated fixes is filled by all lanes.
+// per drive: the cumulative path (n+1 points, a leading duplicate of the origin) -- a dependent
+// chain of additions, sequential by definition -- and the de-duplication state machine
+// (vmvo/utils/trajectory.py:206-216, 243-300).  One warp per drive: 32 deltas are loaded
+// coalesced, every lane walks the same chain (values broadcast by shuffle) and keeps point l of
+// the batch.  The state machine needs no chain: every point between `last` and i equals point
+// `last` bit for bit, so "x[last] != x[i]" is the local test "point i differs from point i-1";
+// segment ends are then found with ballot / ffs / clz, and only runs of repeated fixes longer
+// than a batch need the strided fill.
 __global__ void gps_scan_kernel(int n_drives, const long long* off, long long total, const double* dxy,
                                 double* X, double* Y, int* seg_lo, int* seg_hi, int* status) {
   const int lane = threadIdx.x & 31;
@@ -114,40 +117,42 @@ __global__ void gps_scan_kernel(int n_drives, const long long* off, long long to
     seg_lo[o0] = 0;
     seg_hi[o0] = 0;
   }
-  double xc = 0.0, yc = 0.0;            // point i (replicated in every lane)
-  double xl = 0.0, yl = 0.0;            // point `last`
-  long long last = 0;
+  double xc = 0.0, yc = 0.0;            // last point produced (replicated in every lane)
+  long long last = 0;                   // latest segment end
   int st = 0;
   for (long long base = 0; base < n; base += 32) {
     const long long i0 = base + lane;
-    const double ddx = i0 < n ? dxy[f0 + i0] : 0.0, ddy = i0 < n ? dxy[total + f0 + i0] : 0.0;
+    const bool valid = i0 < n;
+    const double ddx = valid ? dxy[f0 + i0] : 0.0, ddy = valid ? dxy[total + f0 + i0] : 0.0;
+    const double x_in = xc, y_in = yc;  // point `base`
     double mx = 0.0, my = 0.0;
-    const int cnt = (int)(n - base < 32 ? n - base : 32);
-    for (int l = 0; l < cnt; ++l) {
-      xc = dadd(__shfl_sync(FULL, ddx, l), xc);      // x[i+1] = dx_i + x[i]
+#pragma unroll
+    for (int l = 0; l < 32; ++l) {      // x[i+1] = dx_i + x[i]; padding deltas are zero
+      xc = dadd(__shfl_sync(FULL, ddx, l), xc);
       yc = dadd(__shfl_sync(FULL, ddy, l), yc);
       if (l == lane) { mx = xc; my = yc; }
-      const long long i = base + l + 1;              // index of the point just produced
-      if (xl != xc || yl != yc) {                    // warp-uniform
-        if (i == n) st = 1;   // the reference indexes velocity[n] here: IndexError
-        for (long long j = last + 1 + lane; j <= i; j += 32) {
-          seg_lo[o0 + j] = (int)last;
-          seg_hi[o0 + j] = (int)i;
-        }
-        last = i;
-        xl = xc;
-        yl = yc;
-      }
     }
-    if (i0 < n) {
-      X[o0 + i0 + 1] = mx;
-      Y[o0 + i0 + 1] = my;
+    // lane l holds point i = base + l + 1; its predecessor is lane l-1's point (or point `base`)
+    double px = __shfl_up_sync(FULL, mx, 1), py = __shfl_up_sync(FULL, my, 1);
+    if (lane == 0) { px = x_in; py = y_in; }
+    const long long i = base + lane + 1;
+    const unsigned bits = __ballot_sync(FULL, valid && (mx != px || my != py));
+    if (valid) {
+      X[o0 + i] = mx;
+      Y[o0 + i] = my;
+      const unsigned ahead = bits >> lane, behind = bits & ((1u << lane) - 1u);
+      seg_lo[o0 + i] = behind ? (int)(base + (31 - __clz(behind)) + 1) : (int)last;
+      seg_hi[o0 + i] = ahead ? (int)(i + __ffs(ahead) - 1) : -1;   // -1: open (tail unless closed later)
     }
+    if (bits) {
+      const long long first_end = base + __ffs(bits);              // point index of the first end
+      for (long long j = last + 1 + lane; j <= base; j += 32) seg_hi[o0 + j] = (int)first_end;
+      last = base + (31 - __clz(bits)) + 1;
+      if (last == n) st = 1;   // the reference indexes velocity[n] here: IndexError
+    }
+    // carry: the last VALID point of the batch (padding deltas are zero, so xc already is it)
   }
-  for (long long j = last + 1 + lane; j < m; j += 32) {   // "interpolate the last few points"
-    seg_lo[o0 + j] = (int)last;
-    seg_hi[o0 + j] = -1;
-  }
+  (void)m;
   if (lane == 0) status[d] = st;
 }
 
