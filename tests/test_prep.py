@@ -125,3 +125,43 @@ def test_gpu_process_gps_trajectory(cuda_device):
         np.testing.assert_allclose(o["x"], ref["x"], rtol=0, atol=1e-6)
         np.testing.assert_allclose(o["y"], ref["y"], rtol=0, atol=1e-6)
         np.testing.assert_array_equal(o["time"], ref["time"])
+
+
+@pytest.mark.gpu
+def test_gpu_full_chain_like_reference_main(cuda_device):
+    """The call sequence of the reference's main() (optimize_trajectory_v2.py:168-183):
+    process_vo_trajectory + process_gps_trajectory + optimize_trajectory, DataFrames in,
+    Trajectory out -- against the same chain through the oracles."""
+    import pandas as pd
+    from oracle import vmvo_oracle as O
+    from tests.helpers import spec_of
+    from vehiclemodelvisualodometry_b200 import BicycleModel, SearchConfig, optimize_trajectory
+    from vehiclemodelvisualodometry_b200.optimize import DEFAULT_CFG
+    from vehiclemodelvisualodometry_b200.trajectory import process_gps_trajectory, process_vo_trajectory
+
+    n = 260
+    x, y, rot, _ = _vo_frame(n, 31)
+    lat, lon, heading, speed, stamp = _gps_frame(n, 32)
+    vo_df = pd.DataFrame({"x": x, "y": y, "rot": list(rot), "Timestamp": stamp})
+    gps_df = pd.DataFrame({"heading": heading, "Latitude": lat, "Longitude": lon, "speed": speed,
+                           "Timestamp": stamp})
+    vo_t, gps_t = process_vo_trajectory(vo_df), process_gps_trajectory(gps_df)
+    assert len(vo_t) == n and len(gps_t) == n + 1
+    cfg = SearchConfig(**{**DEFAULT_CFG.__dict__, "grid_v": 8, "grid_s": 8})
+    out = optimize_trajectory(vo_t, gps_t, BicycleModel(), config=cfg)
+    assert len(out) == n
+
+    # the same chain on the CPU: oracle prep (float64), streams rounded to float32 like the
+    # search ABI does, oracle driver
+    pv, pg = P.process_vo(x, y, rot, stamp), P.process_gps(lat, lon, speed, stamp)
+    N = min(n, n + 1)
+    def stream(p):
+        th = np.concatenate([p["theta"], p["theta"][-1:]])[:len(p["x"])] if len(p["theta"]) < len(p["x"]) else p["theta"]
+        return np.stack([p["x"], p["y"], th, p["velocity"]], axis=1)[:N].astype(np.float32)
+    # the facade derives dt and the horizon from the GPS stamps (optimize_trajectory_v2.py:35-42)
+    dt, horizon, _ = O.reference_dt(np.asarray(gps_t.time))
+    spec = O.replace(spec_of(cfg), horizon_frames=horizon, horizon_time=3.0)
+    ref = O.optimize_drive(spec, np.asarray(gps_t.time)[:N], dt, stream(pv), stream(pg))
+    np.testing.assert_allclose(out.x[:N], ref.x, rtol=0, atol=2e-6)
+    np.testing.assert_allclose(out.y[:N], ref.y, rtol=0, atol=2e-6)
+    np.testing.assert_allclose(out.velocity[:N], ref.velocity, rtol=1e-3, atol=1e-9)
