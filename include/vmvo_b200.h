@@ -14,8 +14,8 @@
  *   - calls are stream-ordered on the caller's `stream` (a cudaStream_t passed as void*)
  *     and asynchronous; one host thread per ctx;
  *   - return value: vmvo_status (0 = ok); vmvo_last_error(ctx) gives the text.
- *   - pose streams are float4 (x [m], y [m], theta [rad], v [m/s]) per frame, all drives
- *     concatenated; `d_drive_offsets[n_drives + 1]` delimits them; `d_time` is float64 [s].
+ *   - pose streams are float4 (x [m], y [m], theta [rad], v [m/s]) per frame (double4 in the
+ *     _f64 entry points), all drives concatenated; `d_drive_offsets[n_drives + 1]` delimits them; `d_time` is float64 [s].
  */
 #ifndef VMVO_B200_H
 #define VMVO_B200_H
@@ -123,19 +123,32 @@ int vmvo_grid_search_f32(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n_wi
                          double* d_out_poses, double* d_out_steer, double* d_out_vel,
                          int32_t out_stride, void* stream);
 
+/* The same search over float64 pose streams: double4 (x, y, theta, v) per frame (32-byte
+ * records, 16-byte aligned), d_imu float64.  The reference computes in float64 throughout
+ * (vmvo/schema.py:21-28 holds List[float]); the Python facades use this entry point so that no
+ * input is rounded on its way to the GPU.                                                   */
+int vmvo_grid_search_f64(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n_windows,
+                         const int64_t* d_win_start, const int32_t* d_win_len,
+                         const int32_t* d_win_drive, const double* d_dt_per_drive,
+                         const double* d_vo, const double* d_gps, const double* d_imu,
+                         const double* d_seeds, vmvo_window_result* d_results,
+                         double* d_out_poses, double* d_out_steer, double* d_out_vel,
+                         int32_t out_stride, void* stream);
+
 /* seed_mode = VMVO_SEED_CHAINED (optimize_trajectory_v2.py:46,72,146): the steering seed of a
  * window is the last steering angle of the previous window's optimum, 0 for the first window
  * of a drive.  Windows of a drive are therefore searched in order by one team; drives run in
  * parallel.  d_run_offsets[n_runs + 1] delimits, in window indices of this call, the runs
- * (normally one per drive: the d_window_offsets of vmvo_plan_windows).                     */
-int vmvo_grid_search_chained_f32(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n_windows,
-                                 const int64_t* d_win_start, const int32_t* d_win_len,
-                                 const int32_t* d_win_drive, const double* d_dt_per_drive,
-                                 const float* d_vo, const float* d_gps, const float* d_imu,
-                                 int64_t n_runs, const int64_t* d_run_offsets,
-                                 vmvo_window_result* d_results, double* d_out_poses,
-                                 double* d_out_steer, double* d_out_vel, int32_t out_stride,
-                                 void* stream);
+ * (normally one per drive: the d_window_offsets of vmvo_plan_windows).  stream_f64 = 0: the
+ * streams are float4 / float as in vmvo_grid_search_f32; 1: double4 / double as in _f64.    */
+int vmvo_grid_search_chained(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n_windows,
+                             const int64_t* d_win_start, const int32_t* d_win_len,
+                             const int32_t* d_win_drive, const double* d_dt_per_drive,
+                             const void* d_vo, const void* d_gps, const void* d_imu,
+                             int32_t stream_f64, int64_t n_runs, const int64_t* d_run_offsets,
+                             vmvo_window_result* d_results, double* d_out_poses,
+                             double* d_out_steer, double* d_out_vel, int32_t out_stride,
+                             void* stream);
 
 /* Test hook: the same search, additionally exporting the FP32 scan cost of EVERY hypothesis
  * and the width of its error band, [n_windows][grid_v * grid_s] each, so tests can check
@@ -156,6 +169,12 @@ int vmvo_grid_search_debug_f32(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_
 int vmvo_write_back_f32(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int32_t n_drives,
                         int64_t total_frames, const int64_t* d_drive_offsets, const int64_t* d_window_offsets,
                         const double* d_dt_per_drive, const float* d_vo, const float* d_gps,
+                        const vmvo_window_result* d_results, double* d_out_x, double* d_out_y,
+                        double* d_out_theta, double* d_out_vel, void* stream);
+/* float64 pose streams (double4 per frame), otherwise identical */
+int vmvo_write_back_f64(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int32_t n_drives,
+                        int64_t total_frames, const int64_t* d_drive_offsets, const int64_t* d_window_offsets,
+                        const double* d_dt_per_drive, const double* d_vo, const double* d_gps,
                         const vmvo_window_result* d_results, double* d_out_x, double* d_out_y,
                         double* d_out_theta, double* d_out_vel, void* stream);
 

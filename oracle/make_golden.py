@@ -29,7 +29,7 @@ sys.path.insert(0, ROOT)
 
 from oracle import ref_bridge  # noqa: E402
 from oracle import vmvo_oracle as O  # noqa: E402
-from vehiclemodelvisualodometry_b200.synthetic import synthetic_drives  # noqa: E402
+from vehiclemodelvisualodometry_b200.synthetic import off_float32_grid, synthetic_drives  # noqa: E402
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
@@ -223,13 +223,20 @@ def kat_grid(ref):
     return out
 
 
-def kat_driver(ref):
-    """The reference loop with mpc_run replaced by the oracle's grid solver (pins a12)."""
+def kat_driver(ref, f64_inputs=False):
+    """The reference loop with mpc_run replaced by the oracle's grid solver (pins a12).
+
+    ``f64_inputs``: pose values that float32 cannot represent (synthetic.off_float32_grid), the
+    case the float64 stream entry points (vmvo_grid_search_f64 / vmvo_write_back_f64) exist for.
+    """
     v2 = ref_bridge.load_v2()
     T = ref.schema.Trajectory
     n = 260
     batch = synthetic_drives(1, n, seed=9)
     time, vo, gps, imu = batch.drive(0)
+    if f64_inputs:
+        vo, gps = off_float32_grid(vo), off_float32_grid(gps)
+        assert not np.array_equal(vo, vo.astype(np.float32).astype(np.float64))
     vo64, gps64 = vo.astype(np.float64), gps.astype(np.float64)
     # G_v = 1: the reference loop re-rolls the returned steering at CONSTANT speed
     # (optimize_trajectory_v2.py:84-91), which only a zero-acceleration hypothesis reproduces
@@ -282,6 +289,7 @@ def main():
         "cost": kat_cost(ref),
         "grid": kat_grid(ref),
         "driver": kat_driver(ref),
+        "driver_f64": kat_driver(ref, f64_inputs=True),
     }
     path = os.path.join(GOLDEN_DIR, "reference_kats.json")
     with open(path, "w") as f:

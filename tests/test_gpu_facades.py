@@ -7,7 +7,7 @@ from oracle import vmvo_oracle as O
 from tests.helpers import load_golden, spec_of, unhex
 from vehiclemodelvisualodometry_b200 import (DEFAULT_CFG, REFERENCE_CFG, BicycleModel, SearchConfig,
                                              Trajectory, grid_run, mpc_run, optimize_trajectory)
-from vehiclemodelvisualodometry_b200.synthetic import synthetic_drives
+from vehiclemodelvisualodometry_b200.synthetic import off_float32_grid, synthetic_drives
 
 pytestmark = pytest.mark.gpu
 G = load_golden()
@@ -28,8 +28,9 @@ def test_grid_run_has_mpc_run_contract(cuda_device):
     v = (sub.velocity[0] + sub.velocity[-1]) / 2
     cfg = SearchConfig(grid_v=8, grid_s=16, target_mode="traverse", seed_mode="given")
     u, rec, out = grid_run(sub, BicycleModel(), v, 25.0, 0.05, config=cfg, return_info=True)
-    # oracle on the same (float32-rounded) local window
-    xy = np.stack([np.float32(sub.x), np.float32(sub.y)], axis=1).astype(np.float64)
+    # oracle on the same local window: float64 end to end, nothing is rounded on the way in
+    xy = np.stack([sub.x, sub.y], axis=1).astype(np.float64)
+    assert not np.array_equal(xy, xy.astype(np.float32))
     interp = O.traverse_trajectory(xy, v * 0.05)
     spec = O.SearchSpec(grid_v=8, grid_s=16, target_mode="traverse", seed_mode="given")
     wt = O.WindowTargets(n_steps=len(interp) - 1, status=0, v_seed=v, s_seed=25.0, vo_xy=interp)
@@ -53,7 +54,8 @@ def test_grid_run_empty_window_returns_empty(cuda_device):
 def test_optimize_trajectory_matches_oracle(cuda_device, which):
     n = 230
     batch = synthetic_drives(1, n, seed=41)
-    time, vo, gps = batch.time[0], batch.vo[0], batch.gps[0]
+    # Trajectory columns are List[float] (float64): use values float32 cannot hold
+    time, vo, gps = batch.time[0], off_float32_grid(batch.vo[0]), off_float32_grid(batch.gps[0])
     base = DEFAULT_CFG if which == "default" else REFERENCE_CFG
     cfg = SearchConfig(**{**base.__dict__, "grid_v": 8, "grid_s": 12})
     vo_t, gps_t = _traj(time, vo), _traj(time[:-3], gps[:-3])    # unequal lengths: N = min
@@ -70,6 +72,23 @@ def test_optimize_trajectory_matches_oracle(cuda_device, which):
     np.testing.assert_array_equal(out.theta[:N], ref.theta)
     np.testing.assert_array_equal(out.velocity[:N], ref.velocity)
     np.testing.assert_array_equal(out.x[N:], vo_t.x[N:])
+
+
+def test_optimize_trajectory_reproduces_frozen_reference_output(cuda_device):
+    """optimize_trajectory (this package) against the frozen output of the reference's own
+    optimize_trajectory loop (tests/golden, key driver_f64: float64 inputs off the float32 grid,
+    grid solver patched in for mpc_run)."""
+    g = G["driver_f64"]
+    batch = synthetic_drives(1, g["n"], seed=g["seed"])
+    time = batch.time[0]
+    vo_t, gps_t = _traj(time, off_float32_grid(batch.vo[0])), _traj(time, off_float32_grid(batch.gps[0]))
+    cfg = SearchConfig(**{**REFERENCE_CFG.__dict__, "grid_v": g["grid"][0], "grid_s": g["grid"][1]})
+    out, (so, plan, rec) = optimize_trajectory(vo_t, gps_t, BicycleModel(), config=cfg, return_details=True)
+    np.testing.assert_array_equal(rec["best_idx"], g["best_idx"])
+    np.testing.assert_allclose(out.x, unhex(g["x"]), rtol=0, atol=1e-9)
+    np.testing.assert_allclose(out.y, unhex(g["y"]), rtol=0, atol=1e-9)
+    np.testing.assert_array_equal(out.theta, unhex(g["theta"]))
+    np.testing.assert_array_equal(out.velocity, unhex(g["velocity"]))
 
 
 def test_optimize_trajectory_stationary_raises_like_reference(cuda_device):

@@ -11,7 +11,7 @@ from vehiclemodelvisualodometry_b200 import (BicycleModel, DriveSet, SearchConfi
                                              optimize_drives, rollout_batch, sequence_cost,
                                              traverse_trajectory)
 from vehiclemodelvisualodometry_b200 import _lib
-from vehiclemodelvisualodometry_b200.synthetic import synthetic_drives
+from vehiclemodelvisualodometry_b200.synthetic import off_float32_grid, synthetic_drives
 
 pytestmark = pytest.mark.gpu
 G = load_golden()
@@ -156,16 +156,22 @@ def test_write_back_matches_oracle_driver(cuda_device, mode):
         np.testing.assert_array_equal(traj[3, sl], ref.velocity)
 
 
-def test_write_back_golden_reference_loop(cuda_device):
+@pytest.mark.parametrize("key", ["driver", "driver_f64"])
+def test_write_back_golden_reference_loop(cuda_device, key):
     """The frozen output of the REFERENCE driver loop (optimize_trajectory_v2.py:24-148 with the
-    grid solver patched in for mpc_run), reproduced by plan -> search -> write-back."""
-    g = G["driver"]
+    grid solver patched in for mpc_run), reproduced by plan -> search -> write-back; with
+    float32 streams, and with float64 streams on inputs float32 cannot represent."""
+    g = G[key]
     batch = synthetic_drives(1, g["n"], seed=g["seed"])
+    vo, gps, sd = batch.vo[0], batch.gps[0], np.float32
+    if key == "driver_f64":
+        vo, gps, sd = off_float32_grid(vo), off_float32_grid(gps), np.float64
     cfg = SearchConfig(grid_v=g["grid"][0], grid_s=g["grid"][1], window_mode="time", horizon_time=3.0,
                        horizon_frames=g["horizon"], target_mode="traverse", primary="gps", w_vo=0.0,
                        w_gps=1.0)
-    drives = DriveSet.from_arrays([batch.time[0]], [float.fromhex(g["dt"])], vo=[batch.vo[0]],
-                                  gps=[batch.gps[0]])
+    drives = DriveSet.from_arrays([batch.time[0]], [float.fromhex(g["dt"])], vo=[vo], gps=[gps],
+                                  stream_dtype=sd)
+    assert drives.f64 == (key == "driver_f64")
     so, traj, plan = optimize_drives(cfg, drives)
     traj = traj.cpu().numpy()
     np.testing.assert_array_equal(so.records()["best_idx"], g["best_idx"])

@@ -15,7 +15,7 @@ from oracle import vmvo_oracle as O
 from tests.helpers import assert_records_match, oracle_windows, spec_of
 from vehiclemodelvisualodometry_b200 import (DriveSet, SearchConfig, grid_search, optimize_drives,
                                              plan_windows)
-from vehiclemodelvisualodometry_b200.synthetic import synthetic_drives
+from vehiclemodelvisualodometry_b200.synthetic import off_float32_grid, synthetic_drives
 
 pytestmark = pytest.mark.gpu
 
@@ -61,6 +61,41 @@ def test_search_matches_oracle(cuda_device, name):
         # IEEE ops on the seeds; the seed itself carries atan's last-bit difference
         np.testing.assert_allclose(steer[w, :N], r.steer, rtol=1e-13, atol=1e-12)
         np.testing.assert_allclose(vel[w, :N], r.vel, rtol=1e-13, atol=1e-13)
+
+
+@pytest.mark.parametrize("name", ["vo_16x16", "gps_traverse", "vo_gps_imu", "time_windows"])
+def test_float64_streams_match_oracle(cuda_device, name):
+    """vmvo_grid_search_f64: double4 pose streams, inputs float32 cannot represent."""
+    cfg = CASES[name]
+    n = 2 * cfg.horizon() + 25
+    batch = synthetic_drives(2, n, seed=zlib.crc32(name.encode()) % 1000 + 1)
+    vo, gps, imu = off_float32_grid(batch.vo), off_float32_grid(batch.gps), off_float32_grid(batch.imu)
+    drives = DriveSet.from_arrays(list(batch.time), [batch.dt] * 2, vo=list(vo), gps=list(gps),
+                                  imu=list(imu), stream_dtype=np.float64)
+    assert drives.f64 and drives.vo.dtype == torch.float64
+    plan = plan_windows(cfg, drives)
+    out = grid_search(cfg, drives, plan, want_rollouts=True)
+    rec = out.records()
+    ref = []
+    for d in range(2):
+        ref += oracle_windows(cfg, batch.time[d], batch.dt, vo[d], gps[d], imu[d])
+    assert_records_match(rec, ref)
+    poses = out.poses.cpu().numpy()
+    for w, r in enumerate(ref):
+        np.testing.assert_allclose(poses[w, :r.n_steps], r.poses, rtol=0, atol=1e-9)
+    # the float32 entry point on the same data sees rounded inputs: its costs differ
+    d32 = DriveSet.from_arrays(list(batch.time), [batch.dt] * 2, vo=list(vo), gps=list(gps), imu=list(imu))
+    rec32 = grid_search(cfg, d32, plan).records()
+    assert not np.array_equal(rec32["best_cost"], rec["best_cost"])
+
+
+def test_mixed_stream_dtypes_are_rejected(cuda_device):
+    cfg = CASES["vo_gps"]
+    batch = synthetic_drives(1, 80, seed=3)
+    drives = DriveSet.from_arrays([batch.time[0]], [batch.dt], vo=[batch.vo[0]], gps=[batch.gps[0]])
+    drives.gps = drives.gps.double()
+    with pytest.raises(ValueError, match="one dtype"):
+        grid_search(cfg, drives, plan_windows(cfg, drives))
 
 
 @pytest.mark.parametrize("fast", ["0", "1"])
@@ -115,8 +150,9 @@ def test_window_range_and_out_buffer(cuda_device):
         np.testing.assert_array_equal(got[f], full[f])
 
 
+@pytest.mark.parametrize("stream", ["f32", "f64"])
 @pytest.mark.parametrize("target_mode", ["time", "traverse"])
-def test_chained_seed_mode(cuda_device, target_mode):
+def test_chained_seed_mode(cuda_device, target_mode, stream):
     """seed_mode chained (optimize_trajectory_v2.py:46,72,146): S_w of window w+1 is the last
     steering angle of window w's optimum; drives are independent runs."""
     cfg = SearchConfig(grid_v=8, grid_s=16, window_frames=20, seed_mode="chained", target_mode=target_mode)
@@ -124,7 +160,10 @@ def test_chained_seed_mode(cuda_device, target_mode):
     batch = synthetic_drives(3, 120, seed=17)
     time = [batch.time[d][:n] for d, n in enumerate(lengths)]
     vo = [batch.vo[d][:n] for d, n in enumerate(lengths)]
-    drives = DriveSet.from_arrays(time, [batch.dt] * 3, vo=vo)
+    if stream == "f64":
+        vo = [off_float32_grid(v) for v in vo]
+    drives = DriveSet.from_arrays(time, [batch.dt] * 3, vo=vo,
+                                  stream_dtype=np.float64 if stream == "f64" else np.float32)
     so, traj, plan = optimize_drives(cfg, drives)
     rec = so.records()
     assert plan.window_offsets == [0, 35, 35, 115]

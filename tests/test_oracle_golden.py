@@ -7,7 +7,7 @@ import pytest
 from oracle import ref_bridge
 from oracle import vmvo_oracle as O
 from tests.helpers import load_golden, unhex
-from vehiclemodelvisualodometry_b200.synthetic import synthetic_drives
+from vehiclemodelvisualodometry_b200.synthetic import off_float32_grid, synthetic_drives
 
 G = load_golden()
 # the frozen floats come from this container's libm; other hosts may differ in the last bit
@@ -94,10 +94,13 @@ def test_grid_cases_pinned_through_reference_model():
         np.testing.assert_allclose(wt.s_seed, float.fromhex(case["s_seed"]), rtol=1e-14, atol=1e-13)
 
 
-def test_driver_loop_golden():
-    g = G["driver"]
+@pytest.mark.parametrize("key", ["driver", "driver_f64"])
+def test_driver_loop_golden(key):
+    g = G[key]
     batch = synthetic_drives(1, g["n"], seed=g["seed"])
     time, vo, gps, imu = batch.drive(0)
+    if key == "driver_f64":      # inputs float32 cannot represent
+        vo, gps = off_float32_grid(vo), off_float32_grid(gps)
     dt, horizon, _ = O.reference_dt(time)
     assert horizon == g["horizon"] and dt == float.fromhex(g["dt"])
     spec = O.SearchSpec(grid_v=g["grid"][0], grid_s=g["grid"][1], window_mode="time", target_mode="traverse",

@@ -58,13 +58,18 @@ _SIGNATURES = {
     "vmvo_grid_search_f32": (C.c_int, [_c_vp, C.POINTER(SearchCfg), _c_i64, _c_vp, _c_vp, _c_vp, _c_vp,
                                        _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i32,
                                        _c_vp]),
-    "vmvo_grid_search_chained_f32": (C.c_int, [_c_vp, C.POINTER(SearchCfg), _c_i64, _c_vp, _c_vp, _c_vp,
-                                               _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp,
-                                               _c_vp, _c_vp, _c_i32, _c_vp]),
+    "vmvo_grid_search_f64": (C.c_int, [_c_vp, C.POINTER(SearchCfg), _c_i64, _c_vp, _c_vp, _c_vp, _c_vp,
+                                       _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i32,
+                                       _c_vp]),
+    "vmvo_grid_search_chained": (C.c_int, [_c_vp, C.POINTER(SearchCfg), _c_i64, _c_vp, _c_vp, _c_vp,
+                                           _c_vp, _c_vp, _c_vp, _c_vp, _c_i32, _c_i64, _c_vp, _c_vp,
+                                           _c_vp, _c_vp, _c_vp, _c_i32, _c_vp]),
     "vmvo_grid_search_debug_f32": (C.c_int, [_c_vp, C.POINTER(SearchCfg), _c_i64, _c_vp, _c_vp, _c_vp,
                                              _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp,
                                              _c_vp]),
     "vmvo_write_back_f32": (C.c_int, [_c_vp, C.POINTER(SearchCfg), _c_i32, _c_i64, _c_vp, _c_vp, _c_vp,
+                                      _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),
+    "vmvo_write_back_f64": (C.c_int, [_c_vp, C.POINTER(SearchCfg), _c_i32, _c_i64, _c_vp, _c_vp, _c_vp,
                                       _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),
     "vmvo_rollout_f64": (C.c_int, [_c_vp, _c_i64, _c_i32, _c_vp, _c_vp, _c_f64, _c_vp, _c_f64, _c_f64,
                                    _c_vp, _c_vp, _c_vp]),

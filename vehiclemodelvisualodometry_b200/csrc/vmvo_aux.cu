@@ -70,10 +70,11 @@ __global__ void plan_windows_kernel(int window_mode, int window_frames, double h
 // for i = 0 .. n_w-1 in order).  Offset m - i == 0 is the first rollout pose kept in the
 // record; deeper offsets (the tail after the last window, or frames behind an empty window)
 // re-run the winning hypothesis with the same warp routine the search used.
+template <typename Pose4>
 __global__ void write_back_kernel(int gv, int gs, double L, double ratio, double max_steer,
                                   double max_accel, double max_rate, int max_steps, int n_drives,
                                   const long long* drive_off, const long long* win_off,
-                                  const double* dt_drive, const float4* vo, const float4* gps,
+                                  const double* dt_drive, const Pose4* vo, const Pose4* gps,
                                   const vmvo_window_result* results, long long total_frames,
                                   double* out_x, double* out_y, double* out_th, double* out_v) {
   const int lane = threadIdx.x & 31;
@@ -91,10 +92,10 @@ __global__ void write_back_kernel(int gv, int gs, double L, double ratio, double
     m = f - drive_off[d];
     w0 = win_off[d];
     nw = win_off[d + 1] - w0;
-    const float4 q = vo[f];
+    const Pose4 q = vo[f];
     x = (double)q.x; y = (double)q.y; th = (double)q.z; v = (double)q.w;
     if (m < nw && gps != nullptr) {
-      const float4 g = gps[f];
+      const Pose4 g = gps[f];
       double dd = pymod_pos(dsub(th, (double)g.z), kTwoPi);
       if (dd > kPi) dd = dsub(dd, kTwoPi);
       th = pymod_pos(dsub(th, ddiv(dd, 2.0)), kTwoPi);
@@ -411,12 +412,13 @@ extern "C" int vmvo_plan_windows(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int3
   return check_launch(ctx, "plan_windows_kernel");
 }
 
-extern "C" int vmvo_write_back_f32(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int32_t n_drives,
-                                   int64_t total_frames, const int64_t* d_drive_offsets, const int64_t* d_window_offsets,
-                                   const double* d_dt_per_drive, const float* d_vo, const float* d_gps,
-                                   const vmvo_window_result* d_results, double* d_out_x,
-                                   double* d_out_y, double* d_out_theta, double* d_out_vel,
-                                   void* stream) {
+template <typename Pose4>
+static int write_back_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int32_t n_drives,
+                           int64_t total_frames, const int64_t* d_drive_offsets,
+                           const int64_t* d_window_offsets, const double* d_dt_per_drive,
+                           const void* d_vo, const void* d_gps, const vmvo_window_result* d_results,
+                           double* d_out_x, double* d_out_y, double* d_out_theta, double* d_out_vel,
+                           void* stream) {
   if (!ctx) return VMVO_ERR_BAD_ARG;
   int rc = validate_cfg(ctx, cfg);
   if (rc) return rc;
@@ -424,18 +426,44 @@ extern "C" int vmvo_write_back_f32(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, in
   if (!d_drive_offsets || !d_window_offsets || !d_dt_per_drive || !d_vo || !d_results || !d_out_x ||
       !d_out_y || !d_out_theta || !d_out_vel)
     return fail(ctx, VMVO_ERR_BAD_ARG, "NULL pointer");
+  if (((uintptr_t)d_vo | (uintptr_t)d_gps) & 15)
+    return fail(ctx, VMVO_ERR_BAD_ARG, "pose streams must be 16-byte aligned");
   VMVO_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = (cudaStream_t)stream;
   const long long total = total_frames;
   if (total <= 0) return VMVO_OK;
   const int threads = 256;
   const long long blocks = (total + threads - 1) / threads;
-  write_back_kernel<<<(unsigned)blocks, threads, 0, st>>>(
+  write_back_kernel<Pose4><<<(unsigned)blocks, threads, 0, st>>>(
       cfg->grid_v, cfg->grid_s, cfg->wheel_base, cfg->steering_ratio, cfg->max_steer, cfg->max_accel,
       cfg->max_steer_rate, cfg->max_window_poses, n_drives, (const long long*)d_drive_offsets,
-      (const long long*)d_window_offsets, d_dt_per_drive, (const float4*)d_vo, (const float4*)d_gps,
+      (const long long*)d_window_offsets, d_dt_per_drive, (const Pose4*)d_vo, (const Pose4*)d_gps,
       d_results, total, d_out_x, d_out_y, d_out_theta, d_out_vel);
   return check_launch(ctx, "write_back_kernel");
+}
+
+extern "C" int vmvo_write_back_f32(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int32_t n_drives,
+                                   int64_t total_frames, const int64_t* d_drive_offsets,
+                                   const int64_t* d_window_offsets, const double* d_dt_per_drive,
+                                   const float* d_vo, const float* d_gps,
+                                   const vmvo_window_result* d_results, double* d_out_x,
+                                   double* d_out_y, double* d_out_theta, double* d_out_vel,
+                                   void* stream) {
+  return write_back_impl<float4>(ctx, cfg, n_drives, total_frames, d_drive_offsets, d_window_offsets,
+                                 d_dt_per_drive, d_vo, d_gps, d_results, d_out_x, d_out_y,
+                                 d_out_theta, d_out_vel, stream);
+}
+
+extern "C" int vmvo_write_back_f64(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int32_t n_drives,
+                                   int64_t total_frames, const int64_t* d_drive_offsets,
+                                   const int64_t* d_window_offsets, const double* d_dt_per_drive,
+                                   const double* d_vo, const double* d_gps,
+                                   const vmvo_window_result* d_results, double* d_out_x,
+                                   double* d_out_y, double* d_out_theta, double* d_out_vel,
+                                   void* stream) {
+  return write_back_impl<double4>(ctx, cfg, n_drives, total_frames, d_drive_offsets, d_window_offsets,
+                                  d_dt_per_drive, d_vo, d_gps, d_results, d_out_x, d_out_y,
+                                  d_out_theta, d_out_vel, stream);
 }
 
 template <typename T>

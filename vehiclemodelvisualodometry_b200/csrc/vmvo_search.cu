@@ -45,9 +45,9 @@ struct SearchParams {
   const int* win_len;
   const int* win_drive;
   const double* dt_drive;
-  const float4* vo;
-  const float4* gps;
-  const float* imu;
+  const void* vo;        // pose streams: float4 or double4 per frame (kernel template SF)
+  const void* gps;
+  const void* imu;       // yaw per frame, float or double
   const double* seeds;
   vmvo_window_result* results;
   double* out_poses;
@@ -80,9 +80,9 @@ struct SmemLayout {
       off_vd, off_cand, total;
   // P poses per window, n_streams pose streams staged, optional terms only when configured
   __host__ __device__ SmemLayout(int P, int gs, int vd_cols, int team_warps, int n_streams,
-                                 bool dual, bool imu, bool traverse) {
+                                 bool dual, bool imu, bool traverse, int pose_bytes) {
     int o = kHeaderBytes;                       // barriers, window ids, reductions
-    off_raw = o;  o += 2 * n_streams * P * 16;  // float4 raw[2 buffers][streams][P]
+    off_raw = o;  o += 2 * n_streams * P * pose_bytes;  // raw[2 buffers][streams][P] float4/double4
     off_loc = o;  o += n_streams * 3 * P * 8;   // double loc[streams][3][P]  (lx, ly, lth)
     off_loci = o; o += imu ? P * 8 : 0;         // double imu yaw relative to the window start
     off_tgt = o;  o += (2 + (dual ? 2 : 0) + (imu ? 1 : 0)) * P * 8;  // tAx, tAy, [tBx, tBy], [tI]
@@ -395,21 +395,29 @@ __device__ __forceinline__ void scan_item_fast(int N, int gs, int vd_cols, int j
 // WARPS warps per CTA, MINB CTAs per SM.  Only <8, 2> (128 registers per thread, 16 warps/SM) is
 // instantiated: at 80 or 64 registers (24 / 32 warps/SM) both scan loops spill inside the loop and
 // every such variant measured slower (profiles/README.md).
-template <int C, int WARPS, int MINB, bool DUAL, bool IMU>
+template <typename SF> struct PoseOf;
+template <> struct PoseOf<float> { using type = float4; };
+template <> struct PoseOf<double> { using type = double4; };
+
+template <int C, int WARPS, int MINB, bool DUAL, bool IMU, typename SF>
 __global__ void __launch_bounds__(32 * WARPS, MINB)
 vmvo_window_search_kernel(const SearchParams p) {
+  using Pose4 = typename PoseOf<SF>::type;
   constexpr int kC = C;
   extern __shared__ __align__(1024) unsigned char smem_cta[];
   const int P = p.maxp;
   const int n_streams = p.load_vo + p.load_gps;
   const SmemLayout lay(P, p.gs, p.vd_cols, p.team_warps, n_streams, DUAL, IMU,
-                       p.target_mode == VMVO_TARGET_TRAVERSE);
+                       p.target_mode == VMVO_TARGET_TRAVERSE, (int)sizeof(Pose4));
   // stream s (0 = VO, 1 = GPS) lives in slot s when both are staged, else in slot 0
   const int slot_vo = 0, slot_gps = p.load_vo ? 1 : 0;
   const Team team{p.team_warps, p.team_warps * 32, (int)threadIdx.x / (p.team_warps * 32)};
   unsigned char* smem = smem_cta + (size_t)team.id * lay.total;
   SmemHeader* hd = reinterpret_cast<SmemHeader*>(smem);
-  float4* raw = reinterpret_cast<float4*>(smem + lay.off_raw);
+  Pose4* raw = reinterpret_cast<Pose4*>(smem + lay.off_raw);
+  const Pose4* g_vo = reinterpret_cast<const Pose4*>(p.vo);
+  const Pose4* g_gps = reinterpret_cast<const Pose4*>(p.gps);
+  const SF* g_imu = reinterpret_cast<const SF*>(p.imu);
   double* loc = reinterpret_cast<double*>(smem + lay.off_loc);
   double* loci = reinterpret_cast<double*>(smem + lay.off_loci);
   double* tgt = reinterpret_cast<double*>(smem + lay.off_tgt);
@@ -440,14 +448,14 @@ vmvo_window_search_kernel(const SearchParams p) {
     int len = p.win_len[w];
     len = len < P ? len : P;
     len = len > 0 ? len : 0;
-    const unsigned bytes = (unsigned)len * 16u;
+    const unsigned bytes = (unsigned)len * (unsigned)sizeof(Pose4);
     const unsigned total = bytes * (unsigned)(p.load_vo + p.load_gps);
     mbar_arrive_expect_tx(&hd->mbar[buf], total);
     if (bytes) {
       if (p.load_vo)
-        bulk_g2s(raw + (buf * n_streams + slot_vo) * P, p.vo + start, bytes, &hd->mbar[buf]);
+        bulk_g2s(raw + (buf * n_streams + slot_vo) * P, g_vo + start, bytes, &hd->mbar[buf]);
       if (p.load_gps)
-        bulk_g2s(raw + (buf * n_streams + slot_gps) * P, p.gps + start, bytes, &hd->mbar[buf]);
+        bulk_g2s(raw + (buf * n_streams + slot_gps) * P, g_gps + start, bytes, &hd->mbar[buf]);
     }
   };
 
@@ -517,8 +525,8 @@ vmvo_window_search_kernel(const SearchParams p) {
       for (int s = 0; s < 2; ++s) {
         if (!(s == 0 ? p.load_vo : p.load_gps)) continue;
         const int slot = s == 0 ? slot_vo : slot_gps;
-        const float4* rs = raw + (cur * n_streams + slot) * P;
-        const float4 p0 = rs[0];
+        const Pose4* rs = raw + (cur * n_streams + slot) * P;
+        const Pose4 p0 = rs[0];
         const double th0 = (double)p0.z;
         double sn, cs;
         sincos(th0, &sn, &cs);
@@ -526,7 +534,7 @@ vmvo_window_search_kernel(const SearchParams p) {
         double* ly = loc + (slot * 3 + 1) * P;
         double* lt = loc + (slot * 3 + 2) * P;
         for (int m = tid; m < len; m += T) {
-          const float4 q = rs[m];
+          const Pose4 q = rs[m];
           const double dx = dsub((double)q.x, (double)p0.x);
           const double dy = dsub((double)q.y, (double)p0.y);
           lx[m] = dadd(dmul(dx, cs), dmul(dy, sn));
@@ -536,8 +544,8 @@ vmvo_window_search_kernel(const SearchParams p) {
       }
     }
     if (IMU) {
-      const double y0 = (double)p.imu[start];
-      for (int m = tid; m < len; m += T) loci[m] = dsub((double)p.imu[start + m], y0);
+      const double y0 = (double)g_imu[start];
+      for (int m = tid; m < len; m += T) loci[m] = dsub((double)g_imu[start + m], y0);
     }
     team.sync();
 
@@ -547,7 +555,7 @@ vmvo_window_search_kernel(const SearchParams p) {
     const double* ply = loc + (slot_prim * 3 + 1) * P;
     const double* plt = loc + (slot_prim * 3 + 2) * P;
     if (warp == 0) {
-      const float4* rp = raw + (cur * n_streams + slot_prim) * P;
+      const Pose4* rp = raw + (cur * n_streams + slot_prim) * P;
       double v_seed, s_seed;
       if (p.seed_mode == VMVO_SEED_GIVEN) {
         v_seed = p.seeds[2 * w];
@@ -980,12 +988,12 @@ vmvo_window_search_kernel(const SearchParams p) {
   }
 }
 
-template <int C, int WARPS, int MINB, bool DUAL, bool IMU>
+template <int C, int WARPS, int MINB, bool DUAL, bool IMU, typename SF>
 static int launch_search(vmvo_ctx* ctx, const SearchParams& p, cudaStream_t st) {
-  auto kern = vmvo_window_search_kernel<C, WARPS, MINB, DUAL, IMU>;
+  auto kern = vmvo_window_search_kernel<C, WARPS, MINB, DUAL, IMU, SF>;
   constexpr int kCtaThreads = 32 * WARPS;
   const SmemLayout lay(p.maxp, p.gs, p.vd_cols, p.team_warps, p.load_vo + p.load_gps, DUAL, IMU,
-                       p.target_mode == VMVO_TARGET_TRAVERSE);
+                       p.target_mode == VMVO_TARGET_TRAVERSE, (int)(4 * sizeof(SF)));
   const int teams = WARPS / p.team_warps;
   const int smem = lay.total * teams;
   if (smem > 200 * 1024)
@@ -1011,7 +1019,7 @@ static int launch_search(vmvo_ctx* ctx, const SearchParams& p, cudaStream_t st) 
 static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n_windows,
                             const int64_t* d_win_start, const int32_t* d_win_len,
                             const int32_t* d_win_drive, const double* d_dt_per_drive,
-                            const float* d_vo, const float* d_gps, const float* d_imu,
+                            const void* d_vo, const void* d_gps, const void* d_imu, bool f64,
                             const double* d_seeds, vmvo_window_result* d_results,
                             double* d_out_poses, double* d_out_steer, double* d_out_vel,
                             int32_t out_stride, float* d_dbg_cost, float* d_dbg_err,
@@ -1026,7 +1034,7 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
   if (cfg->seed_mode == VMVO_SEED_CHAINED && !d_run_offsets)
     return fail(ctx, VMVO_ERR_UNSUPPORTED,
                 "seed_mode chained walks the windows of a drive in order: call "
-                "vmvo_grid_search_chained_f32 with the per-drive window ranges");
+                "vmvo_grid_search_chained with the per-drive window ranges");
   if (d_run_offsets && (cfg->seed_mode != VMVO_SEED_CHAINED || n_runs < 1))
     return fail(ctx, VMVO_ERR_BAD_ARG, "run offsets are for seed_mode chained with n_runs >= 1");
   if (cfg->seed_mode == VMVO_SEED_GIVEN && !d_seeds)
@@ -1041,6 +1049,7 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
   if (use_imu && !d_imu) return fail(ctx, VMVO_ERR_BAD_ARG, "w_imu != 0 but d_imu is NULL");
   if (((uintptr_t)d_vo | (uintptr_t)d_gps) & 15)
     return fail(ctx, VMVO_ERR_BAD_ARG, "pose streams must be 16-byte aligned");
+  if ((uintptr_t)d_imu & (f64 ? 7 : 3)) return fail(ctx, VMVO_ERR_BAD_ARG, "imu stream misaligned");
   if ((d_out_poses || d_out_steer || d_out_vel) && out_stride < 1)
     return fail(ctx, VMVO_ERR_BAD_ARG, "out_stride < 1");
   if ((d_dbg_cost == nullptr) != (d_dbg_err == nullptr))
@@ -1062,7 +1071,8 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
     int ch = (th + p.gs - 1) / p.gs + 1;
     if (ch > p.n_ic) ch = p.n_ic;
     const SmemLayout probe(cfg->max_window_poses, p.gs, ch * kC, tw, (int)load_vo + (int)load_gps,
-                           use_vo && use_gps, use_imu, cfg->target_mode == VMVO_TARGET_TRAVERSE);
+                           use_vo && use_gps, use_imu, cfg->target_mode == VMVO_TARGET_TRAVERSE,
+                           f64 ? 32 : 16);
     if (tw == cta_warps || probe.total * (cta_warps / tw) <= 110 * 1024) break;
     tw *= 2;
   }
@@ -1110,8 +1120,8 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
   p.win_len = d_win_len;
   p.win_drive = d_win_drive;
   p.dt_drive = d_dt_per_drive;
-  p.vo = (const float4*)d_vo;
-  p.gps = (const float4*)d_gps;
+  p.vo = d_vo;
+  p.gps = d_gps;
   p.imu = d_imu;
   p.seeds = d_seeds;
   p.results = d_results;
@@ -1133,12 +1143,12 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
   p.work_counter = counter;
 
   const bool dual = use_vo && use_gps;
-#define VMVO_LAUNCH(W)                                                                   \
-  (dual ? (use_imu ? launch_search<8, W, 2, true, true>(ctx, p, st)                      \
-                   : launch_search<8, W, 2, true, false>(ctx, p, st))                    \
-        : (use_imu ? launch_search<8, W, 2, false, true>(ctx, p, st)                     \
-                   : launch_search<8, W, 2, false, false>(ctx, p, st)))
-  return VMVO_LAUNCH(8);
+#define VMVO_LAUNCH(SF)                                                                  \
+  (dual ? (use_imu ? launch_search<8, 8, 2, true, true, SF>(ctx, p, st)                  \
+                   : launch_search<8, 8, 2, true, false, SF>(ctx, p, st))                \
+        : (use_imu ? launch_search<8, 8, 2, false, true, SF>(ctx, p, st)                 \
+                   : launch_search<8, 8, 2, false, false, SF>(ctx, p, st)))
+  return f64 ? VMVO_LAUNCH(double) : VMVO_LAUNCH(float);
 #undef VMVO_LAUNCH
 }
 
@@ -1154,23 +1164,36 @@ extern "C" int vmvo_grid_search_f32(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, i
                                     double* d_out_poses, double* d_out_steer, double* d_out_vel,
                                     int32_t out_stride, void* stream) {
   return grid_search_impl(ctx, cfg, n_windows, d_win_start, d_win_len, d_win_drive, d_dt_per_drive,
-                          d_vo, d_gps, d_imu, d_seeds, d_results, d_out_poses, d_out_steer, d_out_vel,
-                          out_stride, nullptr, nullptr, 0, nullptr, stream);
+                          d_vo, d_gps, d_imu, false, d_seeds, d_results, d_out_poses, d_out_steer,
+                          d_out_vel, out_stride, nullptr, nullptr, 0, nullptr, stream);
 }
 
-extern "C" int vmvo_grid_search_chained_f32(vmvo_ctx* ctx, const vmvo_search_cfg* cfg,
-                                            int64_t n_windows, const int64_t* d_win_start,
-                                            const int32_t* d_win_len, const int32_t* d_win_drive,
-                                            const double* d_dt_per_drive, const float* d_vo,
-                                            const float* d_gps, const float* d_imu, int64_t n_runs,
-                                            const int64_t* d_run_offsets,
-                                            vmvo_window_result* d_results, double* d_out_poses,
-                                            double* d_out_steer, double* d_out_vel,
-                                            int32_t out_stride, void* stream) {
+extern "C" int vmvo_grid_search_f64(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n_windows,
+                                    const int64_t* d_win_start, const int32_t* d_win_len,
+                                    const int32_t* d_win_drive, const double* d_dt_per_drive,
+                                    const double* d_vo, const double* d_gps, const double* d_imu,
+                                    const double* d_seeds, vmvo_window_result* d_results,
+                                    double* d_out_poses, double* d_out_steer, double* d_out_vel,
+                                    int32_t out_stride, void* stream) {
+  return grid_search_impl(ctx, cfg, n_windows, d_win_start, d_win_len, d_win_drive, d_dt_per_drive,
+                          d_vo, d_gps, d_imu, true, d_seeds, d_results, d_out_poses, d_out_steer,
+                          d_out_vel, out_stride, nullptr, nullptr, 0, nullptr, stream);
+}
+
+// stream_f64 != 0: the pose streams are double4 / double (as in vmvo_grid_search_f64)
+extern "C" int vmvo_grid_search_chained(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n_windows,
+                                        const int64_t* d_win_start, const int32_t* d_win_len,
+                                        const int32_t* d_win_drive, const double* d_dt_per_drive,
+                                        const void* d_vo, const void* d_gps, const void* d_imu,
+                                        int32_t stream_f64, int64_t n_runs,
+                                        const int64_t* d_run_offsets, vmvo_window_result* d_results,
+                                        double* d_out_poses, double* d_out_steer, double* d_out_vel,
+                                        int32_t out_stride, void* stream) {
   if (!d_run_offsets) return fail(ctx, VMVO_ERR_BAD_ARG, "d_run_offsets is NULL");
   return grid_search_impl(ctx, cfg, n_windows, d_win_start, d_win_len, d_win_drive, d_dt_per_drive,
-                          d_vo, d_gps, d_imu, nullptr, d_results, d_out_poses, d_out_steer, d_out_vel,
-                          out_stride, nullptr, nullptr, n_runs, d_run_offsets, stream);
+                          d_vo, d_gps, d_imu, stream_f64 != 0, nullptr, d_results, d_out_poses,
+                          d_out_steer, d_out_vel, out_stride, nullptr, nullptr, n_runs, d_run_offsets,
+                          stream);
 }
 
 extern "C" int vmvo_grid_search_debug_f32(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n_windows,
@@ -1181,6 +1204,6 @@ extern "C" int vmvo_grid_search_debug_f32(vmvo_ctx* ctx, const vmvo_search_cfg* 
                                           float* d_scan_cost, float* d_scan_err, void* stream) {
   if (!d_scan_cost || !d_scan_err) return fail(ctx, VMVO_ERR_BAD_ARG, "debug outputs are NULL");
   return grid_search_impl(ctx, cfg, n_windows, d_win_start, d_win_len, d_win_drive, d_dt_per_drive,
-                          d_vo, d_gps, d_imu, d_seeds, d_results, nullptr, nullptr, nullptr, 0,
+                          d_vo, d_gps, d_imu, false, d_seeds, d_results, nullptr, nullptr, nullptr, 0,
                           d_scan_cost, d_scan_err, 0, nullptr, stream);
 }

@@ -71,7 +71,7 @@ def grid_run(trajectory: Trajectory, bicycle_model: BicycleModel, velocity: floa
                       if len(trajectory.theta) >= n else np.zeros(n),
                       np.asarray(trajectory.velocity, dtype=np.float64)[:n]], axis=1)
     drives = DriveSet.from_arrays([np.asarray(trajectory.time, dtype=np.float64)[:n]], [time_step],
-                                  vo=[poses])
+                                  vo=[poses], stream_dtype=np.float64)
     dev = drives.device
     plan = WindowPlan(window_offsets=[0, 1],
                       d_window_offsets=torch.tensor([0, 1], dtype=torch.int64, device=dev),

@@ -64,7 +64,9 @@ def optimize_trajectory(vo_trajectory: Trajectory, gps_trajectory: Trajectory,
     vo = _stream(vo_trajectory, N)
     gps = _stream(gps_trajectory, N)
     imu = None if imu_yaw is None else [np.asarray(imu_yaw, dtype=np.float64)[:N]]
-    drives = DriveSet.from_arrays([gps_time[:N]], [dt], vo=[vo], gps=[gps], imu=imu)
+    # float64 streams: nothing is rounded on the way in (the reference is float64 throughout)
+    drives = DriveSet.from_arrays([gps_time[:N]], [dt], vo=[vo], gps=[gps], imu=imu,
+                                  stream_dtype=np.float64)
     so, traj, plan = optimize_drives(cfg, drives)
     rec = so.records()
     if np.any(rec["status"] & 4):

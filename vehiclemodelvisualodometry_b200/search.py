@@ -1,10 +1,12 @@
 """Batched tensor API of the window search: drives in HBM -> per-window results.
 
 This is the additive API beneath the reference-shaped facades (``mpc.grid_run``,
-``optimize.optimize_trajectory``): every drive of a batch is concatenated into one float4
-pose stream per sensor, the windows of all drives are planned once
-(``vmvo_plan_windows``), searched by the fused kernel (``vmvo_grid_search_f32``) and written
-back (``vmvo_write_back_f32``).  All device work goes through the C ABI of
+``optimize.optimize_trajectory``): every drive of a batch is concatenated into one pose
+stream per sensor -- float4 per frame (``stream_dtype=float32``, half the bytes) or double4
+(``float64``, no input rounding: what the facades use, the reference being float64
+throughout) -- the windows of all drives are planned once (``vmvo_plan_windows``), searched
+by the fused kernel (``vmvo_grid_search_f32`` / ``_f64``) and written back
+(``vmvo_write_back_f32`` / ``_f64``).  All device work goes through the C ABI of
 include/vmvo_b200.h on the current torch stream.
 """
 from __future__ import annotations
@@ -89,12 +91,13 @@ def _as_dev(a, dtype, device) -> Optional[torch.Tensor]:
 
 @dataclass
 class DriveSet:
-    """Drives resident in HBM: concatenated float4 pose streams + float64 stamps."""
+    """Drives resident in HBM: concatenated pose streams (all float32 or all float64) +
+    float64 stamps."""
 
     time: torch.Tensor                     # float64 [F]
-    vo: Optional[torch.Tensor]             # float32 [F, 4]
-    gps: Optional[torch.Tensor]            # float32 [F, 4]
-    imu: Optional[torch.Tensor]            # float32 [F]
+    vo: Optional[torch.Tensor]             # float32 / float64 [F, 4]
+    gps: Optional[torch.Tensor]            # float32 / float64 [F, 4]
+    imu: Optional[torch.Tensor]            # float32 / float64 [F]
     drive_offsets: List[int]               # host copy, len D+1
     d_drive_offsets: torch.Tensor          # int64 [D+1]
     dt: torch.Tensor                       # float64 [D]   step length per drive
@@ -111,11 +114,26 @@ class DriveSet:
     def device(self):
         return self.time.device
 
+    @property
+    def f64(self) -> bool:
+        """True when the pose streams are float64 (the ``_f64`` entry points)."""
+        kinds = {t.dtype for t in (self.vo, self.gps, self.imu) if t is not None}
+        if len(kinds) > 1 or not kinds <= {torch.float32, torch.float64}:
+            raise ValueError(f"pose streams must share one dtype (float32 or float64), got {kinds}")
+        return kinds == {torch.float64}
+
     @staticmethod
     def from_arrays(time: Sequence, dt: Sequence[float], vo: Optional[Sequence] = None,
                     gps: Optional[Sequence] = None, imu: Optional[Sequence] = None,
-                    device=None) -> "DriveSet":
-        """``time[d]`` float64 [n_d]; ``vo[d]`` / ``gps[d]`` [n_d, 4]; ``imu[d]`` [n_d]."""
+                    device=None, stream_dtype=np.float32) -> "DriveSet":
+        """``time[d]`` float64 [n_d]; ``vo[d]`` / ``gps[d]`` [n_d, 4]; ``imu[d]`` [n_d].
+
+        ``stream_dtype``: float32 (inputs are rounded once) or float64 (as given).
+        """
+        sd = np.dtype(stream_dtype)
+        if sd not in (np.dtype(np.float32), np.dtype(np.float64)):
+            raise ValueError("stream_dtype must be float32 or float64")
+        td = torch.float32 if sd == np.dtype(np.float32) else torch.float64
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device())
         lens = [len(t) for t in time]
@@ -136,9 +154,9 @@ class DriveSet:
 
         return DriveSet(
             time=_as_dev(cat(time, np.float64, 0), torch.float64, device),
-            vo=_as_dev(cat(vo, np.float32, 4), torch.float32, device),
-            gps=_as_dev(cat(gps, np.float32, 4), torch.float32, device),
-            imu=_as_dev(cat(imu, np.float32, 0), torch.float32, device),
+            vo=_as_dev(cat(vo, sd, 4), td, device),
+            gps=_as_dev(cat(gps, sd, 4), td, device),
+            imu=_as_dev(cat(imu, sd, 0), td, device),
             drive_offsets=offs,
             d_drive_offsets=torch.tensor(offs, dtype=torch.int64, device=device),
             dt=_as_dev(np.asarray(dt, dtype=np.float64), torch.float64, device),
@@ -244,19 +262,20 @@ def grid_search(cfg: SearchConfig, drives: DriveSet, plan: WindowPlan,
             runs = plan.d_window_offsets          # no allocation: usable under graph capture
         else:
             runs = torch.tensor([o - lo for o in offs], dtype=torch.int64, device=dev)
-        ctx.check(ctx.lib.vmvo_grid_search_chained_f32(
+        ctx.check(ctx.lib.vmvo_grid_search_chained(
             ctx.handle, C.byref(c), n, _lib.ptr(plan.win_start[lo:hi]), _lib.ptr(plan.win_len[lo:hi]),
             _lib.ptr(plan.win_drive[lo:hi]), _lib.ptr(drives.dt), _lib.ptr(drives.vo),
-            _lib.ptr(drives.gps), _lib.ptr(drives.imu), len(offs) - 1, _lib.ptr(runs),
+            _lib.ptr(drives.gps), _lib.ptr(drives.imu), int(drives.f64), len(offs) - 1, _lib.ptr(runs),
             _lib.ptr(results), _lib.ptr(so.poses), _lib.ptr(so.steer), _lib.ptr(so.vel), stride,
-            _lib.stream_ptr(dev)), "vmvo_grid_search_chained_f32")
+            _lib.stream_ptr(dev)), "vmvo_grid_search_chained")
     elif n:
-        ctx.check(ctx.lib.vmvo_grid_search_f32(
+        name = "vmvo_grid_search_f64" if drives.f64 else "vmvo_grid_search_f32"
+        ctx.check(getattr(ctx.lib, name)(
             ctx.handle, C.byref(c), n, _lib.ptr(plan.win_start[lo:hi]), _lib.ptr(plan.win_len[lo:hi]),
             _lib.ptr(plan.win_drive[lo:hi]), _lib.ptr(drives.dt), _lib.ptr(drives.vo),
             _lib.ptr(drives.gps), _lib.ptr(drives.imu), _lib.ptr(d_seeds), _lib.ptr(results),
             _lib.ptr(so.poses), _lib.ptr(so.steer), _lib.ptr(so.vel), stride,
-            _lib.stream_ptr(dev)), "vmvo_grid_search_f32")
+            _lib.stream_ptr(dev)), name)
     return so
 
 
@@ -267,6 +286,8 @@ def grid_search_debug(cfg: SearchConfig, drives: DriveSet, plan: WindowPlan,
     ctx = _lib.context(drives.device.index)
     c = cfg.to_c()
     n, dev = plan.n_windows, drives.device
+    if drives.f64:
+        raise ValueError("the debug export is built for float32 streams")
     results = torch.empty((n, 64), dtype=torch.uint8, device=dev)
     cost = torch.full((n, cfg.grid_v * cfg.grid_s), float("nan"), dtype=torch.float32, device=dev)
     err = torch.full_like(cost, float("nan"))
@@ -293,11 +314,12 @@ def write_back(cfg: SearchConfig, drives: DriveSet, plan: WindowPlan, results: t
     elif out.shape != (4, drives.n_frames) or out.dtype != torch.float64 or not out.is_contiguous():
         raise ValueError("out must be a contiguous float64 [4, n_frames] tensor")
     gps = drives.gps if blend_gps else None
-    ctx.check(ctx.lib.vmvo_write_back_f32(
+    name = "vmvo_write_back_f64" if drives.f64 else "vmvo_write_back_f32"
+    ctx.check(getattr(ctx.lib, name)(
         ctx.handle, C.byref(c), drives.n_drives, drives.n_frames, _lib.ptr(drives.d_drive_offsets),
         _lib.ptr(plan.d_window_offsets), _lib.ptr(drives.dt), _lib.ptr(drives.vo), _lib.ptr(gps),
         _lib.ptr(results), _lib.ptr(out[0]), _lib.ptr(out[1]), _lib.ptr(out[2]), _lib.ptr(out[3]),
-        _lib.stream_ptr(drives.device)), "vmvo_write_back_f32")
+        _lib.stream_ptr(drives.device)), name)
     return out
 
 

@@ -112,3 +112,11 @@ def synthetic_drives(n_drives: int, n_frames: int, seed: int = 1658384707877 % (
 
     return DriveBatch(time=time, vo=vo.astype(np.float32), gps=gps.astype(np.float32),
                       imu=imu.astype(np.float32), gt=gt, dt=dt)
+
+
+def off_float32_grid(a: np.ndarray) -> np.ndarray:
+    """float64 copy of ``a`` nudged off the float32 grid by a deterministic pattern of pure IEEE
+    operations (no libm), relative size ~1e-9: inputs for the float64 stream entry points."""
+    a = np.asarray(a, dtype=np.float64)
+    k = (np.arange(a.size, dtype=np.float64).reshape(a.shape) % 7.0) - 3.0
+    return a + (np.abs(a) + 1.0) * (k / 3.0) * 1.0e-9
