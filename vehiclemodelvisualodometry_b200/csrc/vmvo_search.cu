@@ -101,6 +101,14 @@ struct SmemLayout {
   }
 };
 
+// acceleration chunks (of C) one pass of T items can touch: items [pass*T, pass*T + T) of the
+// (chunk, j) item space, gs items per chunk
+__host__ __device__ inline int chunks_per_pass(int T, int gs) {
+  if (T % gs == 0) return T / gs;
+  if (gs % T == 0) return 1;
+  return (T + gs - 1) / gs + 1;
+}
+
 struct SmemHeader {
   uint64_t mbar[2];
   long long wid[2];
@@ -155,6 +163,16 @@ struct BandWin {       // window-level inputs, identical in every thread
 struct Band {
   float c0, c1, c2;
   __device__ __forceinline__ float err(float J) const { return fmaf(c1, sqrtf(J), fmaf(c2, J, c0)); }
+  // Largest cost that can still be a candidate under the bound U on the minimum: g(J) = J - err(J)
+  // is convex with g(0) <= 0 <= U, so {J >= 0 : g(J) <= U} = [0, T] with sqrt(T) the larger root of
+  // (1 - c2) s^2 - c1 s - (c0 + U) = 0.  One sqrt per thread instead of one per hypothesis; T is
+  // rounded up (relative 2^-16) so that the test J <= T never drops a hypothesis g(J) <= U keeps.
+  __device__ __forceinline__ float threshold(float U) const {
+    if (!(c2 < 0.5f)) return CUDART_INF_F;
+    const float a = 1.f - c2;
+    const float s = (c1 + sqrtf(fmaf(c1, c1, 4.f * a * (c0 + U)))) / (2.f * a);
+    return s * s * 1.0000153f;
+  }
 };
 
 // fast = the packed / rotation scan (scan_item_fast): headings are the affine form A_k + a_i*B_k
@@ -251,18 +269,21 @@ __device__ __forceinline__ void scan_item(int N, int gs, int vd_cols, int j, int
 #pragma unroll
   for (int c = 0; c < C; ++c) th[c] = ex[c] = ey[c] = JA[c] = JB[c] = JI[c] = 0.f;
   float vmax = 0.f, tv = 0.f, tlmax = 0.f;
+  // running pointers: the table strides are run-time values, and an index multiply per load
+  // would sit on the FMA pipe the loop is bound by
   const float* tl = TL + j;
   const float* vd = VD + m0;
+  const float2* df = Df;
 #pragma unroll 1
-  for (int k = 1; k <= N; ++k) {
-    const float tlk = tl[(k - 1) * gs];
+  for (int k = 1; k <= N; ++k, tl += gs, vd += vd_cols) {
+    const float tlk = *tl;
     float v[C];
 #pragma unroll
     for (int c4 = 0; c4 < C; c4 += 4) {
-      const float4 q = *reinterpret_cast<const float4*>(vd + (k - 1) * vd_cols + c4);
+      const float4 q = *reinterpret_cast<const float4*>(vd + c4);
       v[c4] = q.x; v[c4 + 1] = q.y; v[c4 + 2] = q.z; v[c4 + 3] = q.w;
     }
-    const float2 d = Df[k];
+    const float2 d = *++df;
     float2 dab = make_float2(0.f, 0.f);
     float ti = 0.f;
     if (DUAL) dab = Dab[k];
@@ -333,12 +354,13 @@ __device__ __forceinline__ void scan_item_fast(int N, int gs, int vd_cols, int j
   const float a1 = a0 + da, a4 = fmaf(4.f, da, a0), a5 = fmaf(5.f, da, a0), da2 = da + da;
   const float* tl = TL + j;
   const float* vd = VD + m0;
+  const float2* df = Df;
 #pragma unroll 1
-  for (int k = 1; k <= N; ++k) {
-    const float tlk = tl[(k - 1) * gs];
-    const float4 va = *reinterpret_cast<const float4*>(vd + (k - 1) * vd_cols);
-    const float4 vb = *reinterpret_cast<const float4*>(vd + (k - 1) * vd_cols + 4);
-    const float2 d = Df[k];
+  for (int k = 1; k <= N; ++k, tl += gs, vd += vd_cols) {
+    const float tlk = *tl;
+    const float4 va = *reinterpret_cast<const float4*>(vd);
+    const float4 vb = *reinterpret_cast<const float4*>(vd + 4);
+    const float2 d = *++df;
     float2 dab = pk(0.f, 0.f);
     if (DUAL) dab = Dab[k];
     const float kdt2 = (float)k * dt2;
@@ -783,7 +805,15 @@ vmvo_window_search_kernel(const SearchParams p) {
         bw.eps_tl = (10.f + (float)p.kappa) * u;
         bw.wpos = wA + (DUAL ? wB : 0.f);
         bw.wimu = IMU ? wI : 0.f;
-        bw.c2 = 2.0f * (2.f * u * sqrtf(24.f * bw.s2) + 24.f * u * u * bw.s2 + 2.f * (n + 2.f) * u + 16.f * u);
+        // J-proportional part.  The error recurrence rounds twice per step, each <= u*|e_m| (+ u*vmax,
+        // carried by q1); by Cauchy-Schwarz sum_{m<=k} |e_m| <= sqrt(k) * sqrt(J_A), so the pose error
+        // from these roundings after k steps is <= 2u*sqrt(k)*sqrt(J_A), and over both axes and the
+        // three-term split sum_k (.)^2 <= S1*u^2*J_A with S1 = 6 * 4 * sum k = 12 N (N+1).  With two
+        // position terms the recurrence state is A's error: J_A <= J / w_A, and
+        // w_A*J_A + w_B*sqrt(J_A*J_B) <= (1 + w_B/(2 w_A)) * J.  Last: rounding of the cost sums.
+        const float S1 = 12.f * n * (n + 1.f);
+        const float fac = DUAL ? 1.f + wB / (2.f * wA) : 1.f;
+        bw.c2 = 2.0f * (fac * (2.f * u * sqrtf(S1) + u * u * S1) + 2.f * (n + 2.f) * u + 16.f * u);
       }
       float U = CUDART_INF_F;          // upper bound on the true minimum cost
       float Uw = CUDART_INF_F;         // this warp's tightened copy (after float64 re-scores)
@@ -870,10 +900,13 @@ vmvo_window_search_kernel(const SearchParams p) {
               }
           }
         }
+        // upper bound on the minimum: J + err(J) grows with J, so only the item's smallest cost
+        // needs the band evaluated
         float m = CUDART_INF_F;
 #pragma unroll
         for (int c = 0; c < kC; ++c)
-          if ((valid >> c) & 1u) m = fminf(m, so.J[c] + band.err(so.J[c]));  // fminf drops NaN
+          if ((valid >> c) & 1u) m = fminf(m, so.J[c]);  // fminf drops NaN
+        if (m < CUDART_INF_F) m += band.err(m);
         m = warp_min_f32_nonneg(fmaxf(m, 0.f));
         if (lane == 0) hd->red[warp] = m;
         team.sync();
@@ -881,9 +914,10 @@ vmvo_window_search_kernel(const SearchParams p) {
         bm = warp_min_f32_nonneg(bm);
         U = fminf(U, bm);
         unsigned pend = 0;
+        const float Jcut = band.threshold(U);   // J - err(J) <= U  <=>  J <= Jcut; NaN stays in
 #pragma unroll
         for (int c = 0; c < kC; ++c)
-          if (((valid >> c) & 1u) && !(so.J[c] - band.err(so.J[c]) > U)) pend |= 1u << c;
+          if (((valid >> c) & 1u) && !(so.J[c] > Jcut)) pend |= 1u << c;
         // drop structural duplicates: only the lowest index of a class can win (np.argmin)
         if (j > wi.sat_lo && j <= wi.sat_hi) pend = 0;
 #pragma unroll
@@ -1068,7 +1102,7 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
   // ... unless the per-team tables would not leave room for two CTAs per SM
   for (;;) {
     const int th = tw * 32;
-    int ch = (th + p.gs - 1) / p.gs + 1;
+    int ch = chunks_per_pass(th, p.gs);
     if (ch > p.n_ic) ch = p.n_ic;
     const SmemLayout probe(cfg->max_window_poses, p.gs, ch * kC, tw, (int)load_vo + (int)load_gps,
                            use_vo && use_gps, use_imu, cfg->target_mode == VMVO_TARGET_TRAVERSE,
@@ -1092,7 +1126,7 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
   }
   const int threads = tw * 32;
   // accelerations one pass can touch: items [pass*T, pass*T + T) span at most this many chunks
-  int chunks = (threads + p.gs - 1) / p.gs + 1;
+  int chunks = chunks_per_pass(threads, p.gs);
   if (chunks > p.n_ic) chunks = p.n_ic;
   p.vd_cols = chunks * kC;
   p.target_mode = cfg->target_mode;
