@@ -44,8 +44,8 @@ BASE_SEED = 1658384707877 % (2 ** 32)
 # ops (tan = sin + cos + rcp) and 25 FP32 flops
 MUFU_PER_HSTEP = 5
 FLOP_PER_HSTEP = 25
-# executed by the kernel per hypothesis-step at C = 8 hypotheses per thread
-EXEC_MUFU_PER_HSTEP = 2.0
+# (what the kernel executes per hypothesis-step depends on the scan it selects:
+# search.executed_mufu_per_hypothesis_step)
 
 WORKLOADS = {
     # name: (frames per drive, grid_v, grid_s, window steps)
@@ -281,7 +281,7 @@ def run_b200(args):
     }
 
     if rank == 0:
-        line["roofline"] = roofline(ctx, dev, hsteps, kern_ms, n_frames, n_win, clocks, args)
+        line["roofline"] = roofline(ctx, dev, hsteps, kern_ms, n_frames, n_win, clocks, args, cfg)
         line.update(extras)
         if world == 1 and not args.no_extras:
             line["cpu_baseline"] = cpu_baseline(args.workload, budget_s=12.0)
@@ -314,8 +314,12 @@ def probe_peak(ctx, dev, kind, ops_per_iter):
     return blocks * threads * iters * ops_per_iter / (best * 1e-3)
 
 
-def roofline(ctx, dev, hsteps, kern_ms, n_frames, n_win, clocks, args):
+def roofline(ctx, dev, hsteps, kern_ms, n_frames, n_win, clocks, args, cfg):
     import torch
+
+    from vehiclemodelvisualodometry_b200.search import executed_mufu_per_hypothesis_step
+
+    EXEC_MUFU_PER_HSTEP = executed_mufu_per_hypothesis_step(cfg)
 
     peaks = {}
     try:

@@ -412,6 +412,15 @@ class DrivePipeline:
         return self.records.cpu().numpy().view(_lib.RESULT_DTYPE).reshape(-1)
 
 
+def executed_mufu_per_hypothesis_step(cfg: SearchConfig) -> float:
+    """SFU operations the search kernel issues per hypothesis-step: 2 in the generic
+    scan (sin + cos; tan is hoisted into a table), 1.25 in the packed / rotation scan, which
+    grid_search_impl (csrc/vmvo_search.cu) selects for grids of >= 128 thread-items without an
+    IMU term."""
+    items = -(-int(cfg.grid_v) // 8) * int(cfg.grid_s)
+    return 1.25 if (items >= 128 and cfg.w_imu == 0) else 2.0
+
+
 def hypothesis_steps(cfg: SearchConfig, records: np.ndarray) -> int:
     """Sum over windows of G_v * G_s * N_w: the unit of the throughput metric."""
     return int(cfg.grid_v) * int(cfg.grid_s) * int(records["n_steps"].astype(np.int64).sum())
