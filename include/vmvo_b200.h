@@ -50,6 +50,14 @@ enum {
   VMVO_WIN_TOO_LONG = 4   /* more poses than cfg.max_window_poses: window not searched      */
 };
 
+/* per-file status bits of vmvo_csv_parse_f64 */
+enum {
+  VMVO_CSV_BAD_NUMBER = 1,      /* a wanted field is not a number (pandas: column dtype object)   */
+  VMVO_CSV_TOO_MANY_FIELDS = 2, /* a row has more fields than the header (pandas: ParserError)    */
+  VMVO_CSV_BAD_ROT = 4,         /* a rot field does not hold nine numbers                         */
+  VMVO_CSV_UNSORTED = 8         /* the sorted_slot column decreases somewhere                     */
+};
+
 /* per-sequence failure kinds of vmvo_rollout_* (the two asserts of bicycle_model.py:48-62) */
 enum { VMVO_FAIL_NONE = 0, VMVO_FAIL_STEER = 1, VMVO_FAIL_ACCEL = 2 };
 
@@ -220,10 +228,13 @@ int vmvo_smooth_f64(vmvo_ctx* ctx, int32_t n_drives, int64_t total_frames, const
                     const double* d_x, const double* d_y, int32_t window, double* d_out_x,
                     double* d_out_y, void* stream);
 /* process_vo_trajectory (vmvo/utils/trajectory.py:13-65): d_rot [frames][9] row-major 3x3,
- * d_stamp_ms the Timestamp column.  Outputs [frames] each.                                   */
+ * d_stamp_ms the Timestamp column.  Outputs [frames] each.  yaw_f32 != 0: the rotation entries
+ * are float32 values (the cached trajectory, bdd_raw.py:163-164) and the yaw is atan2f in
+ * float32, as np.arctan2 on float32 scalars is (trajectory.py:28); 0: float64 atan2.          */
 int vmvo_vo_prepare_f64(vmvo_ctx* ctx, int32_t n_drives, int64_t total_frames,
                         const int64_t* d_offsets, const double* d_x, const double* d_y,
                         const double* d_rot, const double* d_stamp_ms, double scale, int32_t window,
+                        int32_t yaw_f32,
                         double* d_out_x, double* d_out_y, double* d_out_theta, double* d_out_vel,
                         double* d_out_time, void* stream);
 /* process_gps_trajectory (vmvo/utils/trajectory.py:177-335, with geodetic_to_euclidean
@@ -237,6 +248,48 @@ int vmvo_gps_prepare_f64(vmvo_ctx* ctx, int32_t n_drives, int64_t total_frames,
                          const double* d_speed, const double* d_stamp_ms, int32_t window,
                          void* d_scratch, double* d_out_x, double* d_out_y, double* d_out_theta,
                          double* d_out_vel, double* d_out_time, int32_t* d_status, void* stream);
+
+/* ---- next row: the reference's on-disk formats -------------------------------
+ * <id>.csv, the Android log read by pd.read_csv (vmvo/datasets/bdd/bdd_raw.py:53-55; columns
+ * Timestamp [ms], Latitude, Longitude, heading, speed: vmvo/utils/trajectory.py:191-228), and
+ * <id>_traj.csv, the cached VO trajectory (bdd_raw.py:150-168, 331-332: x, y, z, rot with
+ * rot = str(3x3 ndarray), a quoted field spanning three lines).  The raw bytes of n_files files
+ * sit concatenated in d_bytes (16-byte aligned; file f occupies [file_off[f], file_off[f] +
+ * file_len[f]), every file_off a multiple of 16, the buffer readable up to the next multiple of
+ * 16).  h_* are HOST copies of the same two arrays (grid sizes are derived from them).
+ * Well-formed CSV is assumed: quotes delimit fields or are doubled inside quoted fields.
+ *
+ *   1. vmvo_csv_count_rows -> d_row_counts[n_files]: non-blank lines per file (header included;
+ *      newlines inside quoted fields do not end a line).  d_scratch: vmvo_csv_scratch_bytes.
+ *   2. the caller turns the counts into d_row_off[n_files + 1] (exclusive prefix sum) and calls
+ *      vmvo_csv_index_rows (same d_scratch, untouched in between) -> d_row_starts[total_rows]:
+ *      byte offset of every line.
+ *   3. vmvo_csv_parse_f64: the first line of a file is its header; for every other line the
+ *      field with index c of file f goes to output slot d_colmap[f * 64 + c]: -1 = ignored,
+ *      0 .. n_slots-1 = number converted like pandas' default converter (precise_xstrtod:
+ *      bit-identical to what pd.read_csv returns, including its last-digit behaviour on 16-17
+ *      digit inputs), 1000 = the rot field (nine numbers, each the correctly rounded double
+ *      rounded to float32 like np.array(tokens).astype(np.float32), bdd_raw.py:157-165).
+ *      d_out [n_slots][n_data] and d_rot [n_data][9] (may be NULL), n_data = total_rows - n_files,
+ *      data rows of all files back to back.  Empty / NA fields and short rows give NaN.
+ *      d_n_fields[f] = fields in the header of file f.  sorted_slot >= 0: that slot is checked to
+ *      be non-decreasing within each file (bdd_raw.py:55 sorts by Timestamp).
+ *      d_status[n_files]: VMVO_CSV_* bits.                                                    */
+int64_t vmvo_csv_scratch_bytes(int32_t n_files, const int64_t* h_file_len);
+int vmvo_csv_count_rows(vmvo_ctx* ctx, const uint8_t* d_bytes, int32_t n_files,
+                        const int64_t* h_file_off, const int64_t* h_file_len,
+                        const int64_t* d_file_off, const int64_t* d_file_len, void* d_scratch,
+                        int64_t* d_row_counts, void* stream);
+int vmvo_csv_index_rows(vmvo_ctx* ctx, const uint8_t* d_bytes, int32_t n_files,
+                        const int64_t* h_file_off, const int64_t* h_file_len,
+                        const int64_t* d_file_off, const int64_t* d_file_len, void* d_scratch,
+                        const int64_t* d_row_off, int64_t* d_row_starts, void* stream);
+int vmvo_csv_parse_f64(vmvo_ctx* ctx, const uint8_t* d_bytes, int32_t n_files,
+                       const int64_t* d_file_off, const int64_t* d_file_len,
+                       const int64_t* d_row_off, const int64_t* d_row_starts, int64_t total_rows,
+                       const int32_t* d_colmap, const int32_t* d_n_fields, int32_t n_slots,
+                       int32_t sorted_slot, double* d_out, double* d_rot, int32_t* d_status,
+                       void* stream);
 
 /* ---- measurement helpers ------------------------------------------------------------ */
 /* Issue-rate microbenchmarks used for the roofline denominators (bench.py): each thread

@@ -52,10 +52,12 @@ def process_vo(x, y, rot, stamp_ms, scale=0.25, window=20) -> Dict[str, np.ndarr
     """vmvo/utils/trajectory.py:13-65.  ``rot`` [n, 3, 3]; ``stamp_ms`` the Timestamp column."""
     x = np.asarray(x, dtype=np.float64)
     y = np.asarray(y, dtype=np.float64)
-    rot = np.asarray(rot, dtype=np.float64)
+    rot = np.asarray(rot)
+    if rot.dtype != np.float32:     # float32 matrices (the cached trajectory, bdd_raw.py:163-164)
+        rot = rot.astype(np.float64)  # give a float32 arctan2, like the reference's scalar calls
     t = np.asarray(stamp_ms, dtype=np.float64)
     n = len(x)
-    theta = np.arctan2(rot[:, 1, 0], rot[:, 0, 0])
+    theta = np.arctan2(rot[:, 1, 0], rot[:, 0, 0]).astype(np.float64)
     vel = np.zeros(n, dtype=np.float64)
     for i in range(n - 1):
         dist = np.sqrt((x[i] - x[i + 1]) ** 2 + (y[i] - y[i + 1]) ** 2)

@@ -10,5 +10,7 @@ from .search import (DrivePipeline, DriveSet, SearchConfig, SearchOutput, Window
                      grid_search, hypothesis_steps, optimize_drives, plan_windows, write_back)
 from .mpc import grid_run, mpc_run, sequence_cost, traverse_trajectory  # noqa: F401
 from .optimize import DEFAULT_CFG, REFERENCE_CFG, optimize_trajectory  # noqa: F401
+from .dataset import (load_android_drive, load_android_drives_device, optimize_android_drives,  # noqa: F401
+                      parse_csv_files, prepare_android_drives, read_csv)
 
 __version__ = "0.1.0"

@@ -19,6 +19,8 @@ _c_i32, _c_i64, _c_f64, _c_f32, _c_vp = C.c_int32, C.c_int64, C.c_double, C.c_fl
 VMVO_OK = 0
 WIN_EMPTY, WIN_NONFINITE, WIN_TOO_LONG = 1, 2, 4
 FAIL_NONE, FAIL_STEER, FAIL_ACCEL = 0, 1, 2
+CSV_BAD_NUMBER, CSV_TOO_MANY_FIELDS, CSV_BAD_ROT, CSV_UNSORTED = 1, 2, 4, 8
+CSV_SLOT_ROT, CSV_MAX_COLS = 1000, 64
 WINDOW_FRAMES, WINDOW_TIME = 0, 1
 TARGET_TIME, TARGET_TRAVERSE = 0, 1
 SEED_DATA, SEED_GIVEN, SEED_CHAINED = 0, 1, 2
@@ -82,10 +84,16 @@ _SIGNATURES = {
     "vmvo_traverse_f64": (C.c_int, [_c_vp, _c_i32, _c_vp, _c_f64, _c_vp, _c_vp, _c_vp]),
     "vmvo_smooth_f64": (C.c_int, [_c_vp, _c_i32, _c_i64, _c_vp, _c_vp, _c_vp, _c_i32, _c_vp, _c_vp, _c_vp]),
     "vmvo_vo_prepare_f64": (C.c_int, [_c_vp, _c_i32, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_f64,
-                                      _c_i32, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),
+                                      _c_i32, _c_i32, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),
     "vmvo_gps_prepare_scratch_bytes": (_c_i64, [_c_i64, _c_i32]),
     "vmvo_gps_prepare_f64": (C.c_int, [_c_vp, _c_i32, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i32,
                                        _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),
+    "vmvo_csv_scratch_bytes": (_c_i64, [_c_i32, _c_vp]),
+    "vmvo_csv_count_rows": (C.c_int, [_c_vp, _c_vp, _c_i32, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),
+    "vmvo_csv_index_rows": (C.c_int, [_c_vp, _c_vp, _c_i32, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp,
+                                      _c_vp]),
+    "vmvo_csv_parse_f64": (C.c_int, [_c_vp, _c_vp, _c_i32, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp,
+                                     _c_i32, _c_i32, _c_vp, _c_vp, _c_vp, _c_vp]),
     "vmvo_peak_probe": (C.c_int, [_c_vp, _c_i32, _c_i32, _c_i32, _c_i32, _c_vp, _c_vp]),
     "vmvo_launch_count": (_c_i64, [_c_vp]),
 }

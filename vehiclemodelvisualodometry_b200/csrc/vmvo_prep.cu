@@ -49,13 +49,16 @@ __global__ void smooth_kernel(int n_drives, const long long* off, long long tota
 // process_vo_trajectory: yaw from the rotation, speed from RAW positions over a millisecond
 // difference (quirk kept), stamps in seconds
 __global__ void vo_prepare_kernel(int n_drives, const long long* off, long long total, const double* x,
-                                  const double* y, const double* rot, const double* stamp,
+                                  const double* y, const double* rot, const double* stamp, int yaw_f32,
                                   double* theta, double* vel, double* time) {
   for (long long f = blockIdx.x * (long long)blockDim.x + threadIdx.x; f < total;
        f += (long long)gridDim.x * blockDim.x) {
     const int d = seg_of(off, n_drives, f);
     const long long f0 = off[d];
-    theta[f] = atan2(rot[f * 9 + 3], rot[f * 9 + 0]);
+    // np.arctan2(rot[1, 0], rot[0, 0]) (trajectory.py:28): float32 scalars when the rotation came
+    // from the cached trajectory (bdd_raw.py:163-164), and then the result is a float32 too
+    theta[f] = yaw_f32 ? (double)atan2f((float)rot[f * 9 + 3], (float)rot[f * 9 + 0])
+                       : atan2(rot[f * 9 + 3], rot[f * 9 + 0]);
     double v = 0.0;
     if (f > f0) {
       const double ddx = dsub(x[f - 1], x[f]), ddy = dsub(y[f - 1], y[f]);
@@ -253,7 +256,7 @@ extern "C" int vmvo_smooth_f64(vmvo_ctx* ctx, int32_t n_drives, int64_t total_fr
 extern "C" int vmvo_vo_prepare_f64(vmvo_ctx* ctx, int32_t n_drives, int64_t total_frames,
                                    const int64_t* d_offsets, const double* d_x, const double* d_y,
                                    const double* d_rot, const double* d_stamp_ms, double scale,
-                                   int32_t window, double* d_out_x, double* d_out_y,
+                                   int32_t window, int32_t yaw_f32, double* d_out_x, double* d_out_y,
                                    double* d_out_theta, double* d_out_vel, double* d_out_time,
                                    void* stream) {
   if (!ctx) return VMVO_ERR_BAD_ARG;
@@ -267,7 +270,7 @@ extern "C" int vmvo_vo_prepare_f64(vmvo_ctx* ctx, int32_t n_drives, int64_t tota
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned g = blocks_for(total_frames, 256, ctx->sm_count * 8);
   vo_prepare_kernel<<<g, 256, 0, st>>>(n_drives, (const long long*)d_offsets, total_frames, d_x, d_y,
-                                      d_rot, d_stamp_ms, d_out_theta, d_out_vel, d_out_time);
+                                      d_rot, d_stamp_ms, yaw_f32, d_out_theta, d_out_vel, d_out_time);
   int rc = check_launch(ctx, "vo_prepare_kernel");
   if (rc) return rc;
   smooth_kernel<<<g, 256, 0, st>>>(n_drives, (const long long*)d_offsets, total_frames, d_x, d_y,

@@ -59,16 +59,19 @@ def smoothen_traj(trajectory, window_size=3):
 
 
 def vo_prepare_device(d_off: torch.Tensor, n_drives: int, total: int, dx, dy, drot, dstamp,
-                      scale: float = 0.25, window: int = 20, out: Optional[torch.Tensor] = None):
+                      scale: float = 0.25, window: int = 20, out: Optional[torch.Tensor] = None,
+                      yaw_f32: bool = False):
     """Device-resident process_vo_trajectory: float64 CUDA tensors in, float64 [5, total] out
-    (rows x, y, theta, velocity, time)."""
+    (rows x, y, theta, velocity, time).  ``yaw_f32``: the rotation entries are float32 values
+    (the cached trajectory) and the yaw is a float32 atan2, as in the reference."""
     dev = dx.device
     ctx = _lib.context(dev.index)
     if out is None:
         out = torch.empty((5, total), dtype=torch.float64, device=dev)
     ctx.check(ctx.lib.vmvo_vo_prepare_f64(
         ctx.handle, n_drives, total, _lib.ptr(d_off), _lib.ptr(dx), _lib.ptr(dy), _lib.ptr(drot),
-        _lib.ptr(dstamp), float(scale), int(window), _lib.ptr(out[0]), _lib.ptr(out[1]), _lib.ptr(out[2]),
+        _lib.ptr(dstamp), float(scale), int(window), int(bool(yaw_f32)), _lib.ptr(out[0]), _lib.ptr(out[1]),
+        _lib.ptr(out[2]),
         _lib.ptr(out[3]), _lib.ptr(out[4]), _lib.stream_ptr(dev)), "vmvo_vo_prepare_f64")
     return out
 
@@ -95,12 +98,12 @@ def gps_prepare_device(d_off: torch.Tensor, n_drives: int, total: int, dlat, dlo
     return out, status, scratch
 
 
-def vo_prepare_batch(x, y, rot, stamp_ms, scale: float = 0.25, window: int = 20):
+def vo_prepare_batch(x, y, rot, stamp_ms, scale: float = 0.25, window: int = 20, yaw_f32: bool = False):
     """Batched process_vo_trajectory: lists of per-drive arrays -> list of dicts of columns."""
     dev = _device()
     offs, d_off = _offsets([len(a) for a in x], dev)
     dx, dy, dr, dt = _cat(x, dev), _cat(y, dev), _cat(rot, dev, 9), _cat(stamp_ms, dev)
-    out = vo_prepare_device(d_off, len(offs) - 1, offs[-1], dx, dy, dr, dt, scale, window)
+    out = vo_prepare_device(d_off, len(offs) - 1, offs[-1], dx, dy, dr, dt, scale, window, yaw_f32=yaw_f32)
     o = out.cpu().numpy()
     names = ("x", "y", "theta", "velocity", "time")
     return [{k: o[c, a:b] for c, k in enumerate(names)} for a, b in zip(offs, offs[1:])]
@@ -129,9 +132,14 @@ def gps_prepare_batch(lat, lon, speed, stamp_ms, window: int = 20):
 def process_vo_trajectory(trajectory, scale: float = 0.25, smoothen_window: int = 20) -> Trajectory:
     """DataFrame with columns x, y, rot (3x3 per row), Timestamp [ms] -> Trajectory
     (vmvo/utils/trajectory.py:13-65)."""
-    rot = np.stack([np.asarray(r, dtype=np.float64) for r in trajectory["rot"].tolist()])
+    rots = [np.asarray(r) for r in trajectory["rot"].tolist()]
+    # the cached trajectory holds float32 matrices (bdd_raw.py:163-164): np.arctan2 then works,
+    # and returns, in float32 (trajectory.py:28)
+    yaw_f32 = len(rots) > 0 and all(r.dtype == np.float32 for r in rots)
+    rot = np.stack([r.astype(np.float64) for r in rots])
     (c,) = vo_prepare_batch([np.asarray(trajectory["x"])], [np.asarray(trajectory["y"])], [rot],
-                            [np.asarray(trajectory["Timestamp"].tolist())], scale, smoothen_window)
+                            [np.asarray(trajectory["Timestamp"].tolist())], scale, smoothen_window,
+                            yaw_f32=yaw_f32)
     return Trajectory(**{k: v for k, v in c.items()})
 
 
