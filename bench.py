@@ -260,6 +260,7 @@ def run_b200(args):
     if rank == 0 and world == 1 and not args.no_extras:
         extras["dense_grid"] = dense_grid(ctx, dev, timed, args)
         extras["prep"] = prep_rows(ctx, dev, timed)
+        extras["formats"] = formats_rows(ctx, dev, timed)
     clocks = sampler.stop() if rank == 0 else None
 
     line = {
@@ -404,6 +405,57 @@ def prep_rows(ctx, dev, timed):
             "vo_hbm": {"achieved_gbs": vo_gbs, "peak_gbs": hbm, "frac": vo_gbs / hbm},
             "gps_hbm": {"achieved_gbs": gps_gbs, "peak_gbs": hbm, "frac": gps_gbs / hbm},
             "note": "GPS includes the per-drive sequential path sum and de-duplication scan (one warp per drive)"}
+
+
+def formats_rows(ctx, dev, timed):
+    """the reference's two CSV files of 64 drives x 10 000 rows, bytes resident in HBM
+    -> numeric columns (and the 3x3 rot matrices) resident in HBM, through parse_staged (row index,
+    field split, number conversion; includes the one host round trip that sizes the outputs).
+    HBM-bound in principle: algorithmic bytes = the file bytes once + the columns written.  Beside it
+    the reference's own reader (pandas.read_csv + parse_rot, bdd_raw.py:53,155-167) on one host core."""
+    import io
+
+    import pandas as pd
+
+    from oracle.csv_oracle import parse_rot
+    from oracle.make_golden_prep import gps_frame, vo_frame
+    from vehiclemodelvisualodometry_b200.dataset import (CACHE_COLUMNS, LOG_COLUMNS, parse_staged,
+                                                         stage_csv_files)
+
+    D, n = 64, 10000
+    x, y, rot, _ = vo_frame(n, 1)
+    lat, lon, heading, speed, stamp = gps_frame(n, 2)
+    b1, b2 = io.StringIO(), io.StringIO()
+    pd.DataFrame({"Timestamp": stamp, "Latitude": lat, "Longitude": lon, "heading": heading,
+                  "speed": speed}).to_csv(b1, index=False)
+    pd.DataFrame({"x": list(x), "y": list(y), "z": list(x * 0), "rot": [r for r in rot]}).to_csv(b2, index=False)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    out = {"workload": f"{D} drives x {n} rows per file"}
+    for name, text, cols, rc, sc in (("log", b1.getvalue(), LOG_COLUMNS, None, "Timestamp"),
+                                     ("cache", b2.getvalue(), CACHE_COLUMNS, "rot", None)):
+        blob = text.encode()
+        st = stage_csv_files([blob] * D, dev)
+        k = 5
+        ms = timed(lambda: parse_staged(st, cols, rc, sc), k, 2) / k
+        written = D * n * 8 * (len(cols) + (9 if rc else 0))
+        gbs = (st.n_bytes + written) / (ms * 1e-3) / 1e9
+        t0 = time.perf_counter()
+        df = pd.read_csv(io.BytesIO(blob))
+        if rc:
+            df[rc] = df[rc].apply(parse_rot)
+        cpu_s = time.perf_counter() - t0
+        out[name] = {"file_bytes": st.n_bytes, "ms": ms, "rows_per_s": D * n / (ms * 1e-3),
+                     "file_gbs": st.n_bytes / (ms * 1e-3) / 1e9,
+                     "hbm": {"achieved_gbs": gbs, "peak_gbs": hbm, "frac": gbs / hbm},
+                     "cpu_reference_reader": {"mb_per_s": len(blob) / cpu_s / 1e6, "cores": 1,
+                                              "sample": "one drive, pandas.read_csv"
+                                                        + (" + parse_rot" if rc else "")}}
+    return out
 
 
 def dense_grid(ctx, dev, timed, args):

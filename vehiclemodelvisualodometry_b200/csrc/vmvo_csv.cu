@@ -42,6 +42,14 @@ struct CsvBlk { int parity, cnt0, cnt1, base; };
 
 struct CsvMasks { unsigned quote, start; };
 
+// 4-bit mask of the bytes of `w` equal to `c`: exact zero-byte test on w ^ cccc, then the four
+// byte-high bits gathered by one multiply (bit 7 of byte i -> bit i)
+__device__ __forceinline__ unsigned eq4(unsigned w, unsigned c) {
+  const unsigned x = w ^ (c * 0x01010101u);
+  const unsigned t = ~((((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) | 0x7f7f7f7fu);   // 0x80 where x byte == 0
+  return (((t >> 7) * 0x00204081u) >> 21) & 0xfu;
+}
+
 // quote bits and row-start bits of the 16 bytes at `pos` (16-byte aligned) of a file [f0, f1).
 // A row starts at byte i when the byte before it is a newline (or i is the first byte of the
 // file) and the line is not blank (pandas skip_blank_lines: "\n" or "\r\n" alone); whether that
@@ -51,21 +59,17 @@ __device__ __forceinline__ CsvMasks csv_masks(const unsigned char* bytes, long l
   CsvMasks m{0u, 0u};
   if (pos >= f1) return m;
   const uint4 q = *reinterpret_cast<const uint4*>(bytes + pos);
-  const unsigned w[4] = {q.x, q.y, q.z, q.w};
   const int n = (f1 - pos) < 16 ? (int)(f1 - pos) : 16;
-  unsigned prev = pos > f0 ? bytes[pos - 1] : '\n';
-  const unsigned after = pos + 16 < f1 ? bytes[pos + 16] : '\n';
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const unsigned c = (w[i >> 2] >> (8 * (i & 3))) & 0xffu;
-    const unsigned next = i < 15 ? (w[(i + 1) >> 2] >> (8 * ((i + 1) & 3))) & 0xffu : after;
-    const bool in = i < n;
-    const bool last = i == n - 1;
-    const unsigned nx = last && pos + n >= f1 ? '\n' : next;
-    if (in && c == '"') m.quote |= 1u << i;
-    if (in && prev == '\n' && c != '\n' && !(c == '\r' && nx == '\n')) m.start |= 1u << i;
-    prev = c;
-  }
+  const unsigned in = n == 16 ? 0xffffu : (1u << n) - 1u;
+  const unsigned quote = eq4(q.x, '"') | eq4(q.y, '"') << 4 | eq4(q.z, '"') << 8 | eq4(q.w, '"') << 12;
+  const unsigned nl = (eq4(q.x, '\n') | eq4(q.y, '\n') << 4 | eq4(q.z, '\n') << 8 | eq4(q.w, '\n') << 12) & in;
+  const unsigned cr = (eq4(q.x, '\r') | eq4(q.y, '\r') << 4 | eq4(q.z, '\r') << 8 | eq4(q.w, '\r') << 12) & in;
+  const unsigned prev_nl = pos > f0 ? bytes[pos - 1] == '\n' : 1u;
+  // the byte after the last one of this thread; the end of the file acts as a newline
+  const unsigned after_nl = pos + 16 < f1 ? bytes[pos + 16] == '\n' : 1u;
+  const unsigned after = nl >> 1 | (n == 16 ? after_nl << 15 : 1u << (n - 1));   // bit i: byte i+1 is a newline
+  m.quote = quote & in;
+  m.start = (nl << 1 | prev_nl) & in & ~nl & ~(cr & after);
   return m;
 }
 
@@ -96,12 +100,12 @@ __global__ void csv_block_offsets_kernel(int n_files, const long long* file_off,
   }
 }
 
-// EMIT = false: per-block parity and row counts.  EMIT = true: row-start offsets.
-template <bool EMIT>
+// pass 1: the only pass over the bytes.  Per thread: the row starts that count if the block is
+// entered outside a quoted field (low half-word) or inside one (high half-word) -- 4 bytes of
+// scratch per 16 bytes of file -- and per block the quote parity and both row counts.
 __global__ void __launch_bounds__(kCsvThreads)
 csv_scan_kernel(const unsigned char* bytes, int n_files, const long long* file_off,
-                const long long* file_len, const long long* blk_off, CsvBlk* blk,
-                const long long* row_off, long long* row_starts) {
+                const long long* file_len, const long long* blk_off, CsvBlk* blk, unsigned* masks) {
   __shared__ int s_par[kCsvThreads / 32];
   __shared__ int s_c0[kCsvThreads / 32], s_c1[kCsvThreads / 32];
   const long long b = blockIdx.x;
@@ -124,39 +128,50 @@ csv_scan_kernel(const unsigned char* bytes, int n_files, const long long* file_o
   }
   // bit set = inside a quoted field, if the block is entered outside one
   const unsigned inq = excl ^ ((rel & 1) ? 0xffffu : 0u);
-  if (!EMIT) {
-    const int c0 = __reduce_add_sync(FULL, __popc(m.start & ~inq));
-    const int c1 = __reduce_add_sync(FULL, __popc(m.start & inq));
-    if (lane == 0) { s_c0[warp] = c0; s_c1[warp] = c1; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int t0 = 0, t1 = 0;
+  const unsigned v0 = m.start & ~inq, v1 = m.start & inq;
+  masks[b * kCsvThreads + threadIdx.x] = v0 | v1 << 16;
+  const int c0 = __reduce_add_sync(FULL, __popc(v0));
+  const int c1 = __reduce_add_sync(FULL, __popc(v1));
+  if (lane == 0) { s_c0[warp] = c0; s_c1[warp] = c1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t0 = 0, t1 = 0;
 #pragma unroll
-      for (int q = 0; q < kCsvThreads / 32; ++q) { t0 += s_c0[q]; t1 += s_c1[q]; }
-      blk[b] = CsvBlk{blk_par, t0, t1, 0};
-    }
-  } else {
-    const CsvBlk me = blk[b];
-    const unsigned valid = m.start & ~(inq ^ (me.parity ? 0xffffu : 0u));
-    const int cnt = __popc(valid);
-    int incl = cnt;
+    for (int q = 0; q < kCsvThreads / 32; ++q) { t0 += s_c0[q]; t1 += s_c1[q]; }
+    blk[b] = CsvBlk{blk_par, t0, t1, 0};
+  }
+}
+
+// pass 2: row-start offsets from the stored masks and the chained entry parities
+__global__ void __launch_bounds__(kCsvThreads)
+csv_emit_kernel(int n_files, const long long* file_off, const long long* blk_off, const CsvBlk* blk,
+                const unsigned* masks, const long long* row_off, long long* row_starts) {
+  __shared__ int s_cnt[kCsvThreads / 32];
+  const long long b = blockIdx.x;
+  const int f = file_of_block(blk_off, n_files, b);
+  const long long pos = file_off[f] + (b - blk_off[f]) * kCsvChunk + threadIdx.x * 16;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const CsvBlk me = blk[b];
+  const unsigned packed = masks[b * kCsvThreads + threadIdx.x];
+  const unsigned valid = me.parity ? packed >> 16 : packed & 0xffffu;
+  const int cnt = __popc(valid);
+  int incl = cnt;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(FULL, incl, o);
-      if (lane >= o) incl += t;
-    }
-    if (lane == 31) s_c0[warp] = incl;
-    __syncthreads();
-    long long idx = row_off[f] + me.base + (incl - cnt);
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(FULL, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_cnt[warp] = incl;
+  __syncthreads();
+  long long idx = row_off[f] + me.base + (incl - cnt);
 #pragma unroll
-    for (int q = 0; q < kCsvThreads / 32; ++q)
-      if (q < warp) idx += s_c0[q];
-    unsigned v = valid;
-    while (v) {
-      const int i = __ffs(v) - 1;
-      v &= v - 1;
-      row_starts[idx++] = pos + i;
-    }
+  for (int q = 0; q < kCsvThreads / 32; ++q)
+    if (q < warp) idx += s_cnt[q];
+  unsigned v = valid;
+  while (v) {
+    const int i = __ffs(v) - 1;
+    v &= v - 1;
+    row_starts[idx++] = pos + i;
   }
 }
 
@@ -290,20 +305,31 @@ __device__ bool numpy_float32(const unsigned char* p, const unsigned char* end, 
     *out = neg ? -CUDART_INF_F : CUDART_INF_F;
     return true;
   }
+  // w = the digits up to the last non-zero one (trailing zeros carry no information and are
+  // folded into the exponent), at most 19 of them; value = w * 10^e10
   unsigned long long w = 0;
-  int nd = 0, e10 = 0;
-  bool any = false, seen_dot = false;
+  int nd = 0, e10 = 0, tz = 0;
+  bool any = false, seen_dot = false, full = false;
   for (; p < end; ++p) {
     if (is_digit(*p)) {
       any = true;
-      if (nd < 19) {
-        if (w || *p != '0') { w = w * 10ull + (*p - '0'); ++nd; }
-        if (seen_dot) --e10;
-      } else if (!seen_dot) ++e10;       // digits beyond 19 are dropped (not produced by numpy)
+      const unsigned dgt = *p - '0';
+      if (full) { if (!seen_dot) ++e10; continue; }      // digits beyond 19 are dropped (numpy never prints them)
+      if (seen_dot) --e10;
+      if (dgt == 0) { if (w) ++tz; continue; }
+      if (nd + tz + 1 > 19) {                            // no room: this digit and the rest are dropped
+        full = true;
+        ++e10;                 // before the point: one more power of ten; after it: undo the count above
+        continue;
+      }
+      for (; tz > 0; --tz, ++nd) w *= 10ull;
+      w = w * 10ull + dgt;
+      ++nd;
     } else if (*p == '.' && !seen_dot) seen_dot = true;
     else break;
   }
   if (!any) return false;
+  e10 += tz;
   if (p < end && (*p == 'e' || *p == 'E')) {
     ++p;
     bool eneg = false;
@@ -314,7 +340,6 @@ __device__ bool numpy_float32(const unsigned char* p, const unsigned char* end, 
     e10 += eneg ? -k : k;
   }
   if (p != end) return false;
-  while (w && w % 10ull == 0ull) { w /= 10ull; ++e10; --nd; }   // trailing zeros carry no information
   double v;
   if (w == 0) v = 0.0;
   else if (e10 + nd > 45) v = CUDART_INF;          // beyond float32 either way
@@ -343,103 +368,138 @@ __device__ bool numpy_float32(const unsigned char* p, const unsigned char* end, 
 // ---- pass 3: one thread per row ------------------------------------------------------------------
 constexpr int kCsvMaxCols = 64;
 constexpr int kSlotRot = 1000;
+constexpr int kParseThreads = 256;
+constexpr int kParseStage = 48 * 1024;     // bytes of shared memory a block stages its rows in
 
-__global__ void csv_parse_kernel(const unsigned char* bytes, int n_files, const long long* file_off,
-                                 const long long* file_len, const long long* row_off,
-                                 const long long* row_starts, long long total_rows, const int* colmap,
-                                 const int* n_fields, int n_slots, long long n_data, double* out,
-                                 double* rot, int* status) {
-  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < total_rows;
-       r += (long long)gridDim.x * blockDim.x) {
-    int lo = 0, hi = n_files;     // file of the row
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (row_off[mid] <= r) lo = mid; else hi = mid;
+// one data row: bytes [pos, end) relative to `src` (the block's shared-memory copy, or the row's
+// own start in the file); 32-bit offsets keep the byte walk cheap
+__device__ __forceinline__ void csv_parse_row(const unsigned char* __restrict__ src, int pos, int end,
+                                              const int* cm, int n_fields, int n_slots, long long n_data,
+                                              long long d, double* out, double* rot, int* status) {
+  while (end > pos && (src[end - 1] == '\n' || src[end - 1] == '\r')) --end;
+  unsigned seen = 0;
+  bool seen_rot = false;
+  int st = 0, c = 0;
+  while (pos <= end) {
+    int a, b;                  // content of the field
+    if (pos < end && src[pos] == '"') {
+      a = ++pos;
+      for (;;) {
+        if (pos >= end) { b = end; break; }
+        if (src[pos] == '"') {
+          if (pos + 1 < end && src[pos + 1] == '"') { pos += 2; continue; }
+          b = pos++;
+          break;
+        }
+        ++pos;
+      }
+      while (pos < end && src[pos] != ',') ++pos;
+    } else {
+      a = pos;
+      while (pos < end && src[pos] != ',') ++pos;
+      b = pos;
     }
-    const int f = lo;
-    if (r == row_off[f]) continue;                 // the header line
-    const long long d = r - (f + 1);               // data-row index: one header per earlier file
-    const long long f1 = file_off[f] + file_len[f];
-    long long pos = row_starts[r];
-    long long end = r + 1 < row_off[f + 1] ? row_starts[r + 1] : f1;
-    while (end > pos && (bytes[end - 1] == '\n' || bytes[end - 1] == '\r')) --end;
-    const int* cm = colmap + f * kCsvMaxCols;
-    unsigned seen = 0;
-    bool seen_rot = false;
-    int st = 0, c = 0;
-    while (pos <= end) {
-      long long a, b;            // content of the field
-      if (pos < end && bytes[pos] == '"') {
-        a = ++pos;
-        for (;;) {
-          if (pos >= end) { b = end; break; }
-          if (bytes[pos] == '"') {
-            if (pos + 1 < end && bytes[pos + 1] == '"') { pos += 2; continue; }
-            b = pos++;
-            break;
-          }
-          ++pos;
-        }
-        while (pos < end && bytes[pos] != ',') ++pos;
-      } else {
-        a = pos;
-        while (pos < end && bytes[pos] != ',') ++pos;
-        b = pos;
+    const int slot = c < kCsvMaxCols ? cm[c] : -1;
+    if (slot >= 0 && slot < n_slots) {
+      double v = CUDART_NAN;
+      if (!is_na_word(src + a, b - a) && !pandas_float(src + a, src + b, &v)) {
+        v = CUDART_NAN;
+        st |= VMVO_CSV_BAD_NUMBER;
       }
-      const int slot = c < kCsvMaxCols ? cm[c] : -1;
-      if (slot >= 0 && slot < n_slots) {
-        double v = CUDART_NAN;
-        if (!is_na_word(bytes + a, (int)(b - a)) && !pandas_float(bytes + a, bytes + b, &v)) {
-          v = CUDART_NAN;
-          st |= VMVO_CSV_BAD_NUMBER;
-        }
-        out[(long long)slot * n_data + d] = v;
-        seen |= 1u << slot;
-      } else if (slot == kSlotRot && rot) {
-        // "[[ a b c]\n [ d e f]\n [ g h i]]": brackets and newlines dropped, split on white space
-        int k = 0;
-        long long t = a;
-        bool bad = false;
-        while (t < b) {
-          while (t < b && (is_space(bytes[t]) || bytes[t] == '[' || bytes[t] == ']')) ++t;
-          if (t >= b) break;
-          long long u = t;
-          while (u < b && !is_space(bytes[u]) && bytes[u] != '[' && bytes[u] != ']') ++u;
-          float v;
-          if (k < 9 && numpy_float32(bytes + t, bytes + u, &v)) rot[d * 9 + k] = (double)v;
-          else bad = true;
-          ++k;
-          t = u;
-        }
-        if (bad || k != 9) {
-          st |= VMVO_CSV_BAD_ROT;
-          for (int q = 0; q < 9; ++q) rot[d * 9 + q] = CUDART_NAN;
-        }
-        seen_rot = true;
+      out[(long long)slot * n_data + d] = v;
+      seen |= 1u << slot;
+    } else if (slot == kSlotRot && rot) {
+      // "[[ a b c]\n [ d e f]\n [ g h i]]": brackets and newlines dropped, split on white space
+      int k = 0;
+      int t = a;
+      bool bad = false;
+      while (t < b) {
+        while (t < b && (is_space(src[t]) || src[t] == '[' || src[t] == ']')) ++t;
+        if (t >= b) break;
+        int u = t;
+        while (u < b && !is_space(src[u]) && src[u] != '[' && src[u] != ']') ++u;
+        float v;
+        if (k < 9 && numpy_float32(src + t, src + u, &v)) rot[d * 9 + k] = (double)v;
+        else bad = true;
+        ++k;
+        t = u;
       }
-      ++c;
-      if (pos >= end) break;
-      ++pos;                      // the comma
-      if (pos == end) {           // a trailing comma: one more, empty, field
-        const int s2 = c < kCsvMaxCols ? cm[c] : -1;
-        if (s2 >= 0 && s2 < n_slots) { out[(long long)s2 * n_data + d] = CUDART_NAN; seen |= 1u << s2; }
-        ++c;
-        break;
-      }
-    }
-    if (c > n_fields[f]) st |= VMVO_CSV_TOO_MANY_FIELDS;   // pandas: ParserError
-    // short rows: pandas pads with NaN
-    for (int s = 0; s < n_slots; ++s)
-      if (!((seen >> s) & 1u)) out[(long long)s * n_data + d] = CUDART_NAN;
-    if (rot && !seen_rot) {
-      bool wants = false;
-      for (int q = 0; q < kCsvMaxCols; ++q) wants |= cm[q] == kSlotRot;
-      if (wants) {
-        for (int q = 0; q < 9; ++q) rot[d * 9 + q] = CUDART_NAN;
+      if (bad || k != 9) {
         st |= VMVO_CSV_BAD_ROT;
+        for (int q = 0; q < 9; ++q) rot[d * 9 + q] = CUDART_NAN;
+      }
+      seen_rot = true;
+    }
+    ++c;
+    if (pos >= end) break;
+    ++pos;                      // the comma
+    if (pos == end) {           // a trailing comma: one more, empty, field
+      const int s2 = c < kCsvMaxCols ? cm[c] : -1;
+      if (s2 >= 0 && s2 < n_slots) { out[(long long)s2 * n_data + d] = CUDART_NAN; seen |= 1u << s2; }
+      ++c;
+      break;
+    }
+  }
+  if (c > n_fields) st |= VMVO_CSV_TOO_MANY_FIELDS;   // pandas: ParserError
+  // short rows: pandas pads with NaN
+  for (int s = 0; s < n_slots; ++s)
+    if (!((seen >> s) & 1u)) out[(long long)s * n_data + d] = CUDART_NAN;
+  if (rot && !seen_rot) {
+    bool wants = false;
+    for (int q = 0; q < kCsvMaxCols; ++q) wants |= cm[q] == kSlotRot;
+    if (wants) {
+      for (int q = 0; q < 9; ++q) rot[d * 9 + q] = CUDART_NAN;
+      st |= VMVO_CSV_BAD_ROT;
+    }
+  }
+  if (st) atomicOr(status, st);
+}
+
+// A block takes kParseThreads consecutive rows.  Their bytes are one contiguous span of the buffer:
+// it is copied to shared memory with coalesced 16-byte loads, and the threads then walk their rows
+// byte by byte out of shared memory (rows start at arbitrary offsets, so walking them in global
+// memory costs one L1 tag lookup per thread per byte).  Spans over 48 KiB are read in place.
+__global__ void __launch_bounds__(kParseThreads)
+csv_parse_kernel(const unsigned char* bytes, int n_files, const long long* file_off,
+                 const long long* file_len, const long long* row_off, const long long* row_starts,
+                 long long total_rows, const int* colmap, const int* n_fields, int n_slots,
+                 long long n_data, double* out, double* rot, int* status) {
+  __shared__ uint4 stage[kParseStage / 16];
+  const long long buf_end = file_off[n_files - 1] + file_len[n_files - 1];
+  for (long long r0 = blockIdx.x * (long long)kParseThreads; r0 < total_rows;
+       r0 += (long long)gridDim.x * kParseThreads) {
+    const long long r1 = r0 + kParseThreads < total_rows ? r0 + kParseThreads : total_rows;
+    const long long lo = row_starts[r0] & ~15LL;
+    const long long hi = r1 < total_rows ? row_starts[r1] : buf_end;
+    const bool staged = hi - lo <= kParseStage;
+    if (staged) {
+      const uint4* g = reinterpret_cast<const uint4*>(bytes + lo);
+      const int n16 = (int)((hi - lo + 15) >> 4);
+      for (int i = threadIdx.x; i < n16; i += kParseThreads) stage[i] = g[i];
+    }
+    __syncthreads();
+    const long long r = r0 + threadIdx.x;
+    if (r < r1) {
+      int flo = 0, fhi = n_files;     // file of the row
+      while (fhi - flo > 1) {
+        const int mid = (flo + fhi) >> 1;
+        if (row_off[mid] <= r) flo = mid; else fhi = mid;
+      }
+      const int f = flo;
+      if (r != row_off[f]) {          // not the header line
+        const long long pos = row_starts[r];
+        const long long end = r + 1 < row_off[f + 1] ? row_starts[r + 1] : file_off[f] + file_len[f];
+        // data-row index r - (f + 1): one header per earlier file
+        if (staged)
+          csv_parse_row(reinterpret_cast<const unsigned char*>(stage), (int)(pos - lo), (int)(end - lo),
+                        colmap + f * kCsvMaxCols, n_fields[f], n_slots, n_data, r - (f + 1), out, rot,
+                        status + f);
+        else
+          csv_parse_row(bytes + pos, 0, (int)(end - pos), colmap + f * kCsvMaxCols, n_fields[f], n_slots,
+                        n_data, r - (f + 1), out, rot, status + f);
       }
     }
-    if (st) atomicOr(&status[f], st);
+    __syncthreads();
   }
 }
 
@@ -471,7 +531,9 @@ static long long csv_blocks(int32_t n_files, const int64_t* h_file_len) {
 
 extern "C" int64_t vmvo_csv_scratch_bytes(int32_t n_files, const int64_t* h_file_len) {
   if (n_files < 1 || !h_file_len) return 0;
-  return (int64_t)sizeof(long long) * (n_files + 1) + (int64_t)sizeof(CsvBlk) * (csv_blocks(n_files, h_file_len) + 1);
+  const long long nb = csv_blocks(n_files, h_file_len);
+  return (int64_t)sizeof(long long) * (n_files + 1) + (int64_t)sizeof(CsvBlk) * (nb + 1) +
+         (int64_t)sizeof(unsigned) * kCsvThreads * nb;
 }
 
 static int csv_check(vmvo_ctx* ctx, const void* d_bytes, int32_t n_files, const int64_t* h_file_off,
@@ -506,9 +568,9 @@ extern "C" int vmvo_csv_count_rows(vmvo_ctx* ctx, const uint8_t* d_bytes, int32_
   rc = check_launch(ctx, "csv_block_offsets_kernel");
   if (rc) return rc;
   if (nb > 0) {
-    csv_scan_kernel<false><<<(unsigned)nb, kCsvThreads, 0, st>>>(
+    csv_scan_kernel<<<(unsigned)nb, kCsvThreads, 0, st>>>(
         d_bytes, n_files, (const long long*)d_file_off, (const long long*)d_file_len, blk_off, blk,
-        nullptr, nullptr);
+        (unsigned*)(blk + nb + 1));
     rc = check_launch(ctx, "csv_scan_kernel");
     if (rc) return rc;
   }
@@ -531,10 +593,10 @@ extern "C" int vmvo_csv_index_rows(vmvo_ctx* ctx, const uint8_t* d_bytes, int32_
   CsvBlk* blk = (CsvBlk*)(blk_off + n_files + 1);
   const long long nb = csv_blocks(n_files, h_file_len);
   if (nb == 0) return VMVO_OK;
-  csv_scan_kernel<true><<<(unsigned)nb, kCsvThreads, 0, (cudaStream_t)stream>>>(
-      d_bytes, n_files, (const long long*)d_file_off, (const long long*)d_file_len, blk_off, blk,
+  csv_emit_kernel<<<(unsigned)nb, kCsvThreads, 0, (cudaStream_t)stream>>>(
+      n_files, (const long long*)d_file_off, blk_off, blk, (const unsigned*)(blk + nb + 1),
       (const long long*)d_row_off, (long long*)d_row_starts);
-  return check_launch(ctx, "csv_scan_kernel");
+  return check_launch(ctx, "csv_emit_kernel");
 }
 
 extern "C" int vmvo_csv_parse_f64(vmvo_ctx* ctx, const uint8_t* d_bytes, int32_t n_files,
@@ -555,7 +617,7 @@ extern "C" int vmvo_csv_parse_f64(vmvo_ctx* ctx, const uint8_t* d_bytes, int32_t
   cudaStream_t st = (cudaStream_t)stream;
   VMVO_CUDA(ctx, cudaMemsetAsync(d_status, 0, sizeof(int32_t) * n_files, st));
   if (n_data == 0) return VMVO_OK;
-  const int threads = 128;
+  const int threads = kParseThreads;
   long long blocks = (total_rows + threads - 1) / threads;
   if (blocks > ctx->sm_count * 64LL) blocks = ctx->sm_count * 64LL;
   csv_parse_kernel<<<(unsigned)blocks, threads, 0, st>>>(

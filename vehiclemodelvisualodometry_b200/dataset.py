@@ -68,11 +68,28 @@ class ParsedCsv:
         return len(self.row_offsets) - 1
 
 
-def parse_csv_files(sources: Sequence[Blob], wanted: Optional[Sequence[str]] = None,
-                    rot_column: Optional[str] = None, sorted_column: Optional[str] = None,
-                    device=None, check: bool = True) -> ParsedCsv:
-    """Parse the named numeric columns (default: every column of the first file except
-    ``rot_column``) of a batch of CSV files on the GPU."""
+@dataclass
+class CsvStage:
+    """The bytes of a batch of files in HBM (every file on a 16-byte boundary) + their headers."""
+
+    d_bytes: torch.Tensor                  # uint8
+    offs: np.ndarray                       # int64 [n] host
+    lens: np.ndarray                       # int64 [n] host
+    d_off: torch.Tensor
+    d_len: torch.Tensor
+    headers: List[List[str]]
+
+    @property
+    def n_files(self) -> int:
+        return len(self.headers)
+
+    @property
+    def n_bytes(self) -> int:
+        return int(self.lens.sum())
+
+
+def stage_csv_files(sources: Sequence[Blob], device=None) -> CsvStage:
+    """Host -> HBM: one pinned staging buffer, one copy."""
     import pandas.errors as pe
 
     ctx = _lib.context(None if device is None else torch.device(device).index)
@@ -85,6 +102,30 @@ def parse_csv_files(sources: Sequence[Blob], wanted: Optional[Sequence[str]] = N
     for h in headers:
         if not h:
             raise pe.EmptyDataError("No columns to parse from file")
+    lens = np.array([len(b) for b in blobs], dtype=np.int64)
+    offs = np.zeros(n, dtype=np.int64)
+    pos = 0
+    for f in range(n):
+        offs[f] = pos
+        pos += (int(lens[f]) + 15) // 16 * 16
+    stage = torch.zeros(max(pos, 16), dtype=torch.uint8).pin_memory()
+    view = stage.numpy()
+    for f, b in enumerate(blobs):
+        view[offs[f]:offs[f] + lens[f]] = np.frombuffer(b, dtype=np.uint8)
+    return CsvStage(d_bytes=stage.to(dev, non_blocking=True), offs=offs, lens=lens,
+                    d_off=torch.from_numpy(offs).to(dev), d_len=torch.from_numpy(lens).to(dev),
+                    headers=headers)
+
+
+def parse_staged(stage: CsvStage, wanted: Optional[Sequence[str]] = None, rot_column: Optional[str] = None,
+                 sorted_column: Optional[str] = None, check: bool = True) -> ParsedCsv:
+    """Row index + field split + number conversion of staged files, all on the device; the only
+    host round trip is the per-file row count that sizes the outputs."""
+    import pandas.errors as pe
+
+    dev = stage.d_bytes.device
+    ctx = _lib.context(dev.index)
+    n, headers = stage.n_files, stage.headers
     if wanted is None:
         wanted = [c for c in headers[0] if c != rot_column]
     wanted = tuple(wanted)
@@ -103,21 +144,8 @@ def parse_csv_files(sources: Sequence[Blob], wanted: Optional[Sequence[str]] = N
             elif rot_column is not None and name == rot_column:
                 colmap[f, c] = _lib.CSV_SLOT_ROT
     n_fields = np.array([len(h) for h in headers], dtype=np.int32)
-
-    # every file starts on a 16-byte boundary of one pinned staging buffer
-    lens = np.array([len(b) for b in blobs], dtype=np.int64)
-    offs = np.zeros(n, dtype=np.int64)
-    pos = 0
-    for f in range(n):
-        offs[f] = pos
-        pos += (int(lens[f]) + 15) // 16 * 16
-    stage = torch.zeros(max(pos, 16), dtype=torch.uint8).pin_memory()
-    view = stage.numpy()
-    for f, b in enumerate(blobs):
-        view[offs[f]:offs[f] + lens[f]] = np.frombuffer(b, dtype=np.uint8)
-    d_bytes = stage.to(dev, non_blocking=True)
-    d_off, d_len = torch.from_numpy(offs).to(dev), torch.from_numpy(lens).to(dev)
-    h_off, h_len = offs.ctypes.data, lens.ctypes.data
+    d_bytes, d_off, d_len = stage.d_bytes, stage.d_off, stage.d_len
+    h_off, h_len = stage.offs.ctypes.data, stage.lens.ctypes.data
     sp = _lib.stream_ptr(dev)
     scratch = torch.empty(int(ctx.lib.vmvo_csv_scratch_bytes(n, h_len)), dtype=torch.uint8, device=dev)
     counts = torch.empty(n, dtype=torch.int64, device=dev)
@@ -154,6 +182,14 @@ def parse_csv_files(sources: Sequence[Blob], wanted: Optional[Sequence[str]] = N
                 raise ValueError(f"file {f}: a rot field does not hold nine numbers")
     data_off = [int(row_off[f] - f) for f in range(n + 1)]
     return ParsedCsv(names=wanted, columns=cols, rot=rot, row_offsets=data_off, status=st)
+
+
+def parse_csv_files(sources: Sequence[Blob], wanted: Optional[Sequence[str]] = None,
+                    rot_column: Optional[str] = None, sorted_column: Optional[str] = None,
+                    device=None, check: bool = True) -> ParsedCsv:
+    """Parse the named numeric columns (default: every column of the first file except
+    ``rot_column``) of a batch of CSV files on the GPU."""
+    return parse_staged(stage_csv_files(sources, device), wanted, rot_column, sorted_column, check)
 
 
 def read_csv(source: Blob, columns: Optional[Sequence[str]] = None, rot_column: Optional[str] = None):
