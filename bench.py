@@ -417,14 +417,21 @@ def formats_rows(ctx, dev, timed):
 
     import pandas as pd
 
-    from oracle.csv_oracle import parse_rot
-    from oracle.make_golden_prep import gps_frame, vo_frame
+    from oracle.csv_oracle import parse_rot          # the CPU leg only: the reference's rot un-stringifier
     from vehiclemodelvisualodometry_b200.dataset import (CACHE_COLUMNS, LOG_COLUMNS, parse_staged,
                                                          stage_csv_files)
 
     D, n = 64, 10000
-    x, y, rot, _ = vo_frame(n, 1)
-    lat, lon, heading, speed, stamp = gps_frame(n, 2)
+    rng = np.random.default_rng(7)
+    yaw = np.cumsum(rng.normal(0, 0.01, n))
+    rot = np.zeros((n, 3, 3))
+    rot[:, 0, 0], rot[:, 0, 1], rot[:, 1, 0], rot[:, 1, 1], rot[:, 2, 2] = (np.cos(yaw), -np.sin(yaw),
+                                                                            np.sin(yaw), np.cos(yaw), 1)
+    x, y = np.cumsum(rng.normal(0.5, 0.2, n)), np.cumsum(rng.normal(0.1, 0.2, n))
+    lat = np.repeat(12.97 + np.cumsum(rng.normal(2e-6, 1e-6, n // 2)), 2)
+    lon = np.repeat(77.59 + np.cumsum(rng.normal(3e-6, 1e-6, n // 2)), 2)
+    heading, speed = rng.uniform(0, 360, n), np.abs(rng.normal(8, 2, n))
+    stamp = 1658384707877 + 50 * np.arange(n)
     b1, b2 = io.StringIO(), io.StringIO()
     pd.DataFrame({"Timestamp": stamp, "Latitude": lat, "Longitude": lon, "heading": heading,
                   "speed": speed}).to_csv(b1, index=False)
