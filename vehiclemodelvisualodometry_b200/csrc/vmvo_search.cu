@@ -77,7 +77,7 @@ struct WinInfo {
 // ---- shared-memory carve-up (same function on host and device) ---------------------------
 struct SmemLayout {
   int off_raw, off_loc, off_loci, off_tgt, off_df, off_dab, off_fi, off_keep, off_tl, off_js,
-      off_vd, off_cand, total;
+      off_ts, off_vd, off_cand, total;
   // P poses per window, n_streams pose streams staged, optional terms only when configured
   __host__ __device__ SmemLayout(int P, int gs, int vd_cols, int team_warps, int n_streams,
                                  bool dual, bool imu, bool traverse, int pose_bytes) {
@@ -93,6 +93,7 @@ struct SmemLayout {
     o = (o + 15) & ~15;
     off_tl = o;   o += P * gs * 4;              // float TL[k][j]
     off_js = o;   o += ((gs + 3) & ~3) * 4;     // float K * sum_k S_k(j)^2 (steering penalty)
+    off_ts = o;   o += 3 * ((gs + 3) & ~3) * 4; // float max_k |TL|, sum_k |TL|, sum_k k |TL|  per j
     o = (o + 15) & ~15;
     off_vd = o;   o += P * vd_cols * 4;         // float VD[k][m]
     o = (o + 15) & ~15;
@@ -109,10 +110,21 @@ __host__ __device__ inline int chunks_per_pass(int T, int gs) {
   return (T + gs - 1) / gs + 1;
 }
 
+// window-level inputs of the FP32 error band
+struct BandWin {       // window-level inputs, identical in every thread
+  float n, s2, s4;     // N, sum k^2, bound on sum ((k^2+k)/2)^2
+  float dmax;          // max |target increment|
+  float dabmax;        // max |T_A - T_B|
+  float imax;          // max |imu target|
+  float eps_tl;        // relative error of TL
+  float wpos, wimu;    // weight sums
+  float c2;            // J-proportional coefficient (already includes the safety factor)
+};
 struct SmemHeader {
   uint64_t mbar[2];
   long long wid[2];
   WinInfo wi;
+  BandWin bw;
   float red[3 * kMaxWarps];
   double bcost[kMaxWarps];
   double bpose[kMaxWarps][3];
@@ -151,15 +163,6 @@ struct Team {
 // ---- FP32 error band ----------------------------------------------
 // |J_fp32 - J_fp64| <= c0 + c1*sqrt(J) + c2*J for every hypothesis of an item, from the item's
 // own step length, heading excursion and tan magnitude.
-struct BandWin {       // window-level inputs, identical in every thread
-  float n, s2, s4;     // N, sum k^2, bound on sum ((k^2+k)/2)^2
-  float dmax;          // max |target increment|
-  float dabmax;        // max |T_A - T_B|
-  float imax;          // max |imu target|
-  float eps_tl;        // relative error of TL
-  float wpos, wimu;    // weight sums
-  float c2;            // J-proportional coefficient (already includes the safety factor)
-};
 struct Band {
   float c0, c1, c2;
   __device__ __forceinline__ float err(float J) const { return fmaf(c1, sqrtf(J), fmaf(c2, J, c0)); }
@@ -254,7 +257,6 @@ __device__ double warp_cost64(const SearchParams& p, const WinInfo& wi, const do
 template <int C>
 struct ScanOut {
   float J[C];
-  float vmax, theta_tv, tlmax;   // inputs of the item's error band
 };
 
 template <int C, bool DUAL, bool IMU>
@@ -268,7 +270,6 @@ __device__ __forceinline__ void scan_item(int N, int gs, int vd_cols, int j, int
   float th[C], ex[C], ey[C], JA[C], JB[C], JI[C];
 #pragma unroll
   for (int c = 0; c < C; ++c) th[c] = ex[c] = ey[c] = JA[c] = JB[c] = JI[c] = 0.f;
-  float vmax = 0.f, tv = 0.f, tlmax = 0.f;
   // running pointers: the table strides are run-time values, and an index multiply per load
   // would sit on the FMA pipe the loop is bound by
   const float* tl = TL + j;
@@ -288,10 +289,6 @@ __device__ __forceinline__ void scan_item(int N, int gs, int vd_cols, int j, int
     float ti = 0.f;
     if (DUAL) dab = Dab[k];
     if (IMU) ti = fI[k];
-    // band statistics from the item's fastest hypothesis (VD is non-decreasing in i)
-    tv = fmaf(v[C - 1], fabsf(tlk), tv);
-    tlmax = fmaxf(tlmax, fabsf(tlk));
-    vmax = fmaxf(vmax, v[C - 1]);
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       th[c] = fmaf(v[c], tlk, th[c]);
@@ -320,9 +317,6 @@ __device__ __forceinline__ void scan_item(int N, int gs, int vd_cols, int j, int
     if (IMU) t = fmaf(wI, JI[c], t);
     out.J[c] = t;
   }
-  out.vmax = vmax;
-  out.theta_tv = tv;
-  out.tlmax = tlmax;
 }
 
 // ---- packed FP32x2 + rotation scan (C = 8, no IMU term, V_w >= 0) --------------------------------
@@ -346,71 +340,78 @@ __device__ __forceinline__ void scan_item_fast(int N, int gs, int vd_cols, int j
                                                const float2* __restrict__ Df,
                                                const float2* __restrict__ Dab, float wA, float wB,
                                                float kJS, float vwdt, float dt2, float a0, float da,
-                                               float amax, ScanOut<8>& out) {
-  float2 ex[4], ey[4], JAx[4], JAy[4], JBx[4], JBy[4];
+                                               ScanOut<8>& out) {
+  // x and y cost terms accumulate separately (JA / JA2): one chain of dependent FFMA2 per
+  // accumulator measured 7 % faster on the dense grid than a single merged one
+  float2 ex[4], ey[4], JA[4], JA2[4], JB[4];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) ex[q] = ey[q] = JAx[q] = JAy[q] = JBx[q] = JBy[q] = pk(0.f, 0.f);
-  float A = 0.f, B = 0.f, vmax = 0.f, tv = 0.f, tlmax = 0.f;
-  const float a1 = a0 + da, a4 = fmaf(4.f, da, a0), a5 = fmaf(5.f, da, a0), da2 = da + da;
+  for (int q = 0; q < 4; ++q) ex[q] = ey[q] = JA[q] = JA2[q] = JB[q] = pk(0.f, 0.f);
+  float A = 0.f, B = 0.f;
   const float* tl = TL + j;
   const float* vd = VD + m0;
   const float2* df = Df;
-#pragma unroll 1
-  for (int k = 1; k <= N; ++k, tl += gs, vd += vd_cols) {
+  // sin / cos of the eight headings of step k (advances A, B)
+  auto trig = [&](int k, float2 (&c2)[4], float2 (&s2)[4]) {
     const float tlk = *tl;
-    const float4 va = *reinterpret_cast<const float4*>(vd);
-    const float4 vb = *reinterpret_cast<const float4*>(vd + 4);
-    const float2 d = *++df;
-    float2 dab = pk(0.f, 0.f);
-    if (DUAL) dab = Dab[k];
+    tl += gs;
     const float kdt2 = (float)k * dt2;
     A = fmaf(vwdt, tlk, A);
     B = fmaf(kdt2, tlk, B);
-    // band statistics: heading bound of the fastest-changing hypothesis, largest step
-    tv = fmaf(fmaf(amax, kdt2, vwdt), fabsf(tlk), tv);
-    tlmax = fmaxf(tlmax, fabsf(tlk));
-    vmax = fmaxf(vmax, vb.w);
     float s0, c0, s1, c1, s4, c4, s5, c5, sr, cr;
     __sincosf(fmaf(a0, B, A), &s0, &c0);
-    __sincosf(fmaf(a1, B, A), &s1, &c1);
-    __sincosf(fmaf(a4, B, A), &s4, &c4);
-    __sincosf(fmaf(a5, B, A), &s5, &c5);
-    __sincosf(da2 * B, &sr, &cr);
-    float2 c2[4], s2[4];
+    __sincosf(fmaf(a0 + da, B, A), &s1, &c1);
+    __sincosf(fmaf(fmaf(4.f, da, a0), B, A), &s4, &c4);
+    __sincosf(fmaf(fmaf(5.f, da, a0), B, A), &s5, &c5);
+    __sincosf((da + da) * B, &sr, &cr);
     c2[0] = pk(c0, c1);
     s2[0] = pk(s0, s1);
     c2[2] = pk(c4, c5);
     s2[2] = pk(s4, s5);
     rot_pair(c2[0], s2[0], cr, sr, c2[1], s2[1]);
     rot_pair(c2[2], s2[2], cr, sr, c2[3], s2[3]);
+  };
+  // positions and costs of step k from its sin / cos
+  auto step = [&](int k, const float2 (&c2)[4], const float2 (&s2)[4]) {
+    const float4 va = *reinterpret_cast<const float4*>(vd);
+    const float4 vb = *reinterpret_cast<const float4*>(vd + 4);
+    vd += vd_cols;
+    const float2 d = *++df;
+    float2 dab = pk(0.f, 0.f);
+    if (DUAL) dab = Dab[k];
     const float2 v2[4] = {pk(va.x, va.y), pk(va.z, va.w), pk(vb.x, vb.y), pk(vb.z, vb.w)};
     const float2 ndx = pk(-d.x, -d.x), ndy = pk(-d.y, -d.y);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       ex[q] = __ffma2_rn(v2[q], c2[q], __fadd2_rn(ex[q], ndx));
       ey[q] = __ffma2_rn(v2[q], s2[q], __fadd2_rn(ey[q], ndy));
-      JAx[q] = __ffma2_rn(ex[q], ex[q], JAx[q]);
-      JAy[q] = __ffma2_rn(ey[q], ey[q], JAy[q]);
+      JA[q] = __ffma2_rn(ex[q], ex[q], JA[q]);
+      JA2[q] = __ffma2_rn(ey[q], ey[q], JA2[q]);
       if (DUAL) {
         const float2 bx = __fadd2_rn(ex[q], pk(dab.x, dab.x)), by = __fadd2_rn(ey[q], pk(dab.y, dab.y));
-        JBx[q] = __ffma2_rn(bx, bx, JBx[q]);
-        JBy[q] = __ffma2_rn(by, by, JBy[q]);
+        JB[q] = __ffma2_rn(bx, bx, JB[q]);
+        JB[q] = __ffma2_rn(by, by, JB[q]);
       }
     }
+  };
+#pragma unroll 1
+  for (int k = 1; k <= N; ++k) {
+    float2 c2[4], s2[4];
+    trig(k, c2, s2);
+    step(k, c2, s2);
   }
+  // (running the SFU one step ahead of the FMA pipe -- a two-stage software pipeline -- needs 16
+  // more registers, spills, and measured 13 % slower)
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    float t0 = fmaf(wA, JAx[q].x + JAy[q].x, kJS), t1 = fmaf(wA, JAx[q].y + JAy[q].y, kJS);
+    JA[q] = __fadd2_rn(JA[q], JA2[q]);
+    float t0 = fmaf(wA, JA[q].x, kJS), t1 = fmaf(wA, JA[q].y, kJS);
     if (DUAL) {
-      t0 = fmaf(wB, JBx[q].x + JBy[q].x, t0);
-      t1 = fmaf(wB, JBx[q].y + JBy[q].y, t1);
+      t0 = fmaf(wB, JB[q].x, t0);
+      t1 = fmaf(wB, JB[q].y, t1);
     }
     out.J[2 * q] = t0;
     out.J[2 * q + 1] = t1;
   }
-  out.vmax = vmax;
-  out.theta_tv = tv;
-  out.tlmax = tlmax;
 }
 
 // ---- the kernel -----------------------------------------------------------------------------
@@ -449,6 +450,8 @@ vmvo_window_search_kernel(const SearchParams p) {
   int* keep = reinterpret_cast<int*>(smem + lay.off_keep);
   float* TL = reinterpret_cast<float*>(smem + lay.off_tl);
   float* JS = reinterpret_cast<float*>(smem + lay.off_js);
+  float* TS = reinterpret_cast<float*>(smem + lay.off_ts);
+  const int gs4 = (p.gs + 3) & ~3;
   float* VD = reinterpret_cast<float*>(smem + lay.off_vd);
   uint2* cand = reinterpret_cast<uint2*>(smem + lay.off_cand);
 
@@ -465,7 +468,7 @@ vmvo_window_search_kernel(const SearchParams p) {
   const bool ksteer = p.k_steer != 0.0;
   const double kd = kDegToRad / p.ratio;   // steering-wheel degrees -> road-wheel radians
 
-  auto issue_load = [&](long long w, int buf) {  // thread 0 only
+  auto issue_load = [&](long long w, int buf) {  // the fetcher thread only
     const long long start = p.win_start[w];
     int len = p.win_len[w];
     len = len < P ? len : P;
@@ -482,9 +485,9 @@ vmvo_window_search_kernel(const SearchParams p) {
   };
 
   const bool chained = p.run_offsets != nullptr;
-  long long run_end = 0;     // thread 0: end of the run being walked (chained mode)
+  long long run_end = 0;     // fetcher thread: end of the run being walked (chained mode)
   double s_chain = 0.0;      // all threads: steering seed handed from window to window
-  // thread 0: the window after `w` -- the next one of the same run, else a fresh queue item
+  // fetcher thread: the window after `w` -- the next one of the same run, else a fresh queue item
   auto next_window = [&](long long w, int slot) -> long long {
     if (chained && w >= 0 && w + 1 < run_end) {
       hd->first[slot] = 0;
@@ -500,7 +503,10 @@ vmvo_window_search_kernel(const SearchParams p) {
     }
   };
 
-  if (tid == 0) {
+  // the queue pop and the TMA issue belong to lane 0 of the team's LAST warp: phases A1 / A2 keep
+  // warp 0 busy, so in a multi-warp team the atomic and its dependent loads overlap with them
+  const bool fetcher = tid == T - 32;
+  if (fetcher) {
     mbar_init(&hd->mbar[0], 1);
     mbar_init(&hd->mbar[1], 1);
     mbar_fence_init();
@@ -515,7 +521,7 @@ vmvo_window_search_kernel(const SearchParams p) {
     const int cur = it & 1;
     const long long w = hd->wid[cur];
     if (w >= p.n_windows) break;
-    if (tid == 0) {  // prefetch the next window's poses while this one is searched
+    if (fetcher) {  // prefetch the next window's poses while this one is searched
       const long long wn = next_window(w, cur ^ 1);
       hd->wid[cur ^ 1] = wn;
       if (wn < p.n_windows) issue_load(wn, cur ^ 1);
@@ -526,18 +532,23 @@ vmvo_window_search_kernel(const SearchParams p) {
     const double dt = p.dt_drive[p.win_drive[w]];
     mbar_wait(&hd->mbar[cur], (unsigned)((it >> 1) & 1));
 
-    vmvo_window_result res;
-    res.best_idx = -1;
-    res.n_steps = 0;
-    res.status = 0;
-    res.n_rescored = 0;
-    res.best_cost = CUDART_NAN;
-    res.v_seed = res.s_seed = CUDART_NAN;
-    res.x1 = res.y1 = res.theta1 = CUDART_NAN;
+    // the record of a window that is not searched (too long / empty): everything but the status,
+    // the step count and the seeds stays "none"
+    auto write_unsearched = [&](int st, int n_steps, double vs, double ss) {
+      vmvo_window_result r;
+      r.best_idx = -1;
+      r.n_steps = n_steps;
+      r.status = st;
+      r.n_rescored = 0;
+      r.best_cost = CUDART_NAN;
+      r.v_seed = vs;
+      r.s_seed = ss;
+      r.x1 = r.y1 = r.theta1 = CUDART_NAN;
+      p.results[w] = r;
+    };
 
     if (len > P || len < 1) {  // uniform branch
-      res.status = VMVO_WIN_TOO_LONG;
-      if (tid == 0) p.results[w] = res;
+      if (tid == 0) write_unsearched(VMVO_WIN_TOO_LONG, 0, CUDART_NAN, CUDART_NAN);
       team.sync();
       continue;
     }
@@ -767,54 +778,71 @@ vmvo_window_search_kernel(const SearchParams p) {
       imax = fmaxf(imax, hd->red[2 * kMaxWarps + q]);
     }
     const int status = (N <= 0 ? VMVO_WIN_EMPTY : 0) | (bad ? VMVO_WIN_NONFINITE : 0);
-    WinInfo wi = hd->wi;
-    wi.status = status;
-    res.n_steps = N;
-    res.status = status;
-    res.v_seed = v_seed;
-    res.s_seed = s_seed;
+    // team-uniform per-window state stays in the shared-memory header (hd->wi, hd->bw, the warps'
+    // running best): registers are for the scan
+    const WinInfo& wi = hd->wi;
 
     if (status & VMVO_WIN_EMPTY) {
-      if (tid == 0) p.results[w] = res;
+      if (tid == 0) write_unsearched(status, N, v_seed, s_seed);
       team.sync();
       continue;
     }
 
-    int best_h = -1;
-    double best_cost = CUDART_INF;
-    Pose<double> best_first{CUDART_NAN, CUDART_NAN, CUDART_NAN};
-    int n_rescored = 0;
-
-    if (status & VMVO_WIN_NONFINITE) {
-      // every hypothesis costs NaN or Inf alike: np.argmin returns index 0
-      best_h = 0;
-      best_cost = CUDART_NAN;
-    } else {
-      // ---- phase B: FP32 scan of the whole grid, candidates within the error band -------
-      BandWin bw;
-      {
-        const float u = 5.9604644775390625e-8f;
-        const float n = (float)N;
-        bw.n = n;
-        bw.s2 = n * (n + 1.f) * (2.f * n + 1.f) * (1.f / 6.f);
-        const float n2 = n + 2.f;
-        bw.s4 = 0.05f * n2 * n2 * n2 * n2 * n2;
-        bw.dmax = dmax;
-        bw.dabmax = dabmax;
-        bw.imax = imax;
-        bw.eps_tl = (10.f + (float)p.kappa) * u;
-        bw.wpos = wA + (DUAL ? wB : 0.f);
-        bw.wimu = IMU ? wI : 0.f;
-        // J-proportional part.  The error recurrence rounds twice per step, each <= u*|e_m| (+ u*vmax,
-        // carried by q1); by Cauchy-Schwarz sum_{m<=k} |e_m| <= sqrt(k) * sqrt(J_A), so the pose error
-        // from these roundings after k steps is <= 2u*sqrt(k)*sqrt(J_A), and over both axes and the
-        // three-term split sum_k (.)^2 <= S1*u^2*J_A with S1 = 6 * 4 * sum k = 12 N (N+1).  With two
-        // position terms the recurrence state is A's error: J_A <= J / w_A, and
-        // w_A*J_A + w_B*sqrt(J_A*J_B) <= (1 + w_B/(2 w_A)) * J.  Last: rounding of the cost sums.
-        const float S1 = 12.f * n * (n + 1.f);
-        const float fac = DUAL ? 1.f + wB / (2.f * wA) : 1.f;
-        bw.c2 = 2.0f * (fac * (2.f * u * sqrtf(S1) + u * u * S1) + 2.f * (n + 2.f) * u + 16.f * u);
+    // per steering rate: max |TL|, sum |TL|, sum k |TL| over the steps (the items' band inputs)
+    for (int j = tid; j < p.gs; j += T) {
+      float mx = 0.f, s0 = 0.f, s1 = 0.f;
+      const float* t = TL + j;
+      for (int k = 1; k <= N; ++k, t += p.gs) {
+        const float a = fabsf(*t);
+        mx = fmaxf(mx, a);
+        s0 += a;
+        s1 = fmaf((float)k, a, s1);
       }
+      TS[j] = mx;
+      TS[gs4 + j] = s0;
+      TS[2 * gs4 + j] = s1;
+    }
+
+    // this warp's running best (float64 cost, index, first pose) and its re-score count
+    if (lane == 0) {
+      const bool nonfinite = (status & VMVO_WIN_NONFINITE) != 0;
+      // every hypothesis of a non-finite window costs NaN or Inf alike: np.argmin returns index 0
+      hd->bh[warp] = nonfinite ? 0 : -1;
+      hd->bcost[warp] = nonfinite ? CUDART_NAN : CUDART_INF;
+      hd->bpose[warp][0] = hd->bpose[warp][1] = hd->bpose[warp][2] = CUDART_NAN;
+      hd->nres[warp] = 0;
+    }
+    if (tid == 0) {
+      hd->wi.status = status;
+      BandWin bw;
+      const float u = 5.9604644775390625e-8f;
+      const float n = (float)N;
+      bw.n = n;
+      bw.s2 = n * (n + 1.f) * (2.f * n + 1.f) * (1.f / 6.f);
+      const float n2 = n + 2.f;
+      bw.s4 = 0.05f * n2 * n2 * n2 * n2 * n2;
+      bw.dmax = dmax;
+      bw.dabmax = dabmax;
+      bw.imax = imax;
+      bw.eps_tl = (10.f + (float)p.kappa) * u;
+      bw.wpos = wA + (DUAL ? wB : 0.f);
+      bw.wimu = IMU ? wI : 0.f;
+      // J-proportional part.  The error recurrence rounds twice per step, each <= u*|e_m| (+ u*vmax,
+      // carried by q1); by Cauchy-Schwarz sum_{m<=k} |e_m| <= sqrt(k) * sqrt(J_A), so the pose error
+      // from these roundings after k steps is <= 2u*sqrt(k)*sqrt(J_A), and over both axes and the
+      // three-term split sum_k (.)^2 <= S1*u^2*J_A with S1 = 6 * 4 * sum k = 12 N (N+1).  With two
+      // position terms the recurrence state is A's error: J_A <= J / w_A, and
+      // w_A*J_A + w_B*sqrt(J_A*J_B) <= (1 + w_B/(2 w_A)) * J.  Last: rounding of the cost sums.
+      const float S1 = 12.f * n * (n + 1.f);
+      const float fac = DUAL ? 1.f + wB / (2.f * wA) : 1.f;
+      bw.c2 = 2.0f * (fac * (2.f * u * sqrtf(S1) + u * u * S1) + 2.f * (n + 2.f) * u + 16.f * u);
+      hd->bw = bw;
+    }
+    __syncwarp();
+
+    if (!(status & VMVO_WIN_NONFINITE)) {
+      // ---- phase B: FP32 scan of the whole grid, candidates within the error band -------
+      // (hd->bw and hd->wi.status become visible with the barrier that follows the first VD fill)
       float U = CUDART_INF_F;          // upper bound on the true minimum cost
       float Uw = CUDART_INF_F;         // this warp's tightened copy (after float64 re-scores)
 
@@ -826,12 +854,20 @@ vmvo_window_search_kernel(const SearchParams p) {
           const int h = (int)ce.x;
           Pose<double> first;
           const double c64 = warp_cost64<DUAL, IMU>(p, wi, tgt, P, h, lane, wA64, wB64, &first);
-          ++n_rescored;
-          if (best_h < 0 || c64 < best_cost || (c64 == best_cost && h < best_h)) {
-            best_h = h;
-            best_cost = c64;
-            best_first = first;
+          const int best_h = hd->bh[warp];
+          const double best_cost = hd->bcost[warp];
+          __syncwarp();
+          if (lane == 0) {
+            ++hd->nres[warp];
+            if (best_h < 0 || c64 < best_cost || (c64 == best_cost && h < best_h)) {
+              hd->bh[warp] = h;
+              hd->bcost[warp] = c64;
+              hd->bpose[warp][0] = first.x;
+              hd->bpose[warp][1] = first.y;
+              hd->bpose[warp][2] = first.th;
+            }
           }
+          __syncwarp();
           // a float64 cost is itself an upper bound on the minimum (rounded up to float)
           Uw = fminf(Uw, __double2float_ru(c64));
         }
@@ -875,18 +911,35 @@ vmvo_window_search_kernel(const SearchParams p) {
               const double inv = p.gv > 1 ? p.max_accel / (double)(p.gv - 1) : 0.0;
               const int i0 = ic * kC;
               const double a0d = inv * (double)(2 * i0 - (p.gv - 1));
-              const double a7d = inv * (double)(2 * (i0 + 7) - (p.gv - 1));
               const double dtd = dt * dt;
               scan_item_fast<DUAL>(N, p.gs, p.vd_cols, j, (ic - ic0) * kC, TL, VD, Df, Dab, wA, wB,
                                    ksteer ? JS[j] : 0.f, (float)(v_seed * dt), (float)dtd,
-                                   (float)a0d, (float)(2.0 * inv),
-                                   (float)fmax(fabs(a0d), fabs(a7d)), so);
+                                   (float)a0d, (float)(2.0 * inv), so);
             }
           }
           if (!fast)
             scan_item<C, DUAL, IMU>(N, p.gs, p.vd_cols, j, (ic - ic0) * kC, TL, VD, Df, Dab, fI, wA, wB,
                                     wI, ksteer ? JS[j] : 0.f, so);
-          band = make_band(bw, so.vmax, so.theta_tv, so.tlmax, fast);
+          {
+            // the item's band inputs, from the per-rate table statistics instead of from the loop:
+            // largest step of its fastest hypothesis (V_k is monotone in k, VD non-decreasing in i)
+            // and a bound on the total heading variation, sum_k step_k * |TL_k| with
+            // step_k <= max(V_w, 0) dt + a k dt^2  (a = largest |a_i| of the chunk for the affine
+            // headings of the packed scan, max(a_last, 0) for the generic one)
+            const int i0 = ic * kC;
+            const int il = i0 + kC - 1 < p.gv ? i0 + kC - 1 : p.gv - 1;
+            const float inv = p.gv > 1 ? (float)(p.max_accel / (double)(p.gv - 1)) : 0.f;
+            const float a_first = inv * (float)(2 * i0 - (p.gv - 1));
+            const float a_last = inv * (float)(2 * (i0 + kC - 1) - (p.gv - 1));
+            const float a_gen = inv * (float)(2 * il - (p.gv - 1));
+            const float acoef = fast ? fmaxf(fabsf(a_first), fabsf(a_last)) : fmaxf(a_gen, 0.f);
+            const float dtf = (float)dt;
+            const float* vdc = VD + (ic - ic0) * kC + (kC - 1);
+            const float vmax = fmaxf(vdc[0], vdc[(N - 1) * p.vd_cols]);
+            const float tv = 1.000002f * fmaf(fmaxf((float)v_seed, 0.f) * dtf, TS[gs4 + j],
+                                              1.000002f * acoef * dtf * dtf * TS[2 * gs4 + j]);
+            band = make_band(hd->bw, vmax, tv, TS[j], fast);
+          }
 #pragma unroll
           for (int c = 0; c < kC; ++c)
             if (ic * kC + c < p.gv) valid |= 1u << c;
@@ -947,14 +1000,6 @@ vmvo_window_search_kernel(const SearchParams p) {
     }
 
     // ---- phase D: winner across warps, result record, optional rollout outputs ----------
-    if (lane == 0) {
-      hd->bcost[warp] = best_cost;
-      hd->bh[warp] = best_h;
-      hd->bpose[warp][0] = best_first.x;
-      hd->bpose[warp][1] = best_first.y;
-      hd->bpose[warp][2] = best_first.th;
-      hd->nres[warp] = n_rescored;
-    }
     team.sync();
     if (tid == 0) {
       int bwi = -1;
@@ -967,16 +1012,19 @@ vmvo_window_search_kernel(const SearchParams p) {
           bwi = q;
       }
       if (status & VMVO_WIN_NONFINITE) bwi = 0;
-      res.n_rescored = total;
-      if (bwi >= 0) {
-        res.best_idx = hd->bh[bwi];
-        res.best_cost = hd->bcost[bwi];
-        res.x1 = hd->bpose[bwi][0];
-        res.y1 = hd->bpose[bwi][1];
-        res.theta1 = hd->bpose[bwi][2];
-      }
-      hd->winner = res.best_idx;
-      p.results[w] = res;
+      vmvo_window_result r;
+      r.best_idx = bwi >= 0 ? hd->bh[bwi] : -1;
+      r.n_steps = N;
+      r.status = status;
+      r.n_rescored = total;
+      r.best_cost = bwi >= 0 ? hd->bcost[bwi] : CUDART_NAN;
+      r.v_seed = hd->wi.v_seed;
+      r.s_seed = hd->wi.s_seed;
+      r.x1 = bwi >= 0 ? hd->bpose[bwi][0] : CUDART_NAN;
+      r.y1 = bwi >= 0 ? hd->bpose[bwi][1] : CUDART_NAN;
+      r.theta1 = bwi >= 0 ? hd->bpose[bwi][2] : CUDART_NAN;
+      hd->winner = r.best_idx;
+      p.results[w] = r;
     }
     if (chained) {  // last steering angle of the optimum (optimize_trajectory_v2.py:146)
       team.sync();
