@@ -291,6 +291,11 @@ int vmvo_csv_parse_f64(vmvo_ctx* ctx, const uint8_t* d_bytes, int32_t n_files,
                        int32_t sorted_slot, double* d_out, double* d_rot, int32_t* d_status,
                        void* stream);
 
+/* tan of road-wheel angles [rad] exactly as the search tabulates it (tan delta of
+ * vmvo/bicycle_model.py:66-68 in float32): a polynomial within 1 ulp for |delta| <= 0.62 rad
+ * (steering is mechanically limited: MAX_STEER / ratio = 0.605 rad), tanf beyond.            */
+int vmvo_tan_steer_f32(vmvo_ctx* ctx, int64_t n, const float* d_delta, float* d_out, void* stream);
+
 /* ---- measurement helpers ------------------------------------------------------------ */
 /* Issue-rate microbenchmarks used for the roofline denominators (bench.py): each thread
  * runs `iters` dependent-free MUFU (kind 0: sin+cos pairs), FFMA (kind 1) or DFMA (kind 2)

@@ -204,3 +204,37 @@ def test_drive_pipeline_graph_replay(cuda_device, split):
         assert torch.equal(got_rec.view(torch.int32)[:, :3], so.results.view(torch.int32)[:, :3])
         assert torch.equal(got_rec[:, 16:], so.results[:, 16:])     # costs, seeds, first pose
         assert torch.equal(got_traj, traj)
+
+
+def test_tabulated_tangent_is_within_one_ulp(cuda_device):
+    """tan_steer (the TL table's tangent): every float of [2^-14, 0.62] -- 1.1e8 values -- against
+    float64 tan, <= 1 ulp (the error band's eps_TL assumes 2u = 1 ulp); tanf's range beyond."""
+    import ctypes as C
+
+    from vehiclemodelvisualodometry_b200 import _lib
+
+    ctx = _lib.context(cuda_device.index)
+    lo = int(np.float32(2.0 ** -14).view(np.uint32))
+    hi = int(np.float32(0.62).view(np.uint32))
+    worst = 0.0
+    step = 1 << 24
+    for a in range(lo, hi + 1, step):
+        b = min(a + step, hi + 1)
+        bits = torch.arange(a, b, dtype=torch.int64, device=cuda_device).to(torch.int32)
+        x = bits.view(torch.float32)
+        out = torch.empty_like(x)
+        ctx.check(ctx.lib.vmvo_tan_steer_f32(ctx.handle, x.numel(), _lib.ptr(x), _lib.ptr(out),
+                                             _lib.stream_ptr(cuda_device)), "vmvo_tan_steer_f32")
+        ref = torch.tan(x.double())
+        ulp = torch.abs(ref.float()) * 2.0 ** -23          # >= the spacing at ref / 2
+        err = (torch.abs(out.double() - ref) / ulp.double()).max().item()
+        worst = max(worst, err)
+    assert worst <= 1.0, worst
+    # odd symmetry, zero, and the library range above the polynomial's
+    x = torch.tensor([0.0, -0.3, 0.3, 0.7, -1.2, 1e-30], dtype=torch.float32, device=cuda_device)
+    out = torch.empty_like(x)
+    ctx.check(ctx.lib.vmvo_tan_steer_f32(ctx.handle, x.numel(), _lib.ptr(x), _lib.ptr(out),
+                                         _lib.stream_ptr(cuda_device)), "vmvo_tan_steer_f32")
+    o = out.cpu().numpy()
+    assert o[0] == 0.0 and o[1] == -o[2] and o[5] == np.float32(1e-30)
+    np.testing.assert_allclose(o, np.tan(x.cpu().numpy().astype(np.float64)), rtol=3e-7)

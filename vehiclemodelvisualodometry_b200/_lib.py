@@ -94,6 +94,7 @@ _SIGNATURES = {
                                       _c_vp]),
     "vmvo_csv_parse_f64": (C.c_int, [_c_vp, _c_vp, _c_i32, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp,
                                      _c_i32, _c_i32, _c_vp, _c_vp, _c_vp, _c_vp]),
+    "vmvo_tan_steer_f32": (C.c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp]),
     "vmvo_peak_probe": (C.c_int, [_c_vp, _c_i32, _c_i32, _c_i32, _c_i32, _c_vp, _c_vp]),
     "vmvo_launch_count": (_c_i64, [_c_vp]),
 }

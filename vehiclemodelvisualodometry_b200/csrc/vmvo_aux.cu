@@ -265,6 +265,13 @@ __global__ void traverse_kernel(int n, const double* xy, double D, int* keep, in
   *count = cnt;
 }
 
+// ---- the tangent the search tabulates (exposed so that tests can check the compiled code) -----
+__global__ void tan_steer_kernel(long long n, const float* x, float* out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    out[i] = tan_steer(x[i]);
+}
+
 // ---- issue-rate probes -------------------------------------------------------------------------
 __global__ void peak_probe_kernel(int kind, int iters, float* sink) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -546,6 +553,16 @@ extern "C" int vmvo_traverse_f64(vmvo_ctx* ctx, int32_t n, const double* d_xy, d
   VMVO_CUDA(ctx, cudaSetDevice(ctx->device));
   traverse_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(n, d_xy, D, d_keep, d_count);
   return check_launch(ctx, "traverse_kernel");
+}
+
+extern "C" int vmvo_tan_steer_f32(vmvo_ctx* ctx, int64_t n, const float* d_delta, float* d_out,
+                                  void* stream) {
+  if (!ctx) return VMVO_ERR_BAD_ARG;
+  if (n < 0 || (n > 0 && (!d_delta || !d_out))) return fail(ctx, VMVO_ERR_BAD_ARG, "bad argument");
+  if (n == 0) return VMVO_OK;
+  VMVO_CUDA(ctx, cudaSetDevice(ctx->device));
+  tan_steer_kernel<<<grid_for(n, 256, ctx->sm_count * 16), 256, 0, (cudaStream_t)stream>>>(n, d_delta, d_out);
+  return check_launch(ctx, "tan_steer_kernel");
 }
 
 extern "C" int vmvo_peak_probe(vmvo_ctx* ctx, int32_t kind, int32_t blocks, int32_t threads,

@@ -129,6 +129,28 @@ __device__ __forceinline__ Pose<T> warp_model_round(T v, T s_deg, bool active, T
   return p;
 }
 
+// tan of a road-wheel angle for the search's TL table.  Steering is mechanically limited
+// (MAX_STEER / ratio = 0.605 rad with the reference's constants), so the argument is small: the
+// Taylor polynomial through x^19, Horner in x^2 with FMAs, is within 0.74 ulp of tan(x) for every
+// float |x| <= 0.62 (all 1.1e8 of them checked against float64; tests/test_gpu_operators.py
+// re-checks the compiled code), at a third of tanf's instructions.  Larger angles (a caller's own
+// steering limits) go through tanf (<= 4 ulp).
+constexpr float kTanPolyMax = 0.62f;
+__device__ __forceinline__ float tan_steer(float x) {
+  if (!(fabsf(x) <= kTanPolyMax)) return tanf(x);
+  const float x2 = x * x;
+  float p = 0.0002391291200183332f;           // 443861162/1856156927625  x^19
+  p = fmaf(p, x2, 0.0005900274263694882f);    // 6404582/10854718875       x^17
+  p = fmaf(p, x2, 0.0014558343682438135f);    // 929569/638512875          x^15
+  p = fmaf(p, x2, 0.0035921279340982437f);    // 21844/6081075             x^13
+  p = fmaf(p, x2, 0.0088632358238101f);       // 1382/155925               x^11
+  p = fmaf(p, x2, 0.021869488060474396f);     // 62/2835                   x^9
+  p = fmaf(p, x2, 0.05396825447678566f);      // 17/315                    x^7
+  p = fmaf(p, x2, 0.13333334028720856f);      // 2/15                      x^5
+  p = fmaf(p, x2, 0.3333333432674408f);       // 1/3                       x^3
+  return fmaf(x, x2 * p, x);
+}
+
 // Python / NumPy float modulo by a positive divisor (floor-mod): result in [0, b).
 __device__ __forceinline__ double pymod_pos(double a, double b) {
   double r = fmod(a, b);

@@ -738,7 +738,7 @@ vmvo_window_search_kernel(const SearchParams p) {
           double s = dadd(s_seed, dmul(rdt, (double)k));
           s = s < -p.max_steer ? -p.max_steer : s;
           s = s > p.max_steer ? p.max_steer : s;
-          TL[(k - 1) * p.gs + j] = tanf((float)(s * kd)) * invL;
+          TL[(k - 1) * p.gs + j] = tan_steer((float)(s * kd)) * invL;
         }
       }
       if (ksteer) {
@@ -824,7 +824,10 @@ vmvo_window_search_kernel(const SearchParams p) {
       bw.dmax = dmax;
       bw.dabmax = dabmax;
       bw.imax = imax;
-      bw.eps_tl = (10.f + (float)p.kappa) * u;
+      // relative error of a TL entry: tan_steer <= 1 ulp = 2u below 0.62 rad (tanf: 4 ulp = 8u
+      // above), the float rounding of the angle amplified by tan's condition number kappa, the
+      // product with 1/L and its own rounding
+      bw.eps_tl = ((p.delta_max <= (double)kTanPolyMax ? 4.f : 10.f) + (float)p.kappa) * u;
       bw.wpos = wA + (DUAL ? wB : 0.f);
       bw.wimu = IMU ? wI : 0.f;
       // J-proportional part.  The error recurrence rounds twice per step, each <= u*|e_m| (+ u*vmax,
