@@ -263,53 +263,26 @@ def run_b200(args):
         # streams that all start at the interval's first event and are joined before its last one
         # (so every interval pays for one full H2D and one full D2H; the L2 flush between
         # intervals runs with all streams idle).  The last step's D2H is timed by the drain.
-        sets = []
-        for b in range(2):
-            d = DriveSet.from_arrays([time_h], [batch.dt], vo=[vo_h], device=dev)
-            sets.append((d, DrivePipeline(cfg, d, blend_gps=False),
-                         torch.empty((n_win, 64), dtype=torch.uint8).pin_memory(),
-                         torch.empty((4, n_frames), dtype=torch.float64).pin_memory()))
-        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-        est = {"s": 0}
+        from vehiclemodelvisualodometry_b200 import DriveStream
 
-        def h2d(b):
-            sets[b][0].vo.copy_(vo_pin, non_blocking=True)
-            sets[b][0].time.copy_(t_pin, non_blocking=True)
-
-        def d2h(b):
-            sets[b][2].copy_(sets[b][1].records, non_blocking=True)
-            sets[b][3].copy_(sets[b][1].trajectory, non_blocking=True)
-
-        h2d(0)                                   # inputs of the very first step (untimed warm-up side)
+        stream = DriveStream(cfg, drives, blend_gps=False)       # the public streaming API
+        inputs = {"vo": vo_pin, "time": t_pin}
+        stream.prime(inputs)                                     # inputs of the very first step
         torch.cuda.synchronize(dev)
 
         def e2e_step():  # noqa: F811
-            b = est["s"] & 1
-            main = torch.cuda.current_stream(dev)
-            start = torch.cuda.Event()
-            start.record(main)
-            s_in.wait_event(start)
-            s_out.wait_event(start)
-            with torch.cuda.stream(s_in):
-                h2d(b ^ 1)
-            if est["s"] > 0:
-                with torch.cuda.stream(s_out):
-                    d2h(b ^ 1)
-            sets[b][1].run()
-            main.wait_stream(s_in)
-            main.wait_stream(s_out)
-            est["s"] += 1
+            stream.step(inputs)
 
         def e2e_drain():
-            if est["s"] > 0:
-                d2h((est["s"] - 1) & 1)
+            if stream.n > 0:
+                stream.drain()
             drain()
 
         e2e_ms = timed(e2e_step, args.steps, args.warmup, drain=e2e_drain) / args.steps
         e2e_note = ("pipelined across steps on three streams: each timed interval = H2D(step s+1) || "
                     "plan + search + write-back(step s) || D2H(step s-1), joined before the interval ends")
-        chk = sets[(est["s"] - 1) & 1][2].numpy().view(_lib.RESULT_DTYPE).reshape(-1)
         torch.cuda.synchronize(dev)
+        chk = stream.host[(stream.n - 1) & 1][0].numpy().view(_lib.RESULT_DTYPE).reshape(-1)
         assert np.array_equal(chk["best_idx"], pipe.result_records()["best_idx"]), "e2e records differ"
     else:
         e2e_ms = timed(e2e_step, args.steps, args.warmup) / args.steps

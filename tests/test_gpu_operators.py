@@ -238,3 +238,31 @@ def test_tabulated_tangent_is_within_one_ulp(cuda_device):
     o = out.cpu().numpy()
     assert o[0] == 0.0 and o[1] == -o[2] and o[5] == np.float32(1e-30)
     np.testing.assert_allclose(o, np.tan(x.cpu().numpy().astype(np.float64)), rtol=3e-7)
+
+
+def test_drive_stream_overlaps_copies_and_keeps_order(cuda_device):
+    """DriveStream: batches streamed from pinned host memory (H2D of the next, compute of the
+    current, D2H of the previous on three streams) give, in order, what optimize_drives gives."""
+    from vehiclemodelvisualodometry_b200 import DriveStream
+
+    cfg = SearchConfig(grid_v=8, grid_s=8, window_frames=15)
+    batches = [synthetic_drives(2, 110, seed=80 + i) for i in range(4)]
+    a = batches[0]
+    template = DriveSet.from_arrays(list(a.time), [a.dt] * 2, vo=list(a.vo), gps=list(a.gps))
+    stream = DriveStream(cfg, template)
+
+    def pinned(b):
+        return {"vo": torch.from_numpy(np.ascontiguousarray(b.vo.reshape(-1, 4))).pin_memory(),
+                "gps": torch.from_numpy(np.ascontiguousarray(b.gps.reshape(-1, 4))).pin_memory(),
+                "time": torch.from_numpy(np.ascontiguousarray(b.time.reshape(-1))).pin_memory()}
+
+    got = list(stream.run(pinned(b) for b in batches))
+    assert len(got) == len(batches)
+    for b, (rec, traj) in zip(batches, got):
+        d = DriveSet.from_arrays(list(b.time), [b.dt] * 2, vo=list(b.vo), gps=list(b.gps))
+        so, want, _ = optimize_drives(cfg, d)
+        r = so.records()
+        for f in ("best_idx", "n_steps", "status", "best_cost", "x1", "y1", "theta1"):
+            np.testing.assert_array_equal(rec[f], r[f])
+        np.testing.assert_array_equal(traj, want.cpu().numpy())
+    assert list(DriveStream(cfg, template).run([])) == []

@@ -412,6 +412,112 @@ class DrivePipeline:
         return self.records.cpu().numpy().view(_lib.RESULT_DTYPE).reshape(-1)
 
 
+class DriveStream:
+    """Streams same-shaped batches of drives from HOST memory through plan -> search -> write-back
+    and back, with the copies hidden behind the search: two resident drive buffers and three
+    streams.  One ``step`` carries the host-to-device copy of the NEXT batch, the compute of the
+    CURRENT one and the device-to-host copy of the PREVIOUS one; they start together and are
+    joined before ``step`` returns to the caller's stream.
+
+    ``inputs`` are dicts of pinned host tensors keyed like ``DriveSet`` (``vo``, ``gps``, ``imu``,
+    ``time``), shaped like ``template``'s.  ``run`` wraps the stepping for an iterable of batches.
+    """
+
+    def __init__(self, cfg: SearchConfig, template: DriveSet, blend_gps: bool = True):
+        dev = template.device
+        self.dev = dev
+        self.sets: List[DriveSet] = []
+        self.pipes: List[DrivePipeline] = []
+        self.host: List[Tuple[torch.Tensor, torch.Tensor]] = []
+        for _ in range(2):
+            d = DriveSet(time=template.time.clone(),
+                         vo=None if template.vo is None else template.vo.clone(),
+                         gps=None if template.gps is None else template.gps.clone(),
+                         imu=None if template.imu is None else template.imu.clone(),
+                         drive_offsets=list(template.drive_offsets),
+                         d_drive_offsets=template.d_drive_offsets, dt=template.dt)
+            pipe = DrivePipeline(cfg, d, blend_gps=blend_gps)
+            self.sets.append(d)
+            self.pipes.append(pipe)
+            self.host.append((torch.empty(tuple(pipe.records.shape), dtype=torch.uint8).pin_memory(),
+                              torch.empty(tuple(pipe.trajectory.shape), dtype=torch.float64).pin_memory()))
+        self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self.n = 0                      # steps computed so far
+        self.loaded = False             # inputs of step self.n are resident
+
+    def _h2d(self, b: int, inputs) -> None:
+        d = self.sets[b]
+        for name in ("vo", "gps", "imu", "time"):
+            src = inputs.get(name)
+            if src is not None:
+                getattr(d, name).copy_(src, non_blocking=True)
+
+    def _d2h(self, b: int) -> None:
+        self.host[b][0].copy_(self.pipes[b].records, non_blocking=True)
+        self.host[b][1].copy_(self.pipes[b].trajectory, non_blocking=True)
+
+    def prime(self, inputs) -> None:
+        """Copy the first batch in (nothing to overlap it with yet)."""
+        self._h2d(self.n & 1, inputs)
+        self.loaded = True
+
+    def step(self, next_inputs=None) -> Optional[int]:
+        """Compute the resident batch while ``next_inputs`` go in and the previous results come
+        out.  Returns the buffer index whose host copies (``host[b]``) now hold the PREVIOUS
+        step's results, or None on the first step."""
+        if not self.loaded:
+            raise RuntimeError("prime() the stream with the first batch")
+        b = self.n & 1
+        main = torch.cuda.current_stream(self.dev)
+        start = torch.cuda.Event()
+        start.record(main)
+        self.s_in.wait_event(start)
+        self.s_out.wait_event(start)
+        if next_inputs is not None:
+            with torch.cuda.stream(self.s_in):
+                self._h2d(b ^ 1, next_inputs)
+        if self.n > 0:
+            with torch.cuda.stream(self.s_out):
+                self._d2h(b ^ 1)
+        self.pipes[b].run()
+        main.wait_stream(self.s_in)
+        main.wait_stream(self.s_out)
+        self.loaded = next_inputs is not None
+        prev = (b ^ 1) if self.n > 0 else None
+        self.n += 1
+        return prev
+
+    def drain(self) -> int:
+        """Read the last computed step's results back; returns its buffer index."""
+        b = (self.n - 1) & 1
+        self._d2h(b)
+        return b
+
+    def run(self, batches):
+        """Yields ``(records, trajectory)`` NumPy copies per batch, in order."""
+        it = iter(batches)
+        try:
+            first = next(it)
+        except StopIteration:
+            return
+        self.prime(first)
+        pending = next(it, None)
+        while True:
+            nxt = pending
+            prev = self.step(nxt)
+            if prev is not None:
+                torch.cuda.current_stream(self.dev).synchronize()
+                yield (self.host[prev][0].numpy().view(_lib.RESULT_DTYPE).reshape(-1).copy(),
+                       self.host[prev][1].numpy().copy())
+            if nxt is None:
+                break
+            pending = next(it, None)
+        b = self.drain()
+        torch.cuda.current_stream(self.dev).synchronize()
+        yield (self.host[b][0].numpy().view(_lib.RESULT_DTYPE).reshape(-1).copy(),
+               self.host[b][1].numpy().copy())
+
+
 def executed_mufu_per_hypothesis_step(cfg: SearchConfig) -> float:
     """SFU operations the search kernel issues per hypothesis-step: 2 in the generic
     scan (sin + cos; tan is hoisted into a table), 1.25 in the packed / rotation scan, which
