@@ -87,7 +87,7 @@ typedef struct vmvo_window_result {
   int32_t best_idx;      /* flat index i*G_s + j of the argmin hypothesis, -1 if none      */
   int32_t n_steps;       /* N = number of targets - 1                                      */
   int32_t status;        /* VMVO_WIN_* bits                                                */
-  int32_t n_rescored;    /* hypotheses re-scored in float64 (diagnostic)                   */
+  int32_t n_rescored;    /* hypotheses re-scored in float64 (diagnostic; may vary run to run) */
   double best_cost;      /* float64 cost of the argmin hypothesis                          */
   double v_seed, s_seed; /* window seeds V_w [m/s], S_w [deg]                              */
   double x1, y1, theta1; /* pose after the first step of the best rollout (local frame)    */

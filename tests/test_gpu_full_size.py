@@ -28,7 +28,11 @@ def _check(cfg, batch, n_drives, sample=None, with_gps=False, with_imu=False):
     imu = batch.imu[:n_drives].reshape(n_drives * n) if with_imu else None
     ref, _ = c_oracle.search(cfg.to_c(), ws[sel], wl[sel], wd[sel], [batch.dt] * n_drives, vo, gps, imu)
     bad = np.nonzero(rec["best_idx"][sel] != ref["best_idx"])[0]
-    assert len(bad) == 0, f"{len(bad)} of {len(sel)} argmin mismatches, first windows {sel[bad[:5]]}"
+    detail = [(int(sel[b]), int(rec["best_idx"][sel[b]]), int(ref["best_idx"][b]), float(rec["best_cost"][sel[b]]),
+               float(ref["best_cost"][b]), int(rec["n_rescored"][sel[b]]), int(rec["status"][sel[b]]),
+               float(rec["v_seed"][sel[b]]), float(ref["v_seed"][b])) for b in bad[:5]]
+    assert len(bad) == 0, (f"{len(bad)} of {len(sel)} argmin mismatches; (window, got, want, got cost, want cost, "
+                           f"rescored, status, got v_seed, want v_seed): {detail}")
     np.testing.assert_array_equal(rec["n_steps"][sel], ref["n_steps"])
     np.testing.assert_array_equal(rec["status"][sel], ref["status"])
     np.testing.assert_allclose(rec["best_cost"][sel], ref["best_cost"], rtol=1e-9, atol=1e-18)
@@ -47,7 +51,10 @@ def test_config2_single_drive_10k_frames_every_window(cuda_device):
     # determinism: a second run gives identical bytes; shards give the same records
     again = grid_search(cfg, drives, plan).results
     first = grid_search(cfg, drives, plan).results
-    assert torch.equal(again, first)
+    # (bytes 12..15 are n_rescored, a diagnostic: which warp re-scores which candidate follows the
+    # order of an atomic counter, and a warp prunes with the float64 costs it has seen itself, so
+    # the COUNT of re-scores may differ between runs; everything else is bit-reproducible)
+    assert torch.equal(again[:, :12], first[:, :12]) and torch.equal(again[:, 16:], first[:, 16:])
     buf = torch.zeros_like(first)
     for lo, hi in ((0, 3313), (3313, 3314), (3314, 9940)):
         grid_search(cfg, drives, plan, window_range=(lo, hi), out=buf[lo:hi])

@@ -15,6 +15,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "--shared", "-Xcompiler", "-fPIC",
+    "--threads", "4",               # the four translation units compile side by side
 ]
 
 

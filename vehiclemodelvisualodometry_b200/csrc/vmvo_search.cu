@@ -130,6 +130,7 @@ struct SmemHeader {
   double bpose[kMaxWarps][3];
   int bh[kMaxWarps];
   int nres[kMaxWarps];
+  float ts[3 * 8];           // per warp (<= 8 per team): max over its rates of max|TL|, sum|TL|, sum k|TL|
   int count;
   int winner;
   int first[2];      // chained mode: the window is the first of its run
@@ -422,7 +423,10 @@ template <typename SF> struct PoseOf;
 template <> struct PoseOf<float> { using type = float4; };
 template <> struct PoseOf<double> { using type = double4; };
 
-template <int C, int WARPS, int MINB, bool DUAL, bool IMU, typename SF>
+// SKIP: the grid needs more than two passes per window -- passes run middle-out and warps skip the
+// band / candidate work of passes that cannot matter (a separate instantiation: on two-pass grids
+// the extra code measured 2 % slower for nothing)
+template <int C, int WARPS, int MINB, bool DUAL, bool IMU, typename SF, bool SKIP>
 __global__ void __launch_bounds__(32 * WARPS, MINB)
 vmvo_window_search_kernel(const SearchParams p) {
   using Pose4 = typename PoseOf<SF>::type;
@@ -789,6 +793,7 @@ vmvo_window_search_kernel(const SearchParams p) {
     }
 
     // per steering rate: max |TL|, sum |TL|, sum k |TL| over the steps (the items' band inputs)
+    float tmx = 0.f, ts0 = 0.f, ts1 = 0.f;
     for (int j = tid; j < p.gs; j += T) {
       float mx = 0.f, s0 = 0.f, s1 = 0.f;
       const float* t = TL + j;
@@ -801,6 +806,19 @@ vmvo_window_search_kernel(const SearchParams p) {
       TS[j] = mx;
       TS[gs4 + j] = s0;
       TS[2 * gs4 + j] = s1;
+      tmx = fmaxf(tmx, mx);
+      ts0 = fmaxf(ts0, s0);
+      ts1 = fmaxf(ts1, s1);
+    }
+    if constexpr (SKIP) {   // (non-negative floats are ordered like their bit patterns)
+      tmx = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(tmx)));
+      ts0 = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(ts0)));
+      ts1 = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(ts1)));
+      if (lane == 0) {
+        hd->ts[warp] = tmx;
+        hd->ts[8 + warp] = ts0;
+        hd->ts[16 + warp] = ts1;
+      }
     }
 
     // this warp's running best (float64 cost, index, first pose) and its re-score count
@@ -879,17 +897,29 @@ vmvo_window_search_kernel(const SearchParams p) {
         team.sync();
       };
 
+      const bool fast_w = (C == 8 && !IMU) && p.allow_fast && v_seed >= 0.0;   // window-uniform
       const int n_pass = (p.n_items + T - 1) / T;
-      for (int pass = 0; pass < n_pass; ++pass) {
+      // With more than two passes: (i) the passes run middle-out over the accelerations -- the
+      // optimum usually sits near a = 0, so U is tight after the first pass and few candidates are
+      // listed; (ii) a warp whose smallest cost of a pass lies beyond the reach of the window's
+      // WIDEST band around U skips its band and candidate work (it still meets the barriers).
+      constexpr bool use_skip = SKIP;
+      Band loose{0.f, 0.f, 0.f};
+      for (int pidx = 0; pidx < n_pass; ++pidx) {
+        const int mid = (n_pass - 1) >> 1;
+        const int pass = !use_skip ? pidx : (pidx & 1) ? mid + ((pidx + 1) >> 1) : mid - (pidx >> 1);
         // VD[k][m] = V_k(ic0*C + m) * dt for the accelerations this pass touches
         const int ic0 = (pass * T) / p.gs;
         {
           const int kpar = T >= p.vd_cols ? T / p.vd_cols : 1;
+          // a_i by multiplication (the float64 re-score uses the spec's division; here the last
+          // bit is far below FP32 resolution)
+          const double inv_a = p.gv > 1 ? p.max_accel / (double)(p.gv - 1) : 0.0;
           for (int c = tid; c < p.vd_cols * kpar; c += T) {
             const int m = c % p.vd_cols;
             int i = ic0 * kC + m;
             i = i < p.gv ? i : p.gv - 1;
-            const double adt = dmul(grid_rate(p.max_accel, i, p.gv), dt);
+            const double adt = inv_a * (double)(2 * i - (p.gv - 1)) * dt;
             for (int k = 1 + c / p.vd_cols; k <= N; k += kpar) {
               const double vv = dadd(v_seed, dmul(adt, (double)k));
               VD[(k - 1) * p.vd_cols + m] = (float)((vv > 0.0 ? vv : 0.0) * dt);
@@ -897,17 +927,28 @@ vmvo_window_search_kernel(const SearchParams p) {
           }
         }
         team.sync();
+        if (pidx == 0 && use_skip) {   // hd->bw and hd->ts are visible now: the widest band
+          float tl_all = 0.f, s0_all = 0.f, s1_all = 0.f;
+          for (int qq = 0; qq < NW; ++qq) {
+            tl_all = fmaxf(tl_all, hd->ts[qq]);
+            s0_all = fmaxf(s0_all, hd->ts[8 + qq]);
+            s1_all = fmaxf(s1_all, hd->ts[16 + qq]);
+          }
+          const float dtf = (float)dt, vpos = fmaxf((float)v_seed, 0.f), amax = (float)p.max_accel;
+          const float vmax_all = 1.000002f * (vpos + amax * (float)N * dtf) * dtf;
+          const float tv_all = 1.000002f * fmaf(vpos * dtf, s0_all, 1.000002f * amax * dtf * dtf * s1_all);
+          loose = make_band(hd->bw, vmax_all, tv_all, tl_all, fast_w);
+        }
         const int q = pass * T + tid;
         ScanOut<C> so;
         int ic = 0, j = 0;
         unsigned valid = 0;
         Band band{0.f, 0.f, 0.f};
+        const bool fast = fast_w;
         if (q < p.n_items) {
           ic = q / p.gs;
           j = q - ic * p.gs;
-          bool fast = false;
           if constexpr (C == 8 && !IMU) {
-            fast = p.allow_fast && v_seed >= 0.0;   // affine headings need V to clamp only once
             if (fast) {
               // a_i by multiplication with 1/(G-1): last-bit differences from the spec's
               // division are far below the FP32 resolution this scan works at
@@ -923,19 +964,38 @@ vmvo_window_search_kernel(const SearchParams p) {
           if (!fast)
             scan_item<C, DUAL, IMU>(N, p.gs, p.vd_cols, j, (ic - ic0) * kC, TL, VD, Df, Dab, fI, wA, wB,
                                     wI, ksteer ? JS[j] : 0.f, so);
+#pragma unroll
+          for (int c = 0; c < kC; ++c)
+            if (ic * kC + c < p.gv) valid |= 1u << c;
+        }
+        float mj = CUDART_INF_F;       // the item's smallest cost; fminf drops NaN
+        bool has_nan = false;
+#pragma unroll
+        for (int c = 0; c < kC; ++c)
+          if ((valid >> c) & 1u) {
+            mj = fminf(mj, so.J[c]);
+            has_nan |= !(so.J[c] == so.J[c]);
+          }
+        // J - err(J) <= U needs J <= T(U) under the item's band; T under the widest band is larger
+        // still.  A NaN cost is always a candidate.
+        if constexpr (SKIP) {
+          const bool work = p.dbg_cost != nullptr || __any_sync(FULL, has_nan) ||
+                            !(warp_min_f32_nonneg(fmaxf(mj, 0.f)) > loose.threshold(U));
+          if (!work) valid = 0;        // nothing of this warp can matter: m = inf, no candidates
+        }
+        if (valid) {
           {
             // the item's band inputs, from the per-rate table statistics instead of from the loop:
             // largest step of its fastest hypothesis (V_k is monotone in k, VD non-decreasing in i)
             // and a bound on the total heading variation, sum_k step_k * |TL_k| with
-            // step_k <= max(V_w, 0) dt + a k dt^2  (a = largest |a_i| of the chunk for the affine
-            // headings of the packed scan, max(a_last, 0) for the generic one)
+            // step_k <= max(V_w, 0) dt + a k dt^2  (a = largest |a_i| of the chunk's valid
+            // hypotheses for the affine headings of the packed scan, max(a_last, 0) otherwise)
             const int i0 = ic * kC;
             const int il = i0 + kC - 1 < p.gv ? i0 + kC - 1 : p.gv - 1;
             const float inv = p.gv > 1 ? (float)(p.max_accel / (double)(p.gv - 1)) : 0.f;
             const float a_first = inv * (float)(2 * i0 - (p.gv - 1));
-            const float a_last = inv * (float)(2 * (i0 + kC - 1) - (p.gv - 1));
-            const float a_gen = inv * (float)(2 * il - (p.gv - 1));
-            const float acoef = fast ? fmaxf(fabsf(a_first), fabsf(a_last)) : fmaxf(a_gen, 0.f);
+            const float a_last = inv * (float)(2 * il - (p.gv - 1));
+            const float acoef = fast ? fmaxf(fabsf(a_first), fabsf(a_last)) : fmaxf(a_last, 0.f);
             const float dtf = (float)dt;
             const float* vdc = VD + (ic - ic0) * kC + (kC - 1);
             const float vmax = fmaxf(vdc[0], vdc[(N - 1) * p.vd_cols]);
@@ -943,9 +1003,6 @@ vmvo_window_search_kernel(const SearchParams p) {
                                               1.000002f * acoef * dtf * dtf * TS[2 * gs4 + j]);
             band = make_band(hd->bw, vmax, tv, TS[j], fast);
           }
-#pragma unroll
-          for (int c = 0; c < kC; ++c)
-            if (ic * kC + c < p.gv) valid |= 1u << c;
           if (p.dbg_cost) {
 #pragma unroll
             for (int c = 0; c < kC; ++c)
@@ -958,10 +1015,7 @@ vmvo_window_search_kernel(const SearchParams p) {
         }
         // upper bound on the minimum: J + err(J) grows with J, so only the item's smallest cost
         // needs the band evaluated
-        float m = CUDART_INF_F;
-#pragma unroll
-        for (int c = 0; c < kC; ++c)
-          if ((valid >> c) & 1u) m = fminf(m, so.J[c]);  // fminf drops NaN
+        float m = valid ? mj : CUDART_INF_F;
         if (m < CUDART_INF_F) m += band.err(m);
         m = warp_min_f32_nonneg(fmaxf(m, 0.f));
         if (lane == 0) hd->red[warp] = m;
@@ -1073,9 +1127,9 @@ vmvo_window_search_kernel(const SearchParams p) {
   }
 }
 
-template <int C, int WARPS, int MINB, bool DUAL, bool IMU, typename SF>
-static int launch_search(vmvo_ctx* ctx, const SearchParams& p, cudaStream_t st) {
-  auto kern = vmvo_window_search_kernel<C, WARPS, MINB, DUAL, IMU, SF>;
+template <int C, int WARPS, int MINB, bool DUAL, bool IMU, typename SF, bool SKIP>
+static int launch_search_v(vmvo_ctx* ctx, const SearchParams& p, cudaStream_t st) {
+  auto kern = vmvo_window_search_kernel<C, WARPS, MINB, DUAL, IMU, SF, SKIP>;
   constexpr int kCtaThreads = 32 * WARPS;
   const SmemLayout lay(p.maxp, p.gs, p.vd_cols, p.team_warps, p.load_vo + p.load_gps, DUAL, IMU,
                        p.target_mode == VMVO_TARGET_TRAVERSE, (int)(4 * sizeof(SF)));
@@ -1099,6 +1153,13 @@ static int launch_search(vmvo_ctx* ctx, const SearchParams& p, cudaStream_t st) 
   if (grid > need) grid = need;
   kern<<<(unsigned)grid, kCtaThreads, smem, st>>>(p);
   return check_launch(ctx, "vmvo_window_search_kernel");
+}
+
+template <int C, int WARPS, int MINB, bool DUAL, bool IMU, typename SF>
+static int launch_search(vmvo_ctx* ctx, const SearchParams& p, cudaStream_t st) {
+  const int n_pass = (p.n_items + p.team_warps * 32 - 1) / (p.team_warps * 32);
+  return n_pass > 2 ? launch_search_v<C, WARPS, MINB, DUAL, IMU, SF, true>(ctx, p, st)
+                    : launch_search_v<C, WARPS, MINB, DUAL, IMU, SF, false>(ctx, p, st);
 }
 
 static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n_windows,
