@@ -310,3 +310,59 @@ def test_gpu_device_chain_equals_host_facades(cuda_device, tmp_path):
         np.testing.assert_array_equal(traj[3, a:a + nw], np.asarray(out.velocity)[:nw])
         covered = np.asarray(out.x) != np.asarray(process_vo_trajectory(t).x)
         np.testing.assert_array_equal(traj[0, a:b][covered], np.asarray(out.x)[covered])
+
+
+# ---- randomised structure: quoted text columns with commas / quotes / newlines around the numbers ----
+def _random_csv(rng, n_rows):
+    """A file with two numeric columns to read and two free-text columns to skip."""
+    words = ["", "abc", "a,b", 'say ""hi""', "line1\nline2", "x\r\ny", " ", "1.5", "NaN", "[[1 2]\n [3 4]]", ",,,", '""']
+    nums = _number_strings(rng, 2 * n_rows)
+    eol = "\r\n" if rng.random() < 0.3 else "\n"
+    lines = ["u,note,v,tag"]
+    for i in range(n_rows):
+        a, b = nums[2 * i], nums[2 * i + 1]
+        if rng.random() < 0.1:
+            a = ""
+        if rng.random() < 0.1:
+            b = ["NA", "nan", "inf", "-inf"][int(rng.integers(4))]
+        note, tag = words[int(rng.integers(len(words)))], words[int(rng.integers(len(words)))]
+        q = lambda s: '"%s"' % s if (s == "" and rng.random() < 0.5) or any(c in s for c in ',"\n\r') else s  # noqa: E731
+        row = [a, q(note), b, q(tag)]
+        if rng.random() < 0.05:
+            row = row[:3]                       # short row
+        lines.append(",".join(row))
+        if rng.random() < 0.05:
+            lines.append("")                    # blank line
+    text = eol.join(lines)
+    if rng.random() < 0.7:
+        text += eol
+    return text.encode()
+
+
+def test_oracle_equals_pandas_on_random_structure():
+    rng = np.random.default_rng(11)
+    for _ in range(40):
+        data = _random_csv(rng, int(rng.integers(0, 60)))
+        want = pd.read_csv(io.BytesIO(data), usecols=["u", "v"], dtype={"u": np.float64, "v": np.float64})
+        got = C.read_csv(data, ("u", "v"))
+        np.testing.assert_array_equal(got["u"], want["u"].to_numpy())
+        np.testing.assert_array_equal(got["v"], want["v"].to_numpy())
+
+
+@pytest.mark.gpu
+def test_gpu_batch_of_random_files_equals_pandas(cuda_device):
+    """300 files of random structure in ONE batched parse (sizes from a header alone to several
+    4 KiB blocks), each against pandas."""
+    from vehiclemodelvisualodometry_b200 import parse_csv_files
+
+    rng = np.random.default_rng(12)
+    blobs = [_random_csv(rng, int(rng.integers(0, 400)) if k % 7 else 0) for k in range(300)]
+    p = parse_csv_files(blobs, ("u", "v"))
+    cols = p.columns.cpu().numpy()
+    assert not p.status.any()
+    for f, data in enumerate(blobs):
+        want = pd.read_csv(io.BytesIO(data), usecols=["u", "v"], dtype={"u": np.float64, "v": np.float64})
+        a, b = p.row_offsets[f], p.row_offsets[f + 1]
+        assert b - a == len(want), (f, b - a, len(want))
+        np.testing.assert_array_equal(cols[0, a:b], want["u"].to_numpy())
+        np.testing.assert_array_equal(cols[1, a:b], want["v"].to_numpy())
