@@ -161,14 +161,47 @@ def run_b200(args):
     plan = plan_windows(cfg, drives)
     n_win = plan.n_windows
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # 2x the 126 MB L2
-    # record buffers double as the send buffers of the gather; two sets so that the gather of
-    # pass s can still be in flight while pass s+1 is searched
+    # The only exchange of the path is the per-window records.  Preferred: fused into the search --
+    # every rank's gather buffer is mapped into its peers (CUDA IPC) and the kernel's epilogue
+    # stores each record into all of them over NVLink (scheduler.PeerGather); no second kernel has
+    # to squeeze in beside the persistent search, which owns every SM.  Fallback: an NCCL
+    # all-gather of the record buffer, overlapped with the next pass' search.  Two buffer sets
+    # either way, so that step s + 1 never overwrites records of step s in flight.
     n_buf = 2 if world > 1 else 1
-    gathered = [torch.empty((world * n_win, 64), dtype=torch.uint8, device=dev) for _ in range(n_buf)]
-    local = [g[rank * n_win:(rank + 1) * n_win] for g in gathered]
-    # the public batched API: plan + search + write-back captured once as CUDA graphs
-    pipes = [DrivePipeline(cfg, drives, blend_gps=False, records=local[b], split=world > 1)
-             for b in range(n_buf)]
+    peer = None
+    gather_kind = "none (one GPU)"
+    if world > 1 and not os.environ.get("VMVO_BENCH_GATHER", "").lower().startswith("nccl"):
+        try:
+            from vehiclemodelvisualodometry_b200.scheduler import PeerGather
+
+            peer = [PeerGather(n_win, dev) for _ in range(n_buf)]
+            gather_kind = "fused: records stored into every peer's buffer by the search kernel (CUDA IPC, NVLink)"
+        except Exception as exc:       # no peer access on this box: use the collective
+            peer = None
+            print(f"[bench] peer buffers unavailable ({exc}); using the NCCL all-gather", file=sys.stderr)
+    ok = torch.tensor([1 if (peer is not None or world == 1) else 0], device=dev)
+    if world > 1:
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)          # all ranks take the same path
+        if int(ok.item()) == 0 and peer is not None:
+            for pg in peer:
+                pg.close()
+            peer = None
+    if peer is not None:
+        gathered = [pg.buffer for pg in peer]
+        local = [pg.local for pg in peer]
+        pipes = []
+        for b in range(n_buf):
+            peer[b].enable()           # the graph captures the mirrors in force
+            pipes.append(DrivePipeline(cfg, drives, blend_gps=False, records=local[b]))
+            peer[b].disable()
+    else:
+        if world > 1:
+            gather_kind = "NCCL all_gather_into_tensor, overlapped with the next search"
+        gathered = [torch.empty((world * n_win, 64), dtype=torch.uint8, device=dev) for _ in range(n_buf)]
+        local = [g[rank * n_win:(rank + 1) * n_win] for g in gathered]
+        # the public batched API: plan + search + write-back captured once as CUDA graphs
+        pipes = [DrivePipeline(cfg, drives, blend_gps=False, records=local[b], split=world > 1)
+                 for b in range(n_buf)]
     pipe = pipes[0]
     state = {"n": 0, "work": None}
 
@@ -177,6 +210,8 @@ def run_b200(args):
             return pipe.run()
         b = state["n"] & 1
         state["n"] += 1
+        if peer is not None:
+            return pipes[b].run()          # the records reach every rank from inside the search
         pipes[b].run_search()
         if state["work"] is not None:      # the previous pass's gather had this search to hide behind
             state["work"].wait()
@@ -234,6 +269,16 @@ def run_b200(args):
     drain()
     torch.cuda.synchronize()
     rec = pipe.result_records()
+    if world > 1:
+        # what arrived: every rank's slot of this rank's gather buffer against that rank's own records
+        torch.cuda.synchronize()
+        dist.barrier()
+        last = (state["n"] - 1) & 1
+        check = torch.empty((world * n_win, 64), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(check, local[last].contiguous())
+        torch.cuda.synchronize()
+        if not torch.equal(check, gathered[last]):
+            raise SystemExit(f"rank {rank}: gathered records differ from the ranks' own ({gather_kind})")
     hsteps = int(cfg.grid_v) * int(cfg.grid_s) * int(rec["n_steps"].astype(np.int64).sum())
     ms_per_step = total_ms / args.steps
     value = hsteps * world / (ms_per_step * 1e-3)
@@ -303,6 +348,7 @@ def run_b200(args):
                    "windows_per_gpu": n_win, "hypothesis_steps_per_gpu": hsteps,
                    "cache": "256 MiB L2 flush between timed steps", "base_seed": BASE_SEED},
         "windows_per_s": n_win * world / (ms_per_step * 1e-3),
+        "gather": gather_kind,
         "gpu_launches": int(launches),
         "e2e": {"value": hsteps * world / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(vo_pin.numel() * 4 + t_pin.numel() * 8),
@@ -320,6 +366,10 @@ def run_b200(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+        if peer is not None:
+            del pipes, pipe
+            for pg in peer:
+                pg.close()
         dist.destroy_process_group()
 
 

@@ -168,6 +168,27 @@ int vmvo_grid_search_debug_f32(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_
                                const double* d_seeds, vmvo_window_result* d_results,
                                float* d_scan_cost, float* d_scan_err, void* stream);
 
+/* ---- the result gather, fused into the search ---------------------------------
+ * The only exchange of the multi-GPU path is the per-window records.  Instead of a collective
+ * after the kernel, the search's epilogue can store each record a second, third, ... time:
+ * while mirrors are set, record w of every vmvo_grid_search_* call is written to d_results[w]
+ * AND to ((vmvo_window_result*)mirrors[q])[mirror_offset + w] for q < n_mirrors.  With mirrors
+ * pointing into peer GPUs' gather buffers (mapped through CUDA IPC, below) the records travel
+ * over NVLink as plain stores while the kernel is still searching, and no second kernel runs.
+ * The stores are visible to the peers once the kernel has completed on this GPU (stream /
+ * event / barrier order, as after any kernel).  h_mirrors is a HOST array of device pointers;
+ * n_mirrors = 0 clears.  Launch-time state: a CUDA graph captures the mirrors in force.      */
+#define VMVO_MAX_MIRRORS 16
+int vmvo_set_result_mirrors(vmvo_ctx* ctx, int32_t n_mirrors, void* const* h_mirrors,
+                            int64_t mirror_offset);
+/* A device buffer other processes of the box can map: cudaMalloc + cudaIpcGetMemHandle.
+ * h_handle receives the 64-byte IPC handle (host memory) to send to the peers.               */
+int vmvo_peer_buffer_create(vmvo_ctx* ctx, int64_t bytes, void** d_ptr, uint8_t* h_handle);
+int vmvo_peer_buffer_destroy(vmvo_ctx* ctx, void* d_ptr);
+/* Map / unmap a peer's buffer from its handle (cudaIpcOpenMemHandle with lazy peer access).  */
+int vmvo_peer_buffer_open(vmvo_ctx* ctx, const uint8_t* h_handle, void** d_ptr);
+int vmvo_peer_buffer_close(vmvo_ctx* ctx, void* d_ptr);
+
 /* ---- a12: write-back and blends -----------------------------------------------------
  * Replaces optimize_trajectory_v2.py:32-33,122-137: output columns start as the VO stream,
  * window i overwrites x,y[i : i+N_i] with its local-frame rollout (later windows win),

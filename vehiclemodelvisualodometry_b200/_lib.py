@@ -94,6 +94,11 @@ _SIGNATURES = {
                                       _c_vp]),
     "vmvo_csv_parse_f64": (C.c_int, [_c_vp, _c_vp, _c_i32, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp,
                                      _c_i32, _c_i32, _c_vp, _c_vp, _c_vp, _c_vp]),
+    "vmvo_set_result_mirrors": (C.c_int, [_c_vp, _c_i32, _c_vp, _c_i64]),
+    "vmvo_peer_buffer_create": (C.c_int, [_c_vp, _c_i64, C.POINTER(_c_vp), _c_vp]),
+    "vmvo_peer_buffer_destroy": (C.c_int, [_c_vp, _c_vp]),
+    "vmvo_peer_buffer_open": (C.c_int, [_c_vp, _c_vp, C.POINTER(_c_vp)]),
+    "vmvo_peer_buffer_close": (C.c_int, [_c_vp, _c_vp]),
     "vmvo_tan_steer_f32": (C.c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_vp]),
     "vmvo_peak_probe": (C.c_int, [_c_vp, _c_i32, _c_i32, _c_i32, _c_i32, _c_vp, _c_vp]),
     "vmvo_launch_count": (_c_i64, [_c_vp]),

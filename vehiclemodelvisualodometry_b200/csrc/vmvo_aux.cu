@@ -5,6 +5,7 @@
 #include "vmvo_internal.h"
 
 #include <math_constants.h>
+#include <string.h>
 
 namespace vmvo {
 
@@ -332,6 +333,8 @@ extern "C" int vmvo_ctx_create(int device, vmvo_ctx** out) {
   vmvo_ctx* ctx = new vmvo_ctx();
   ctx->device = device;
   ctx->launches = 0;
+  ctx->n_mirrors = 0;
+  ctx->mirror_off = 0;
   ctx->err[0] = 0;
   ctx->d_work_counter = nullptr;
   cudaDeviceProp prop;
@@ -355,6 +358,66 @@ extern "C" int vmvo_ctx_destroy(vmvo_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaFree(ctx->d_work_counter);
   delete ctx;
+  return VMVO_OK;
+}
+
+// ---- result mirrors and peer buffers (the gather fused into the search) ---------------
+extern "C" int vmvo_set_result_mirrors(vmvo_ctx* ctx, int32_t n_mirrors, void* const* h_mirrors,
+                                       int64_t mirror_offset) {
+  if (!ctx) return VMVO_ERR_BAD_ARG;
+  if (n_mirrors < 0 || n_mirrors > VMVO_MAX_MIRRORS || (n_mirrors > 0 && !h_mirrors) || mirror_offset < 0)
+    return fail(ctx, VMVO_ERR_BAD_ARG, "n_mirrors must be in [0, %d], mirror_offset >= 0", VMVO_MAX_MIRRORS);
+  for (int q = 0; q < n_mirrors; ++q) {
+    if (!h_mirrors[q] || ((uintptr_t)h_mirrors[q] & 15))
+      return fail(ctx, VMVO_ERR_BAD_ARG, "mirror %d is NULL or not 16-byte aligned", q);
+    ctx->mirrors[q] = h_mirrors[q];
+  }
+  ctx->n_mirrors = n_mirrors;
+  ctx->mirror_off = mirror_offset;
+  return VMVO_OK;
+}
+
+extern "C" int vmvo_peer_buffer_create(vmvo_ctx* ctx, int64_t bytes, void** d_ptr, uint8_t* h_handle) {
+  if (!ctx) return VMVO_ERR_BAD_ARG;
+  if (bytes < 1 || !d_ptr || !h_handle) return fail(ctx, VMVO_ERR_BAD_ARG, "bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  VMVO_CUDA(ctx, cudaSetDevice(ctx->device));
+  void* p = nullptr;
+  VMVO_CUDA(ctx, cudaMalloc(&p, (size_t)bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return fail(ctx, VMVO_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+  }
+  memcpy(h_handle, &h, sizeof(h));
+  *d_ptr = p;
+  return VMVO_OK;
+}
+
+extern "C" int vmvo_peer_buffer_destroy(vmvo_ctx* ctx, void* d_ptr) {
+  if (!ctx) return VMVO_ERR_BAD_ARG;
+  if (!d_ptr) return VMVO_OK;
+  VMVO_CUDA(ctx, cudaSetDevice(ctx->device));
+  VMVO_CUDA(ctx, cudaFree(d_ptr));
+  return VMVO_OK;
+}
+
+extern "C" int vmvo_peer_buffer_open(vmvo_ctx* ctx, const uint8_t* h_handle, void** d_ptr) {
+  if (!ctx) return VMVO_ERR_BAD_ARG;
+  if (!h_handle || !d_ptr) return fail(ctx, VMVO_ERR_BAD_ARG, "bad argument");
+  VMVO_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, h_handle, sizeof(h));
+  VMVO_CUDA(ctx, cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return VMVO_OK;
+}
+
+extern "C" int vmvo_peer_buffer_close(vmvo_ctx* ctx, void* d_ptr) {
+  if (!ctx) return VMVO_ERR_BAD_ARG;
+  if (!d_ptr) return VMVO_OK;
+  VMVO_CUDA(ctx, cudaSetDevice(ctx->device));
+  VMVO_CUDA(ctx, cudaIpcCloseMemHandle(d_ptr));
   return VMVO_OK;
 }
 

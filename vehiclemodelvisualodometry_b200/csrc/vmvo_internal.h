@@ -13,6 +13,10 @@ struct vmvo_ctx {
   int sm_count;
   unsigned long long* d_work_counter;  // persistent-kernel work queue head
   long long launches;
+  // result mirrors (vmvo_set_result_mirrors): every record is also stored at mirrors[q][off + w]
+  int n_mirrors;
+  void* mirrors[VMVO_MAX_MIRRORS];
+  long long mirror_off;
   char err[512];
 };
 

@@ -60,6 +60,10 @@ struct SearchParams {
   // steering seed of a window is the last steering angle of the previous window's optimum
   const long long* run_offsets;   // [n_runs + 1] window index ranges, or NULL
   long long n_runs;
+  // result mirrors (vmvo_set_result_mirrors): the gather fused into the epilogue
+  int n_mirrors;
+  long long mirror_off;
+  vmvo_window_result* mirrors[VMVO_MAX_MIRRORS];
   float* dbg_cost;       // optional [n_windows][gv*gs] FP32 scan costs   (tests only)
   float* dbg_err;        // optional [n_windows][gv*gs] error-band widths (tests only)
 };
@@ -488,6 +492,13 @@ vmvo_window_search_kernel(const SearchParams p) {
     }
   };
 
+  // one record, to this GPU's buffer and to every mirror (peer GPUs' gather buffers: plain stores
+  // over NVLink, visible to the peers when the kernel has completed)
+  auto store_record = [&](long long w, const vmvo_window_result& r) {
+    p.results[w] = r;
+    for (int q = 0; q < p.n_mirrors; ++q) p.mirrors[q][p.mirror_off + w] = r;
+  };
+
   const bool chained = p.run_offsets != nullptr;
   long long run_end = 0;     // fetcher thread: end of the run being walked (chained mode)
   double s_chain = 0.0;      // all threads: steering seed handed from window to window
@@ -548,7 +559,7 @@ vmvo_window_search_kernel(const SearchParams p) {
       r.v_seed = vs;
       r.s_seed = ss;
       r.x1 = r.y1 = r.theta1 = CUDART_NAN;
-      p.results[w] = r;
+      store_record(w, r);
     };
 
     if (len > P || len < 1) {  // uniform branch
@@ -1081,7 +1092,7 @@ vmvo_window_search_kernel(const SearchParams p) {
       r.y1 = bwi >= 0 ? hd->bpose[bwi][1] : CUDART_NAN;
       r.theta1 = bwi >= 0 ? hd->bpose[bwi][2] : CUDART_NAN;
       hd->winner = r.best_idx;
-      p.results[w] = r;
+      store_record(w, r);
     }
     if (chained) {  // last steering angle of the optimum (optimize_trajectory_v2.py:146)
       team.sync();
@@ -1279,6 +1290,10 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
   p.n_windows = n_windows;
   p.dbg_cost = d_dbg_cost;
   p.dbg_err = d_dbg_err;
+  p.n_mirrors = ctx->n_mirrors;
+  p.mirror_off = ctx->mirror_off;
+  for (int q = 0; q < VMVO_MAX_MIRRORS; ++q)
+    p.mirrors[q] = q < ctx->n_mirrors ? (vmvo_window_result*)ctx->mirrors[q] : nullptr;
   p.run_offsets = (const long long*)d_run_offsets;
   p.n_runs = d_run_offsets ? n_runs : 0;
 

@@ -5,6 +5,12 @@ holds the (small) pose streams, searches a contiguous range of the global window
 the only exchange is one all-gather of the fixed-size 64-byte result records
 (NCCL over NVLink on GPUs; gloo in the CPU tests).  The search kernel writes its records
 straight into this rank's slice of the gather buffer, so there is no staging copy.
+
+``PeerGather`` removes the collective as well: the gather buffers of the ranks of one box are
+mapped into each other's address space (CUDA IPC) and the search kernel's epilogue stores every
+record into all of them (``vmvo_set_result_mirrors``) -- the exchange rides on the kernel that
+produces the data, as plain NVLink stores, with no second kernel competing for the SMs the
+persistent search occupies.
 """
 from __future__ import annotations
 
@@ -14,6 +20,82 @@ import torch
 import torch.distributed as dist
 
 RECORD_BYTES = 64
+
+
+class _DevicePointer:
+    """Zero-copy view of library-owned device memory for torch (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr: int, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "|u1", "data": (int(ptr), False),
+                                         "version": 2}
+
+
+class PeerGather:
+    """Gather buffers of all ranks of one box, mapped into each other.
+
+    Every rank owns ``buffer`` = uint8 [world * n_records, 64]; rank r's records belong in rows
+    [r * n_records, (r + 1) * n_records) of EVERY rank's buffer.  Between ``enable()`` and
+    ``disable()`` each record a search on this rank writes to ``local`` (its own slot) is also
+    stored into that slot of all peers' buffers by the kernel itself.  The peers see them once the
+    kernel has completed here -- order as after any kernel (event, stream sync, barrier).
+    """
+
+    def __init__(self, n_records: int, device, group=None):
+        import ctypes as C
+
+        from . import _lib
+
+        if not dist.is_initialized():
+            raise RuntimeError("PeerGather needs an initialised process group")
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world - 1 > 16:
+            raise ValueError("at most 17 ranks")
+        self.n = int(n_records)
+        self.ctx = _lib.context(torch.device(device).index)
+        nbytes = self.world * self.n * RECORD_BYTES
+        ptr, handle = C.c_void_p(), (C.c_uint8 * 64)()
+        self.ctx.check(self.ctx.lib.vmvo_peer_buffer_create(self.ctx.handle, nbytes, C.byref(ptr), handle),
+                       "vmvo_peer_buffer_create")
+        self._ptr = ptr.value
+        handles: List[Optional[bytes]] = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        self._peers: List[int] = []
+        for q, h in enumerate(handles):
+            if q == self.rank:
+                continue
+            buf, out = (C.c_uint8 * 64).from_buffer_copy(h), C.c_void_p()
+            self.ctx.check(self.ctx.lib.vmvo_peer_buffer_open(self.ctx.handle, buf, C.byref(out)),
+                           "vmvo_peer_buffer_open")
+            self._peers.append(out.value)
+        self._view = _DevicePointer(self._ptr, (self.world * self.n, RECORD_BYTES))
+        self.buffer = torch.as_tensor(self._view, device=torch.device(device))
+        self.buffer.zero_()
+        self.local = self.buffer[self.rank * self.n:(self.rank + 1) * self.n]
+        torch.cuda.synchronize(device)
+        dist.barrier(group)               # every buffer exists and is zeroed before anyone stores into it
+
+    def enable(self) -> None:
+        import ctypes as C
+
+        arr = (C.c_void_p * max(len(self._peers), 1))(*self._peers)
+        self.ctx.check(self.ctx.lib.vmvo_set_result_mirrors(self.ctx.handle, len(self._peers), arr,
+                                                            self.rank * self.n), "vmvo_set_result_mirrors")
+
+    def disable(self) -> None:
+        self.ctx.check(self.ctx.lib.vmvo_set_result_mirrors(self.ctx.handle, 0, None, 0),
+                       "vmvo_set_result_mirrors")
+
+    def close(self) -> None:
+        self.disable()
+        torch.cuda.synchronize()
+        dist.barrier()
+        for p in self._peers:
+            self.ctx.lib.vmvo_peer_buffer_close(self.ctx.handle, p)
+        self._peers = []
+        self.buffer = self.local = None
+        if self._ptr:
+            self.ctx.lib.vmvo_peer_buffer_destroy(self.ctx.handle, self._ptr)
+            self._ptr = None
 
 
 def shard_range(n_items: int, world: int, rank: int) -> Tuple[int, int]:
