@@ -157,3 +157,30 @@ def test_high_speed_large_heading(cuda_device):
     rec = _run(cfg, t, dt, vo)
     ref = oracle_windows(cfg, t, dt, vo)
     assert_records_match(rec, ref)
+
+
+@pytest.mark.parametrize("defer_min", ["0", "1", "3"])
+def test_deferred_windows_give_the_same_records(cuda_device, monkeypatch, defer_min):
+    """Windows with long candidate lists park them for the second kernel (VMVO_DEFER_MIN entries or
+    more; 0 = never, 1 = every window): index, cost and first pose must not depend on which kernel
+    did the float64 re-scores.  Slow stretches (near-ties over the steering rates) included."""
+    cfg = SearchConfig(grid_v=16, grid_s=32, window_frames=30)
+    # a vehicle creeping at 0.9 m/s with VO noise: the hardest-braking rows stop after one or two
+    # steps and all 32 steering rates of such a row nearly tie; then a normal stretch
+    rng = np.random.default_rng(7)
+    t, slow = _straight(200, 0.9)
+    slow[:, :2] += rng.normal(0, 0.05, (200, 2)).astype(np.float32)
+    slow[:, 3] += rng.normal(0, 0.05, 200).astype(np.float32)
+    batch = synthetic_drives(1, 200, seed=7)
+    fast = batch.vo[0].copy()
+    fast[:, :2] += slow[-1, :2] - fast[0, :2]
+    vo = np.concatenate([slow, fast]).astype(np.float32)
+    time = np.concatenate([t, t[-1] + 0.05 + np.arange(200) * 0.05])
+    monkeypatch.setenv("VMVO_DEFER_MIN", defer_min)
+    rec = _run(cfg, time, 0.05, vo)
+    monkeypatch.setenv("VMVO_DEFER_MIN", "0")
+    base = _run(cfg, time, 0.05, vo)
+    assert base["n_rescored"].max() >= 16
+    for f in ("best_idx", "n_steps", "status", "best_cost", "x1", "y1", "theta1", "v_seed", "s_seed"):
+        np.testing.assert_array_equal(rec[f], base[f])
+    assert_records_match(rec, oracle_windows(cfg, time, 0.05, vo))

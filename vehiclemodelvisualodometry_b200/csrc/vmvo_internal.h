@@ -17,6 +17,12 @@ struct vmvo_ctx {
   int n_mirrors;
   void* mirrors[VMVO_MAX_MIRRORS];
   long long mirror_off;
+  // deferred windows (vmvo_search.cu): candidate lists parked for the second kernel.  Buffers only
+  // grow and old ones stay alive until the ctx is destroyed: captured graphs keep their pointers.
+  unsigned char* d_defer[8];
+  size_t defer_bytes[8];
+  int n_defer;
+  unsigned* d_defer_count;             // 64 counters, one per launch in rotation
   char err[512];
 };
 

@@ -64,6 +64,11 @@ struct SearchParams {
   int n_mirrors;
   long long mirror_off;
   vmvo_window_result* mirrors[VMVO_MAX_MIRRORS];
+  // deferred windows: candidate lists of at least defer_min entries are parked here (one slot
+  // per window) and re-scored by vmvo_deferred_rescore_kernel with the whole GPU
+  unsigned char* defer_buf;
+  unsigned* defer_count;
+  int defer_slots, defer_slot_bytes, defer_min;
   float* dbg_cost;       // optional [n_windows][gv*gs] FP32 scan costs   (tests only)
   float* dbg_err;        // optional [n_windows][gv*gs] error-band widths (tests only)
 };
@@ -114,6 +119,18 @@ __host__ __device__ inline int chunks_per_pass(int T, int gs) {
   return (T + gs - 1) / gs + 1;
 }
 
+// header of a deferred window's slot; the float64 targets and the candidate list follow it
+struct DeferHdr {
+  long long w;
+  int n_steps, status, count, n_rescored;
+  float U;
+  int best_h;                 // best of the re-scores already done in the search kernel, or -1
+  double best_cost, bpose[3];
+  WinInfo wi;
+};
+constexpr int kDeferHdrBytes = 128;
+static_assert(sizeof(DeferHdr) <= kDeferHdrBytes, "deferred-window header too large");
+
 // window-level inputs of the FP32 error band
 struct BandWin {       // window-level inputs, identical in every thread
   float n, s2, s4;     // N, sum k^2, bound on sum ((k^2+k)/2)^2
@@ -137,6 +154,7 @@ struct SmemHeader {
   float ts[3 * 8];           // per warp (<= 8 per team): max over its rates of max|TL|, sum|TL|, sum k|TL|
   int count;
   int winner;
+  int slot;          // deferred-window slot handed out for this window (or -1)
   int first[2];      // chained mode: the window is the first of its run
 };
 static_assert(sizeof(SmemHeader) <= kHeaderBytes, "header too large");
@@ -872,6 +890,7 @@ vmvo_window_search_kernel(const SearchParams p) {
     }
     __syncwarp();
 
+    bool deferred = false;     // the float64 re-scores of this window go to the second kernel
     if (!(status & VMVO_WIN_NONFINITE)) {
       // ---- phase B: FP32 scan of the whole grid, candidates within the error band -------
       // (hd->bw and hd->wi.status become visible with the barrier that follows the first VD fill)
@@ -1064,12 +1083,63 @@ vmvo_window_search_kernel(const SearchParams p) {
           process_list();
         }
       }
-      process_list();
+      // A long list means near-ties (a slow vehicle: every steering rate of the hardest-braking
+      // rows costs almost the same).  Re-scoring it here would keep this team busy for tens of
+      // microseconds; instead the targets and the list are parked in a slot and the second kernel
+      // shares the float64 work of all such windows over the whole GPU.
+      {
+        const int count = hd->count < cand_cap ? hd->count : cand_cap;
+        if (p.defer_buf && count >= p.defer_min) {        // team-uniform
+          if (tid == 0) {
+            const unsigned sl = atomicAdd(p.defer_count, 1u);
+            hd->slot = sl < (unsigned)p.defer_slots ? (int)sl : -1;
+          }
+          team.sync();
+          if (hd->slot >= 0) {
+            deferred = true;
+            unsigned char* slot = p.defer_buf + (size_t)hd->slot * p.defer_slot_bytes;
+            const int n_arr = 2 + (DUAL ? 2 : 0) + (IMU ? 1 : 0);
+            double* g_tgt = reinterpret_cast<double*>(slot + kDeferHdrBytes);
+            uint2* g_cand = reinterpret_cast<uint2*>(slot + kDeferHdrBytes + (size_t)n_arr * P * 8);
+            for (int q = tid; q < n_arr * P; q += T) g_tgt[q] = tgt[q];
+            for (int q = tid; q < count; q += T) g_cand[q] = cand[q];
+            if (tid == 0) {
+              DeferHdr dh;
+              dh.w = w;
+              dh.n_steps = N;
+              dh.status = status;
+              dh.count = count;
+              dh.U = U;
+              dh.best_h = -1;
+              dh.best_cost = CUDART_INF;
+              dh.bpose[0] = dh.bpose[1] = dh.bpose[2] = CUDART_NAN;
+              int total = 0;
+              for (int q = 0; q < NW; ++q) {     // what earlier list flushes of this window found
+                total += hd->nres[q];
+                if (hd->bh[q] < 0) continue;
+                if (dh.best_h < 0 || hd->bcost[q] < dh.best_cost ||
+                    (hd->bcost[q] == dh.best_cost && hd->bh[q] < dh.best_h)) {
+                  dh.best_h = hd->bh[q];
+                  dh.best_cost = hd->bcost[q];
+                  dh.bpose[0] = hd->bpose[q][0];
+                  dh.bpose[1] = hd->bpose[q][1];
+                  dh.bpose[2] = hd->bpose[q][2];
+                }
+              }
+              dh.n_rescored = total;
+              dh.wi = hd->wi;
+              *reinterpret_cast<DeferHdr*>(slot) = dh;
+              hd->count = 0;
+            }
+          }
+        }
+      }
+      if (!deferred) process_list();
     }
 
     // ---- phase D: winner across warps, result record, optional rollout outputs ----------
     team.sync();
-    if (tid == 0) {
+    if (tid == 0 && !deferred) {
       int bwi = -1;
       int total = 0;
       for (int q = 0; q < NW; ++q) {
@@ -1138,6 +1208,87 @@ vmvo_window_search_kernel(const SearchParams p) {
   }
 }
 
+// ---- second kernel: the float64 re-scores of the deferred windows -------------------------------
+// One CTA of four warps per slot; the warps share the window's candidate list round-robin, each
+// candidate through the same warp_cost64 as in the search kernel (the targets are read from the
+// slot instead of shared memory -- same values, same arithmetic, same cost).
+constexpr int kDeferWarps = 4;
+
+template <bool DUAL, bool IMU>
+__global__ void __launch_bounds__(32 * kDeferWarps)
+vmvo_deferred_rescore_kernel(const SearchParams p) {
+  __shared__ double s_cost[kDeferWarps], s_pose[kDeferWarps][3];
+  __shared__ int s_h[kDeferWarps], s_n[kDeferWarps];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned filled = *p.defer_count;
+  const unsigned n = filled < (unsigned)p.defer_slots ? filled : (unsigned)p.defer_slots;
+  const int P = p.maxp;
+  const int n_arr = 2 + (DUAL ? 2 : 0) + (IMU ? 1 : 0);
+  const double wA = p.use_vo ? p.w_vo : p.w_gps, wB = p.w_gps;
+  for (unsigned s = blockIdx.x; s < n; s += gridDim.x) {
+    const unsigned char* slot = p.defer_buf + (size_t)s * p.defer_slot_bytes;
+    const DeferHdr* dh = reinterpret_cast<const DeferHdr*>(slot);
+    const double* tgt = reinterpret_cast<const double*>(slot + kDeferHdrBytes);
+    const uint2* cand = reinterpret_cast<const uint2*>(slot + kDeferHdrBytes + (size_t)n_arr * P * 8);
+    const int count = dh->count;
+    const float U = dh->U;
+    float Uw = CUDART_INF_F;
+    int best_h = -1, n_res = 0;
+    double best_cost = CUDART_INF;
+    Pose<double> best_first{CUDART_NAN, CUDART_NAN, CUDART_NAN};
+    if (warp == 0 && dh->best_h >= 0) {   // what the search kernel had already re-scored
+      best_h = dh->best_h;
+      best_cost = dh->best_cost;
+      best_first = Pose<double>{dh->bpose[0], dh->bpose[1], dh->bpose[2]};
+    }
+    for (int e = warp; e < count; e += kDeferWarps) {
+      const uint2 ce = cand[e];
+      if (__uint_as_float(ce.y) > fminf(U, Uw)) continue;   // warp-uniform; NaN stays in
+      const int h = (int)ce.x;
+      Pose<double> first;
+      const double c64 = warp_cost64<DUAL, IMU>(p, dh->wi, tgt, P, h, lane, wA, wB, &first);
+      ++n_res;
+      if (best_h < 0 || c64 < best_cost || (c64 == best_cost && h < best_h)) {
+        best_h = h;
+        best_cost = c64;
+        best_first = first;
+      }
+      Uw = fminf(Uw, __double2float_ru(c64));
+    }
+    if (lane == 0) {
+      s_h[warp] = best_h;
+      s_cost[warp] = best_cost;
+      s_pose[warp][0] = best_first.x;
+      s_pose[warp][1] = best_first.y;
+      s_pose[warp][2] = best_first.th;
+      s_n[warp] = n_res;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int bwi = -1, total = dh->n_rescored;
+      for (int q = 0; q < kDeferWarps; ++q) {
+        total += s_n[q];
+        if (s_h[q] < 0) continue;
+        if (bwi < 0 || s_cost[q] < s_cost[bwi] || (s_cost[q] == s_cost[bwi] && s_h[q] < s_h[bwi])) bwi = q;
+      }
+      vmvo_window_result r;
+      r.best_idx = bwi >= 0 ? s_h[bwi] : -1;
+      r.n_steps = dh->n_steps;
+      r.status = dh->status;
+      r.n_rescored = total;
+      r.best_cost = bwi >= 0 ? s_cost[bwi] : CUDART_NAN;
+      r.v_seed = dh->wi.v_seed;
+      r.s_seed = dh->wi.s_seed;
+      r.x1 = bwi >= 0 ? s_pose[bwi][0] : CUDART_NAN;
+      r.y1 = bwi >= 0 ? s_pose[bwi][1] : CUDART_NAN;
+      r.theta1 = bwi >= 0 ? s_pose[bwi][2] : CUDART_NAN;
+      p.results[dh->w] = r;
+      for (int q = 0; q < p.n_mirrors; ++q) p.mirrors[q][p.mirror_off + dh->w] = r;
+    }
+    __syncthreads();
+  }
+}
+
 template <int C, int WARPS, int MINB, bool DUAL, bool IMU, typename SF, bool SKIP>
 static int launch_search_v(vmvo_ctx* ctx, const SearchParams& p, cudaStream_t st) {
   auto kern = vmvo_window_search_kernel<C, WARPS, MINB, DUAL, IMU, SF, SKIP>;
@@ -1163,7 +1314,11 @@ static int launch_search_v(vmvo_ctx* ctx, const SearchParams& p, cudaStream_t st
   const long long need = (items + teams - 1) / teams;
   if (grid > need) grid = need;
   kern<<<(unsigned)grid, kCtaThreads, smem, st>>>(p);
-  return check_launch(ctx, "vmvo_window_search_kernel");
+  int rc = check_launch(ctx, "vmvo_window_search_kernel");
+  if (rc || !p.defer_buf) return rc;
+  long long g2 = p.defer_slots < (long long)ctx->sm_count * 16 ? p.defer_slots : (long long)ctx->sm_count * 16;
+  vmvo_deferred_rescore_kernel<DUAL, IMU><<<(unsigned)(g2 > 0 ? g2 : 1), 32 * kDeferWarps, 0, st>>>(p);
+  return check_launch(ctx, "vmvo_deferred_rescore_kernel");
 }
 
 template <int C, int WARPS, int MINB, bool DUAL, bool IMU, typename SF>
@@ -1303,6 +1458,54 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
   unsigned long long* counter = ctx->d_work_counter + (ctx->launches & 63);
   VMVO_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
   p.work_counter = counter;
+
+  // deferred windows: a slot per window up to a 64 MiB budget.  Not with chained seeds (the next
+  // window needs this one's optimum at once), rollout outputs or the debug export.
+  p.defer_buf = nullptr;
+  p.defer_count = nullptr;
+  p.defer_slots = p.defer_slot_bytes = 0;
+  // Pays where a window's scan is short and its team small (a 32x32 window takes a two-warp team
+  // ~30 us, a list of 32 near-ties another ~35 us); an eight-warp team on a dense grid re-scores
+  // faster than the dump and the four-warp CTA of the second kernel would (measured: -5 %).
+  p.defer_min = tw <= 2 ? 12 : 0;
+  if (const char* ov = getenv("VMVO_DEFER_MIN")) p.defer_min = atoi(ov);   // test knob; 0 = never
+  if (p.defer_min > 0 && !d_run_offsets && !d_out_poses && !d_out_steer && !d_out_vel && !d_dbg_cost) {
+    const int n_arr = 2 + ((use_vo && use_gps) ? 2 : 0) + (use_imu ? 1 : 0);
+    const size_t slot_bytes = ((size_t)kDeferHdrBytes + (size_t)n_arr * p.maxp * 8 + (size_t)p.cand_cap * 8 + 127) & ~(size_t)127;
+    long long slots = n_windows;
+    const long long budget = (64LL << 20) / (long long)slot_bytes;
+    if (slots > budget) slots = budget;
+    size_t need = (size_t)slots * slot_bytes;
+    int have = -1;
+    for (int q = 0; q < ctx->n_defer; ++q)
+      if (ctx->defer_bytes[q] >= need) { have = q; break; }
+    if (have < 0) {
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      cudaStreamIsCapturing(st, &cs);
+      if (cs == cudaStreamCaptureStatusNone && ctx->n_defer < 8) {
+        void* buf = nullptr;
+        if (cudaMalloc(&buf, need) == cudaSuccess) {
+          have = ctx->n_defer++;
+          ctx->d_defer[have] = (unsigned char*)buf;
+          ctx->defer_bytes[have] = need;
+        } else {
+          cudaGetLastError();    // no room: search without deferral
+        }
+      } else if (ctx->n_defer > 0) {   // under capture (or out of table entries): the largest buffer there is
+        have = 0;
+        for (int q = 1; q < ctx->n_defer; ++q)
+          if (ctx->defer_bytes[q] > ctx->defer_bytes[have]) have = q;
+        slots = (long long)(ctx->defer_bytes[have] / slot_bytes);
+      }
+    }
+    if (have >= 0 && slots > 0) {
+      p.defer_buf = ctx->d_defer[have];
+      p.defer_slots = (int)(slots > 0x7fffffff ? 0x7fffffff : slots);
+      p.defer_slot_bytes = (int)slot_bytes;
+      p.defer_count = ctx->d_defer_count + (ctx->launches & 63);
+      VMVO_CUDA(ctx, cudaMemsetAsync(p.defer_count, 0, sizeof(unsigned), st));
+    }
+  }
 
   const bool dual = use_vo && use_gps;
 #define VMVO_LAUNCH(SF)                                                                  \

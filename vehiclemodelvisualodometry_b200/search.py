@@ -335,14 +335,15 @@ def optimize_drives(cfg: SearchConfig, drives: DriveSet, plan: Optional[WindowPl
 
 class DrivePipeline:
     """plan -> search -> write-back for one resident batch of drives, captured once as a CUDA
-    graph and replayed: three kernel launches and a memset per pass, no per-pass host work.
+    graph and replayed: four kernel launches (plan, search, deferred re-scores, write-back) and two
+    memsets per pass, no per-pass host work.
 
     The pose streams and stamps are read from ``drives`` at replay time, so new data of the
     same shape can be copied into ``drives.vo`` / ``.gps`` / ``.imu`` / ``.time`` between passes.
     ``records`` (uint8 [n_windows, 64]) may be a slice of a larger gather buffer.
     """
 
-    KERNELS_PER_PASS = 3
+    KERNELS_PER_PASS = 4
 
     def __init__(self, cfg: SearchConfig, drives: DriveSet, blend_gps: bool = True,
                  records: Optional[torch.Tensor] = None, use_graph: bool = True,
