@@ -1209,10 +1209,10 @@ vmvo_window_search_kernel(const SearchParams p) {
 }
 
 // ---- second kernel: the float64 re-scores of the deferred windows -------------------------------
-// One CTA of four warps per slot; the warps share the window's candidate list round-robin, each
+// One CTA of eight warps per slot; the warps share the window's candidate list round-robin, each
 // candidate through the same warp_cost64 as in the search kernel (the targets are read from the
 // slot instead of shared memory -- same values, same arithmetic, same cost).
-constexpr int kDeferWarps = 4;
+constexpr int kDeferWarps = 8;
 
 template <bool DUAL, bool IMU>
 __global__ void __launch_bounds__(32 * kDeferWarps)
@@ -1466,8 +1466,8 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
   p.defer_slots = p.defer_slot_bytes = 0;
   // Pays where a window's scan is short and its team small (a 32x32 window takes a two-warp team
   // ~30 us, a list of 32 near-ties another ~35 us); an eight-warp team on a dense grid re-scores
-  // faster than the dump and the four-warp CTA of the second kernel would (measured: -5 %).
-  p.defer_min = tw <= 2 ? 12 : 0;
+  // faster than the dump and the CTA of the second kernel would (measured: -5 %).
+  p.defer_min = tw <= 2 ? 8 : 0;
   if (const char* ov = getenv("VMVO_DEFER_MIN")) p.defer_min = atoi(ov);   // test knob; 0 = never
   if (p.defer_min > 0 && !d_run_offsets && !d_out_poses && !d_out_steer && !d_out_vel && !d_dbg_cost) {
     const int n_arr = 2 + ((use_vo && use_gps) ? 2 : 0) + (use_imu ? 1 : 0);
