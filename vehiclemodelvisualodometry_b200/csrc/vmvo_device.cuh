@@ -136,8 +136,7 @@ __device__ __forceinline__ Pose<T> warp_model_round(T v, T s_deg, bool active, T
 // re-checks the compiled code), at a third of tanf's instructions.  Larger angles (a caller's own
 // steering limits) go through tanf (<= 4 ulp).
 constexpr float kTanPolyMax = 0.62f;
-__device__ __forceinline__ float tan_steer(float x) {
-  if (!(fabsf(x) <= kTanPolyMax)) return tanf(x);
+__device__ __forceinline__ float tan_poly(float x) {   // |x| <= kTanPolyMax
   const float x2 = x * x;
   float p = 0.0002391291200183332f;           // 443861162/1856156927625  x^19
   p = fmaf(p, x2, 0.0005900274263694882f);    // 6404582/10854718875       x^17
@@ -149,6 +148,10 @@ __device__ __forceinline__ float tan_steer(float x) {
   p = fmaf(p, x2, 0.13333334028720856f);      // 2/15                      x^5
   p = fmaf(p, x2, 0.3333333432674408f);       // 1/3                       x^3
   return fmaf(x, x2 * p, x);
+}
+__device__ __forceinline__ float tan_steer(float x) {
+  if (!(fabsf(x) <= kTanPolyMax)) return tanf(x);
+  return tan_poly(x);
 }
 
 // Python / NumPy float modulo by a positive divisor (floor-mod): result in [0, b).

@@ -41,6 +41,10 @@ struct SearchParams {
   double w_vo, w_gps, w_imu, k_steer;
   double L, ratio, max_steer, max_accel, max_rate;
   double delta_max, kappa;     // kappa = 2*delta_max / sin(2*delta_max): tan's condition number
+  // for the FP32 tables only (the float64 re-score divides as the spec does): the grid spacings
+  // max_accel / (gv - 1) and max_rate / (gs - 1) (0 on a one-point axis), and 1 / L
+  double acc_step, rate_step;
+  float inv_L;
   const long long* win_start;
   const int* win_len;
   const int* win_drive;
@@ -83,10 +87,13 @@ struct WinInfo {
   int n_dead, sat_lo, sat_hi;
 };
 
+// threads of a team that share one steering rate in the TL fill (each takes every kpar-th step)
+__host__ __device__ inline int tl_kpar(int T, int gs) { return T >= gs ? T / gs : 1; }
+
 // ---- shared-memory carve-up (same function on host and device) ---------------------------
 struct SmemLayout {
   int off_raw, off_loc, off_loci, off_tgt, off_df, off_dab, off_fi, off_keep, off_tl, off_js,
-      off_ts, off_vd, off_cand, total;
+      off_ts, off_tsp, off_vd, off_cand, total;
   // P poses per window, n_streams pose streams staged, optional terms only when configured
   __host__ __device__ SmemLayout(int P, int gs, int vd_cols, int team_warps, int n_streams,
                                  bool dual, bool imu, bool traverse, int pose_bytes) {
@@ -103,6 +110,8 @@ struct SmemLayout {
     off_tl = o;   o += P * gs * 4;              // float TL[k][j]
     off_js = o;   o += ((gs + 3) & ~3) * 4;     // float K * sum_k S_k(j)^2 (steering penalty)
     off_ts = o;   o += 3 * ((gs + 3) & ~3) * 4; // float max_k |TL|, sum_k |TL|, sum_k k |TL|  per j
+    // the same three, per (step slice, j), as the TL fill leaves them: T / gs threads share a rate
+    off_tsp = o;  o += 3 * tl_kpar(team_warps * 32, gs) * ((gs + 3) & ~3) * 4;
     o = (o + 15) & ~15;
     off_vd = o;   o += P * vd_cols * 4;         // float VD[k][m]
     o = (o + 15) & ~15;
@@ -156,6 +165,11 @@ struct SmemHeader {
   int winner;
   int slot;          // deferred-window slot handed out for this window (or -1)
   int first[2];      // chained mode: the window is the first of its run
+  // plan entry of the window in each staging buffer, read once by the fetcher (the other threads
+  // would each wait for two dependent L2 round trips at the top of the window)
+  int wlen[2];
+  long long wstart[2];
+  double wdt[2];
 };
 static_assert(sizeof(SmemHeader) <= kHeaderBytes, "header too large");
 
@@ -196,7 +210,8 @@ struct Band {
   __device__ __forceinline__ float threshold(float U) const {
     if (!(c2 < 0.5f)) return CUDART_INF_F;
     const float a = 1.f - c2;
-    const float s = (c1 + sqrtf(fmaf(c1, c1, 4.f * a * (c0 + U)))) / (2.f * a);
+    // (2a is in (1, 2]: the approximate division is good to 2 ulp, far inside the rounding-up)
+    const float s = __fdividef(c1 + sqrtf(fmaf(c1, c1, 4.f * a * (c0 + U))), 2.f * a);
     return s * s * 1.0000153f;
   }
 };
@@ -477,6 +492,7 @@ vmvo_window_search_kernel(const SearchParams p) {
   float* TL = reinterpret_cast<float*>(smem + lay.off_tl);
   float* JS = reinterpret_cast<float*>(smem + lay.off_js);
   float* TS = reinterpret_cast<float*>(smem + lay.off_ts);
+  float* TSP = reinterpret_cast<float*>(smem + lay.off_tsp);
   const int gs4 = (p.gs + 3) & ~3;
   float* VD = reinterpret_cast<float*>(smem + lay.off_vd);
   uint2* cand = reinterpret_cast<uint2*>(smem + lay.off_cand);
@@ -497,6 +513,9 @@ vmvo_window_search_kernel(const SearchParams p) {
   auto issue_load = [&](long long w, int buf) {  // the fetcher thread only
     const long long start = p.win_start[w];
     int len = p.win_len[w];
+    hd->wstart[buf] = start;
+    hd->wlen[buf] = len;
+    hd->wdt[buf] = p.dt_drive[p.win_drive[w]];
     len = len < P ? len : P;
     len = len > 0 ? len : 0;
     const unsigned bytes = (unsigned)len * (unsigned)sizeof(Pose4);
@@ -560,9 +579,9 @@ vmvo_window_search_kernel(const SearchParams p) {
       if (wn < p.n_windows) issue_load(wn, cur ^ 1);
     }
     if (chained && hd->first[cur]) s_chain = 0.0;   // optimize_trajectory_v2.py:46
-    const long long start = p.win_start[w];
-    const int len = p.win_len[w];
-    const double dt = p.dt_drive[p.win_drive[w]];
+    const long long start = hd->wstart[cur];
+    const int len = hd->wlen[cur];
+    const double dt = hd->wdt[cur];
     mbar_wait(&hd->mbar[cur], (unsigned)((it >> 1) & 1));
 
     // the record of a window that is not searched (too long / empty): everything but the status,
@@ -584,6 +603,29 @@ vmvo_window_search_kernel(const SearchParams p) {
       if (tid == 0) write_unsearched(VMVO_WIN_TOO_LONG, 0, CUDART_NAN, CUDART_NAN);
       team.sync();
       continue;
+    }
+
+    const int slot_prim = p.primary == VMVO_PRIMARY_VO ? slot_vo : slot_gps;
+    const Pose4* rp = raw + (cur * n_streams + slot_prim) * P;
+    if (warp == (NW > 1 ? 1 : 0)) {
+      // rows that never move: a_i <= 0 and V_w + a_i*t_1 <= 0 (a_i grows with i: a prefix).  On a
+      // second warp when the team has one: warp 0 has the seed's division and atan to wait for.
+      const double v_seed = p.seed_mode == VMVO_SEED_GIVEN
+                                ? p.seeds[2 * w]
+                                : dmul(dadd((double)rp[0].w, (double)rp[len - 1].w), 0.5);
+      int n_dead = 0;
+      for (int i0 = 0; i0 < p.gv; i0 += 32) {
+        const int i = i0 + lane;
+        bool dead = false;
+        if (i < p.gv) {
+          const double a = grid_rate(p.max_accel, i, p.gv);
+          dead = a <= 0.0 && !(dadd(v_seed, dmul(a, dmul(1.0, dt))) > 0.0) && v_seed == v_seed;
+        }
+        const unsigned b = __ballot_sync(FULL, dead);
+        n_dead += __popc(b);
+        if (b != FULL) break;
+      }
+      if (lane == 0) hd->wi.n_dead = n_dead;
     }
 
     // ---- phase A1: local frames (a7), one pose per thread ---------------------------------
@@ -616,21 +658,21 @@ vmvo_window_search_kernel(const SearchParams p) {
     team.sync();
 
     // ---- phase A2 (warp 0): seeds, decimation (a9) ----------------------------------------
-    const int slot_prim = p.primary == VMVO_PRIMARY_VO ? slot_vo : slot_gps;
     const double* plx = loc + (slot_prim * 3 + 0) * P;
     const double* ply = loc + (slot_prim * 3 + 1) * P;
     const double* plt = loc + (slot_prim * 3 + 2) * P;
     if (warp == 0) {
-      const Pose4* rp = raw + (cur * n_streams + slot_prim) * P;
       double v_seed, s_seed;
       if (p.seed_mode == VMVO_SEED_GIVEN) {
         v_seed = p.seeds[2 * w];
         s_seed = p.seeds[2 * w + 1];
       } else {
-        v_seed = ddiv(dadd((double)rp[0].w, (double)rp[len - 1].w), 2.0);
+        v_seed = dmul(dadd((double)rp[0].w, (double)rp[len - 1].w), 0.5);   // (/ 2, exactly)
         s_seed = 0.0;
         if (len >= 2 && dmul(v_seed, dt) > 1e-6) {
-          const double dth = remainder(dsub(plt[1], plt[0]), kTwoPi);
+          // IEEE remainder by 2 pi; below pi in magnitude it is the argument itself, exactly
+          const double dth0 = dsub(plt[1], plt[0]);
+          const double dth = fabs(dth0) < kPi ? dth0 : remainder(dth0, kTwoPi);
           const double ang = atan(ddiv(dmul(p.L, dth), dmul(v_seed, dt)));
           s_seed = dmul(dmul(ang, kRadToDeg), p.ratio);
           s_seed = s_seed < -p.max_steer ? -p.max_steer : s_seed;
@@ -659,19 +701,6 @@ vmvo_window_search_kernel(const SearchParams p) {
         }
         n_targets = __shfl_sync(FULL, n_targets, 0);
       }
-      // rows that never move: a_i <= 0 and V_w + a_i*t_1 <= 0 (a_i grows with i: a prefix)
-      int n_dead = 0;
-      for (int i0 = 0; i0 < p.gv; i0 += 32) {
-        const int i = i0 + lane;
-        bool dead = false;
-        if (i < p.gv) {
-          const double a = grid_rate(p.max_accel, i, p.gv);
-          dead = a <= 0.0 && !(dadd(v_seed, dmul(a, dmul(1.0, dt))) > 0.0) && v_seed == v_seed;
-        }
-        const unsigned b = __ballot_sync(FULL, dead);
-        n_dead += __popc(b);
-        if (b != FULL) break;
-      }
       // steering rates that clamp to the seed's bound for every step
       int sat_lo = 0, sat_hi = -1;
       if (s_seed == p.max_steer || s_seed == -p.max_steer) {
@@ -699,7 +728,6 @@ vmvo_window_search_kernel(const SearchParams p) {
         hd->wi.dt = dt;
         hd->wi.n_targets = n_targets;
         hd->wi.n_steps = n_targets > 1 ? n_targets - 1 : 0;
-        hd->wi.n_dead = n_dead;
         hd->wi.sat_lo = sat_lo;
         hd->wi.sat_hi = sat_hi;
       }
@@ -762,17 +790,51 @@ vmvo_window_search_kernel(const SearchParams p) {
     // ---- phase A4: TL[k][j] = tan(delta_k(j)) / L and the steering penalty per j -------------
     if (N > 0) {
       // one steering rate per thread (one division), steps strided over the threads that share it
-      const float invL = (float)(1.0 / p.L);
-      const int kpar = T >= p.gs ? T / p.gs : 1;
+      // Four steps at a time: the entries are independent chains (three float64 operations, the
+      // conversion, a ten-term Horner polynomial), and a team of two warps is latency-bound here.
+      // The per-rate statistics of the band (max |TL|, sum |TL|, sum k |TL|) are taken on the way;
+      // the threads that share a rate leave their parts in TSP, added up after the barrier.
+      const float invL = p.inv_L;
+      const int kpar = tl_kpar(T, p.gs);
+      const bool poly = p.delta_max <= 0.6199;     // every clamped angle is inside the polynomial's range
       for (int c = tid; c < p.gs * kpar; c += T) {
-        const int j = c % p.gs;
-        const double rdt = dmul(grid_rate(p.max_rate, j, p.gs), dt);
-        for (int k = 1 + c / p.gs; k <= N; k += kpar) {
-          double s = dadd(s_seed, dmul(rdt, (double)k));
-          s = s < -p.max_steer ? -p.max_steer : s;
-          s = s > p.max_steer ? p.max_steer : s;
-          TL[(k - 1) * p.gs + j] = tan_steer((float)(s * kd)) * invL;
+        const int ks = c / p.gs, j = c - ks * p.gs;
+        // r_j by multiplication: its last float64 bit is far below the float rounding of the angle
+        const double rdt = p.rate_step * (double)(2 * j - (p.gs - 1)) * dt;
+        float mx = 0.f, s0 = 0.f, s1 = 0.f;
+        for (int k0 = 1 + ks; k0 <= N; k0 += 4 * kpar) {
+          float x[4], tl[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int k = k0 + u * kpar;
+            double sd = dadd(s_seed, dmul(rdt, (double)k));
+            sd = sd < -p.max_steer ? -p.max_steer : sd;
+            sd = sd > p.max_steer ? p.max_steer : sd;
+            x[u] = (float)(sd * kd);
+          }
+          if (poly) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) tl[u] = tan_poly(x[u]) * invL;
+          } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) tl[u] = tan_steer(x[u]) * invL;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int k = k0 + u * kpar;
+            if (k <= N) {
+              TL[(k - 1) * p.gs + j] = tl[u];
+              const float a = fabsf(tl[u]);
+              mx = fmaxf(mx, a);
+              s0 += a;
+              s1 = fmaf((float)k, a, s1);
+            }
+          }
         }
+        float* tp = TSP + 3 * gs4 * ks;
+        tp[j] = mx;
+        tp[gs4 + j] = s0;
+        tp[2 * gs4 + j] = s1;
       }
       if (ksteer) {
         for (int j = tid; j < p.gs; j += T) {
@@ -823,14 +885,14 @@ vmvo_window_search_kernel(const SearchParams p) {
 
     // per steering rate: max |TL|, sum |TL|, sum k |TL| over the steps (the items' band inputs)
     float tmx = 0.f, ts0 = 0.f, ts1 = 0.f;
+    const int tl_slices = tl_kpar(T, p.gs);
     for (int j = tid; j < p.gs; j += T) {
       float mx = 0.f, s0 = 0.f, s1 = 0.f;
-      const float* t = TL + j;
-      for (int k = 1; k <= N; ++k, t += p.gs) {
-        const float a = fabsf(*t);
-        mx = fmaxf(mx, a);
-        s0 += a;
-        s1 = fmaf((float)k, a, s1);
+      const float* t = TSP + j;
+      for (int q = 0; q < tl_slices; ++q, t += 3 * gs4) {
+        mx = fmaxf(mx, t[0]);
+        s0 += t[gs4];
+        s1 += t[2 * gs4];
       }
       TS[j] = mx;
       TS[gs4 + j] = s0;
@@ -929,6 +991,7 @@ vmvo_window_search_kernel(const SearchParams p) {
 
       const bool fast_w = (C == 8 && !IMU) && p.allow_fast && v_seed >= 0.0;   // window-uniform
       const int n_pass = (p.n_items + T - 1) / T;
+      const bool vd_full = p.vd_cols >= p.n_ic * kC;
       // With more than two passes: (i) the passes run middle-out over the accelerations -- the
       // optimum usually sits near a = 0, so U is tight after the first pass and few candidates are
       // listed; (ii) a warp whose smallest cost of a pass lies beyond the reach of the window's
@@ -939,24 +1002,26 @@ vmvo_window_search_kernel(const SearchParams p) {
         const int mid = (n_pass - 1) >> 1;
         const int pass = !use_skip ? pidx : (pidx & 1) ? mid + ((pidx + 1) >> 1) : mid - (pidx >> 1);
         // VD[k][m] = V_k(ic0*C + m) * dt for the accelerations this pass touches
-        const int ic0 = (pass * T) / p.gs;
-        {
+        // (a table that covers every acceleration is filled once per window: vd_full)
+        const int ic0 = vd_full ? 0 : (pass * T) / p.gs;
+        if (!vd_full || pidx == 0) {
           const int kpar = T >= p.vd_cols ? T / p.vd_cols : 1;
           // a_i by multiplication (the float64 re-score uses the spec's division; here the last
           // bit is far below FP32 resolution)
-          const double inv_a = p.gv > 1 ? p.max_accel / (double)(p.gv - 1) : 0.0;
+          const double inv_a = p.acc_step;
           for (int c = tid; c < p.vd_cols * kpar; c += T) {
             const int m = c % p.vd_cols;
             int i = ic0 * kC + m;
             i = i < p.gv ? i : p.gv - 1;
             const double adt = inv_a * (double)(2 * i - (p.gv - 1)) * dt;
+#pragma unroll 4
             for (int k = 1 + c / p.vd_cols; k <= N; k += kpar) {
               const double vv = dadd(v_seed, dmul(adt, (double)k));
               VD[(k - 1) * p.vd_cols + m] = (float)((vv > 0.0 ? vv : 0.0) * dt);
             }
           }
+          team.sync();
         }
-        team.sync();
         if (pidx == 0 && use_skip) {   // hd->bw and hd->ts are visible now: the widest band
           float tl_all = 0.f, s0_all = 0.f, s1_all = 0.f;
           for (int qq = 0; qq < NW; ++qq) {
@@ -982,7 +1047,7 @@ vmvo_window_search_kernel(const SearchParams p) {
             if (fast) {
               // a_i by multiplication with 1/(G-1): last-bit differences from the spec's
               // division are far below the FP32 resolution this scan works at
-              const double inv = p.gv > 1 ? p.max_accel / (double)(p.gv - 1) : 0.0;
+              const double inv = p.acc_step;
               const int i0 = ic * kC;
               const double a0d = inv * (double)(2 * i0 - (p.gv - 1));
               const double dtd = dt * dt;
@@ -1022,7 +1087,7 @@ vmvo_window_search_kernel(const SearchParams p) {
             // hypotheses for the affine headings of the packed scan, max(a_last, 0) otherwise)
             const int i0 = ic * kC;
             const int il = i0 + kC - 1 < p.gv ? i0 + kC - 1 : p.gv - 1;
-            const float inv = p.gv > 1 ? (float)(p.max_accel / (double)(p.gv - 1)) : 0.f;
+            const float inv = (float)p.acc_step;
             const float a_first = inv * (float)(2 * i0 - (p.gv - 1));
             const float a_last = inv * (float)(2 * il - (p.gv - 1));
             const float acoef = fast ? fmaxf(fabsf(a_first), fabsf(a_last)) : fmaxf(a_last, 0.f);
@@ -1175,6 +1240,7 @@ vmvo_window_search_kernel(const SearchParams p) {
         s_chain = s_last;
       }
     }
+#ifndef VMVO_EXP_NO_OUT
     if (p.out_poses || p.out_steer || p.out_vel) {
       team.sync();
       const int h = hd->winner;
@@ -1204,6 +1270,7 @@ vmvo_window_search_kernel(const SearchParams p) {
         }
       }
     }
+#endif
     team.sync();
   }
 }
@@ -1377,11 +1444,14 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
   // team size: about two passes of 32 items per warp (measured best on 32x32: two warps)
   int tw = 1;
   while (tw < cta_warps && p.n_items > tw * 32 * 2) tw *= 2;
+  // a small grid's whole VD table (every acceleration) fits beside the rest: one fill and one
+  // barrier per window instead of one per pass
+  const bool vd_whole = (size_t)p.n_ic * kC * cfg->max_window_poses * 4 <= 8192;
   // ... unless the per-team tables would not leave room for two CTAs per SM
   for (;;) {
     const int th = tw * 32;
     int ch = chunks_per_pass(th, p.gs);
-    if (ch > p.n_ic) ch = p.n_ic;
+    if (ch > p.n_ic || vd_whole) ch = p.n_ic;
     const SmemLayout probe(cfg->max_window_poses, p.gs, ch * kC, tw, (int)load_vo + (int)load_gps,
                            use_vo && use_gps, use_imu, cfg->target_mode == VMVO_TARGET_TRAVERSE,
                            f64 ? 32 : 16);
@@ -1407,6 +1477,7 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
   // accelerations one pass can touch: items [pass*T, pass*T + T) span at most this many chunks
   int chunks = chunks_per_pass(threads, p.gs);
   if (chunks > p.n_ic) chunks = p.n_ic;
+  if (vd_whole) chunks = p.n_ic;
   p.vd_cols = chunks * kC;
   p.target_mode = cfg->target_mode;
   p.target_offset = cfg->target_offset;
@@ -1428,6 +1499,9 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
   p.max_rate = cfg->max_steer_rate;
   p.delta_max = cfg->max_steer * kDegToRad / cfg->steering_ratio;
   p.kappa = 2 * p.delta_max / sin(2 * p.delta_max);
+  p.acc_step = p.gv > 1 ? cfg->max_accel / (double)(p.gv - 1) : 0.0;
+  p.rate_step = p.gs > 1 ? cfg->max_steer_rate / (double)(p.gs - 1) : 0.0;
+  p.inv_L = (float)(1.0 / cfg->wheel_base);
   if (!(p.kappa > 0) || p.kappa > 64) p.kappa = 64;
   p.win_start = (const long long*)d_win_start;
   p.win_len = d_win_len;
