@@ -336,13 +336,11 @@ extern "C" int vmvo_ctx_create(int device, vmvo_ctx** out) {
   ctx->n_mirrors = 0;
   ctx->mirror_off = 0;
   ctx->n_defer = 0;
-  ctx->d_defer_count = nullptr;
   ctx->err[0] = 0;
   ctx->d_work_counter = nullptr;
   cudaDeviceProp prop;
   if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess ||
-      cudaMalloc(&ctx->d_work_counter, 64 * sizeof(unsigned long long)) != cudaSuccess ||
-      cudaMalloc(&ctx->d_defer_count, 64 * sizeof(unsigned)) != cudaSuccess) {
+      cudaMalloc(&ctx->d_work_counter, 64 * 2 * sizeof(unsigned long long)) != cudaSuccess) {
     delete ctx;
     return VMVO_ERR_CUDA;
   }
@@ -360,7 +358,6 @@ extern "C" int vmvo_ctx_destroy(vmvo_ctx* ctx) {
   if (!ctx) return VMVO_OK;
   cudaSetDevice(ctx->device);
   cudaFree(ctx->d_work_counter);
-  cudaFree(ctx->d_defer_count);
   for (int q = 0; q < ctx->n_defer; ++q) cudaFree(ctx->d_defer[q]);
   delete ctx;
   return VMVO_OK;

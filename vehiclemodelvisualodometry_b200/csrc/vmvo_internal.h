@@ -11,7 +11,9 @@
 struct vmvo_ctx {
   int device;
   int sm_count;
-  unsigned long long* d_work_counter;  // persistent-kernel work queue head
+  // 64 pairs (work-queue head of the persistent search, deferred-window slot count), one pair per
+  // launch in rotation: 16 bytes, cleared by one memset
+  unsigned long long* d_work_counter;
   long long launches;
   // result mirrors (vmvo_set_result_mirrors): every record is also stored at mirrors[q][off + w]
   int n_mirrors;
@@ -22,7 +24,6 @@ struct vmvo_ctx {
   unsigned char* d_defer[8];
   size_t defer_bytes[8];
   int n_defer;
-  unsigned* d_defer_count;             // 64 counters, one per launch in rotation
   char err[512];
 };
 

@@ -797,20 +797,29 @@ vmvo_window_search_kernel(const SearchParams p) {
       const float invL = p.inv_L;
       const int kpar = tl_kpar(T, p.gs);
       const bool poly = p.delta_max <= 0.6199;     // every clamped angle is inside the polynomial's range
+      const bool noclamp = fabs(s_seed) + p.max_rate * ((double)N * fabs(dt)) * 1.000001 <= p.max_steer;
       for (int c = tid; c < p.gs * kpar; c += T) {
         const int ks = c / p.gs, j = c - ks * p.gs;
         // r_j by multiplication: its last float64 bit is far below the float rounding of the angle
         const double rdt = p.rate_step * (double)(2 * j - (p.gs - 1)) * dt;
+        const double c0 = s_seed * kd, ck = rdt * kd, kstep = (double)kpar;
+        const float kstepf = (float)kpar;
         float mx = 0.f, s0 = 0.f, s1 = 0.f;
         for (int k0 = 1 + ks; k0 <= N; k0 += 4 * kpar) {
           float x[4], tl[4];
+          const double kq = (double)k0;
+          const float kf = (float)k0;
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const int k = k0 + u * kpar;
-            double sd = dadd(s_seed, dmul(rdt, (double)k));
-            sd = sd < -p.max_steer ? -p.max_steer : sd;
-            sd = sd > p.max_steer ? p.max_steer : sd;
-            x[u] = (float)(sd * kd);
+            const double ku = fma((double)u, kstep, kq);     // k = k0 + u * kpar
+            if (noclamp) {       // window-uniform: no rate reaches the steering limit within N steps
+              x[u] = (float)fma(ck, ku, c0);
+            } else {
+              double sd = dadd(s_seed, dmul(rdt, ku));
+              sd = sd < -p.max_steer ? -p.max_steer : sd;
+              sd = sd > p.max_steer ? p.max_steer : sd;
+              x[u] = (float)(sd * kd);
+            }
           }
           if (poly) {
 #pragma unroll
@@ -827,7 +836,7 @@ vmvo_window_search_kernel(const SearchParams p) {
               const float a = fabsf(tl[u]);
               mx = fmaxf(mx, a);
               s0 += a;
-              s1 = fmaf((float)k, a, s1);
+              s1 = fmaf(fmaf((float)u, kstepf, kf), a, s1);
             }
           }
         }
@@ -852,12 +861,12 @@ vmvo_window_search_kernel(const SearchParams p) {
     }
     {
       // block max of the band inputs
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        dmax = fmaxf(dmax, __shfl_xor_sync(FULL, dmax, o));
-        dabmax = fmaxf(dabmax, __shfl_xor_sync(FULL, dabmax, o));
-        imax = fmaxf(imax, __shfl_xor_sync(FULL, imax, o));
-      }
+      // (non-negative floats order like their bit patterns; a non-finite input anywhere in the
+      // window travels as dmax = +inf, which no finite increment can reach)
+      if (!finite) dmax = CUDART_INF_F;
+      dmax = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(dmax)));
+      if (DUAL) dabmax = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(dabmax)));
+      if (IMU) imax = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(imax)));
       if (lane == 0) {
         hd->red[warp] = dmax;
         hd->red[kMaxWarps + warp] = dabmax;
@@ -865,13 +874,13 @@ vmvo_window_search_kernel(const SearchParams p) {
       }
     }
     team.sync();   // red[] complete
-    const int bad = team.any(finite ? 0 : 1);
     dmax = dabmax = imax = 0.f;
     for (int q = 0; q < NW; ++q) {
       dmax = fmaxf(dmax, hd->red[q]);
-      dabmax = fmaxf(dabmax, hd->red[kMaxWarps + q]);
-      imax = fmaxf(imax, hd->red[2 * kMaxWarps + q]);
+      if (DUAL) dabmax = fmaxf(dabmax, hd->red[kMaxWarps + q]);
+      if (IMU) imax = fmaxf(imax, hd->red[2 * kMaxWarps + q]);
     }
+    const bool bad = !(dmax < CUDART_INF_F);
     const int status = (N <= 0 ? VMVO_WIN_EMPTY : 0) | (bad ? VMVO_WIN_NONFINITE : 0);
     // team-uniform per-window state stays in the shared-memory header (hd->wi, hd->bw, the warps'
     // running best): registers are for the scan
@@ -1016,7 +1025,7 @@ vmvo_window_search_kernel(const SearchParams p) {
             const double adt = inv_a * (double)(2 * i - (p.gv - 1)) * dt;
 #pragma unroll 4
             for (int k = 1 + c / p.vd_cols; k <= N; k += kpar) {
-              const double vv = dadd(v_seed, dmul(adt, (double)k));
+              const double vv = fma(adt, (double)k, v_seed);
               VD[(k - 1) * p.vd_cols + m] = (float)((vv > 0.0 ? vv : 0.0) * dt);
             }
           }
@@ -1124,16 +1133,19 @@ vmvo_window_search_kernel(const SearchParams p) {
         for (int c = 0; c < kC; ++c)
           if (((valid >> c) & 1u) && !(so.J[c] > Jcut)) pend |= 1u << c;
         // drop structural duplicates: only the lowest index of a class can win (np.argmin)
-        if (j > wi.sat_lo && j <= wi.sat_hi) pend = 0;
+        if (pend) {      // (few threads hold a candidate at all)
+          if (j > wi.sat_lo && j <= wi.sat_hi) pend = 0;
 #pragma unroll
-        for (int c = 0; c < kC; ++c) {
-          const int i = ic * kC + c;
-          // (with a steering penalty the cost of a motionless row still depends on j)
-          if (i < wi.n_dead && (i > 0 || (j > 0 && !ksteer))) pend &= ~(1u << c);
+          for (int c = 0; c < kC; ++c) {
+            const int i = ic * kC + c;
+            // (with a steering penalty the cost of a motionless row still depends on j)
+            if (i < wi.n_dead && (i > 0 || (j > 0 && !ksteer))) pend &= ~(1u << c);
+          }
         }
         for (;;) {
 #pragma unroll
           for (int c = 0; c < kC; ++c) {
+            if (pend == 0) break;
             if ((pend >> c) & 1u) {
               const int slot = atomicAdd(&hd->count, 1);
               if (slot < cand_cap) {
@@ -1529,8 +1541,8 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
   cudaStream_t st = (cudaStream_t)stream;
   VMVO_CUDA(ctx, cudaSetDevice(ctx->device));
   // one of 64 queue heads per launch so launches on different streams do not share one
-  unsigned long long* counter = ctx->d_work_counter + (ctx->launches & 63);
-  VMVO_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
+  unsigned long long* counter = ctx->d_work_counter + 2 * (ctx->launches & 63);
+  VMVO_CUDA(ctx, cudaMemsetAsync(counter, 0, 2 * sizeof(unsigned long long), st));   // head + slot count
   p.work_counter = counter;
 
   // deferred windows: a slot per window up to a 64 MiB budget.  Not with chained seeds (the next
@@ -1576,8 +1588,7 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
       p.defer_buf = ctx->d_defer[have];
       p.defer_slots = (int)(slots > 0x7fffffff ? 0x7fffffff : slots);
       p.defer_slot_bytes = (int)slot_bytes;
-      p.defer_count = ctx->d_defer_count + (ctx->launches & 63);
-      VMVO_CUDA(ctx, cudaMemsetAsync(p.defer_count, 0, sizeof(unsigned), st));
+      p.defer_count = reinterpret_cast<unsigned*>(counter + 1);
     }
   }
 

@@ -335,8 +335,8 @@ def optimize_drives(cfg: SearchConfig, drives: DriveSet, plan: Optional[WindowPl
 
 class DrivePipeline:
     """plan -> search -> write-back for one resident batch of drives, captured once as a CUDA
-    graph and replayed: four kernel launches (plan, search, deferred re-scores, write-back) and two
-    memsets per pass, no per-pass host work.
+    graph and replayed: four kernel launches (plan, search, deferred re-scores, write-back) and one
+    memset per pass, no per-pass host work.
 
     The pose streams and stamps are read from ``drives`` at replay time, so new data of the
     same shape can be copied into ``drives.vo`` / ``.gps`` / ``.imu`` / ``.time`` between passes.
