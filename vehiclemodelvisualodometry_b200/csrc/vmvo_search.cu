@@ -38,6 +38,10 @@ struct SearchParams {
   int team_warps;        // warps per team (1, 2, 4 or 8)
   int cand_cap;          // candidate list entries per team (<= kCandPerWarp * team_warps)
   int allow_fast;        // use the packed / rotation scan where its preconditions hold
+  // launch constants the kernel would otherwise divide for, window after window: passes per window,
+  // threads that share a rate in the TL fill / a column in the VD fill, and log2 of gs, vd_cols and
+  // the team's thread count when they are powers of two (-1: divide)
+  int n_pass, tl_slices, vd_kpar, gs_sh, vd_sh, t_sh;
   double w_vo, w_gps, w_imu, k_steer;
   double L, ratio, max_steer, max_accel, max_rate;
   double delta_max, kappa;     // kappa = 2*delta_max / sin(2*delta_max): tan's condition number
@@ -173,6 +177,14 @@ struct SmemHeader {
 };
 static_assert(sizeof(SmemHeader) <= kHeaderBytes, "header too large");
 
+// x / d for x >= 0, by a shift when the host found d to be a power of two (sh = log2 d, else -1)
+__device__ __forceinline__ int div_sh(int x, int d, int sh) { return sh >= 0 ? x >> sh : x / d; }
+static inline int log2_exact(int d) {
+  for (int b = 0; b < 31; ++b)
+    if (d == (1 << b)) return b;
+  return -1;
+}
+
 // ---- team barriers: named barrier 1 + team index; a one-warp team only needs __syncwarp ------
 struct Team {
   int warps, threads, id;
@@ -246,7 +258,7 @@ __device__ __forceinline__ Band make_band(const BandWin& w, float vmax, float th
 template <bool DUAL, bool IMU>
 __device__ double warp_cost64(const SearchParams& p, const WinInfo& wi, const double* tgt, int P,
                               int h, int lane, double wA, double wB, Pose<double>* first) {
-  const int i = h / p.gs, j = h - i * p.gs;
+  const int i = div_sh(h, p.gs, p.gs_sh), j = h - i * p.gs;
   GridCtl g{wi.v_seed, wi.s_seed, wi.dt, grid_rate(p.max_accel, i, p.gv),
             grid_rate(p.max_rate, j, p.gs), p.max_steer};
   const double* tAx = tgt;
@@ -475,7 +487,7 @@ vmvo_window_search_kernel(const SearchParams p) {
                        p.target_mode == VMVO_TARGET_TRAVERSE, (int)sizeof(Pose4));
   // stream s (0 = VO, 1 = GPS) lives in slot s when both are staged, else in slot 0
   const int slot_vo = 0, slot_gps = p.load_vo ? 1 : 0;
-  const Team team{p.team_warps, p.team_warps * 32, (int)threadIdx.x / (p.team_warps * 32)};
+  const Team team{p.team_warps, p.team_warps * 32, (int)threadIdx.x >> p.t_sh};
   unsigned char* smem = smem_cta + (size_t)team.id * lay.total;
   SmemHeader* hd = reinterpret_cast<SmemHeader*>(smem);
   Pose4* raw = reinterpret_cast<Pose4*>(smem + lay.off_raw);
@@ -795,24 +807,26 @@ vmvo_window_search_kernel(const SearchParams p) {
       // The per-rate statistics of the band (max |TL|, sum |TL|, sum k |TL|) are taken on the way;
       // the threads that share a rate leave their parts in TSP, added up after the barrier.
       const float invL = p.inv_L;
-      const int kpar = tl_kpar(T, p.gs);
+      const int kpar = p.tl_slices;
       const bool poly = p.delta_max <= 0.6199;     // every clamped angle is inside the polynomial's range
       const bool noclamp = fabs(s_seed) + p.max_rate * ((double)N * fabs(dt)) * 1.000001 <= p.max_steer;
       for (int c = tid; c < p.gs * kpar; c += T) {
-        const int ks = c / p.gs, j = c - ks * p.gs;
+        const int ks = div_sh(c, p.gs, p.gs_sh), j = c - ks * p.gs;
         // r_j by multiplication: its last float64 bit is far below the float rounding of the angle
         const double rdt = p.rate_step * (double)(2 * j - (p.gs - 1)) * dt;
         const double c0 = s_seed * kd, ck = rdt * kd, kstep = (double)kpar;
         const float kstepf = (float)kpar;
         float mx = 0.f, s0 = 0.f, s1 = 0.f;
-        for (int k0 = 1 + ks; k0 <= N; k0 += 4 * kpar) {
+        // fast: no clamps, polynomial tangent; full: all four steps are inside the window -- the
+        // common group is then one straight line of code (the lambda is specialised per call)
+        auto group = [&](int k0, const bool fast, const bool full) {
           float x[4], tl[4];
           const double kq = (double)k0;
           const float kf = (float)k0;
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const double ku = fma((double)u, kstep, kq);     // k = k0 + u * kpar
-            if (noclamp) {       // window-uniform: no rate reaches the steering limit within N steps
+            if (fast || noclamp) {
               x[u] = (float)fma(ck, ku, c0);
             } else {
               double sd = dadd(s_seed, dmul(rdt, ku));
@@ -821,7 +835,7 @@ vmvo_window_search_kernel(const SearchParams p) {
               x[u] = (float)(sd * kd);
             }
           }
-          if (poly) {
+          if (fast || poly) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) tl[u] = tan_poly(x[u]) * invL;
           } else {
@@ -831,13 +845,22 @@ vmvo_window_search_kernel(const SearchParams p) {
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int k = k0 + u * kpar;
-            if (k <= N) {
+            if (full || k <= N) {
               TL[(k - 1) * p.gs + j] = tl[u];
               const float a = fabsf(tl[u]);
               mx = fmaxf(mx, a);
               s0 += a;
               s1 = fmaf(fmaf((float)u, kstepf, kf), a, s1);
             }
+          }
+        };
+        const bool fastpath = noclamp && poly;     // window-uniform
+        for (int k0 = 1 + ks; k0 <= N; k0 += 4 * kpar) {
+          if (fastpath) {
+            if (k0 + 3 * kpar <= N) group(k0, true, true);
+            else group(k0, true, false);
+          } else {
+            group(k0, false, false);
           }
         }
         float* tp = TSP + 3 * gs4 * ks;
@@ -894,7 +917,7 @@ vmvo_window_search_kernel(const SearchParams p) {
 
     // per steering rate: max |TL|, sum |TL|, sum k |TL| over the steps (the items' band inputs)
     float tmx = 0.f, ts0 = 0.f, ts1 = 0.f;
-    const int tl_slices = tl_kpar(T, p.gs);
+    const int tl_slices = p.tl_slices;
     for (int j = tid; j < p.gs; j += T) {
       float mx = 0.f, s0 = 0.f, s1 = 0.f;
       const float* t = TSP + j;
@@ -999,7 +1022,7 @@ vmvo_window_search_kernel(const SearchParams p) {
       };
 
       const bool fast_w = (C == 8 && !IMU) && p.allow_fast && v_seed >= 0.0;   // window-uniform
-      const int n_pass = (p.n_items + T - 1) / T;
+      const int n_pass = p.n_pass;
       const bool vd_full = p.vd_cols >= p.n_ic * kC;
       // With more than two passes: (i) the passes run middle-out over the accelerations -- the
       // optimum usually sits near a = 0, so U is tight after the first pass and few candidates are
@@ -1012,19 +1035,19 @@ vmvo_window_search_kernel(const SearchParams p) {
         const int pass = !use_skip ? pidx : (pidx & 1) ? mid + ((pidx + 1) >> 1) : mid - (pidx >> 1);
         // VD[k][m] = V_k(ic0*C + m) * dt for the accelerations this pass touches
         // (a table that covers every acceleration is filled once per window: vd_full)
-        const int ic0 = vd_full ? 0 : (pass * T) / p.gs;
+        const int ic0 = vd_full ? 0 : div_sh(pass * T, p.gs, p.gs_sh);
         if (!vd_full || pidx == 0) {
-          const int kpar = T >= p.vd_cols ? T / p.vd_cols : 1;
+          const int kpar = p.vd_kpar;
           // a_i by multiplication (the float64 re-score uses the spec's division; here the last
           // bit is far below FP32 resolution)
           const double inv_a = p.acc_step;
           for (int c = tid; c < p.vd_cols * kpar; c += T) {
-            const int m = c % p.vd_cols;
+            const int kv = div_sh(c, p.vd_cols, p.vd_sh), m = c - kv * p.vd_cols;
             int i = ic0 * kC + m;
             i = i < p.gv ? i : p.gv - 1;
             const double adt = inv_a * (double)(2 * i - (p.gv - 1)) * dt;
 #pragma unroll 4
-            for (int k = 1 + c / p.vd_cols; k <= N; k += kpar) {
+            for (int k = 1 + kv; k <= N; k += kpar) {
               const double vv = fma(adt, (double)k, v_seed);
               VD[(k - 1) * p.vd_cols + m] = (float)((vv > 0.0 ? vv : 0.0) * dt);
             }
@@ -1050,7 +1073,7 @@ vmvo_window_search_kernel(const SearchParams p) {
         Band band{0.f, 0.f, 0.f};
         const bool fast = fast_w;
         if (q < p.n_items) {
-          ic = q / p.gs;
+          ic = div_sh(q, p.gs, p.gs_sh);
           j = q - ic * p.gs;
           if constexpr (C == 8 && !IMU) {
             if (fast) {
@@ -1491,6 +1514,12 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
   if (chunks > p.n_ic) chunks = p.n_ic;
   if (vd_whole) chunks = p.n_ic;
   p.vd_cols = chunks * kC;
+  p.n_pass = (p.n_items + threads - 1) / threads;
+  p.tl_slices = tl_kpar(threads, p.gs);
+  p.vd_kpar = threads >= p.vd_cols ? threads / p.vd_cols : 1;
+  p.gs_sh = log2_exact(p.gs);
+  p.vd_sh = log2_exact(p.vd_cols);
+  p.t_sh = log2_exact(threads);
   p.target_mode = cfg->target_mode;
   p.target_offset = cfg->target_offset;
   p.seed_mode = cfg->seed_mode;
