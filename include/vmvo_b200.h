@@ -10,9 +10,11 @@
  * Conventions
  *   - plain C types; every `const T* d_xxx` / `T* d_xxx` is a DEVICE pointer owned by the
  *     caller (e.g. torch.Tensor.data_ptr()); the library allocates nothing persistent
- *     except the opaque vmvo_ctx (work counter, error text);
+ *     except the opaque vmvo_ctx (work counters, the scratch of deferred windows, error text);
  *   - calls are stream-ordered on the caller's `stream` (a cudaStream_t passed as void*)
- *     and asynchronous; one host thread per ctx;
+ *     and asynchronous; one host thread per ctx.  Searches of one ctx share its deferred-window
+ *     scratch: issue them on one stream (or on streams that do not run them at the same time);
+ *     for searches that overlap in time use one ctx per stream;
  *   - return value: vmvo_status (0 = ok); vmvo_last_error(ctx) gives the text.
  *   - pose streams are float4 (x [m], y [m], theta [rad], v [m/s]) per frame (double4 in the
  *     _f64 entry points), all drives concatenated; `d_drive_offsets[n_drives + 1]` delimits them; `d_time` is float64 [s].

@@ -25,6 +25,8 @@ CASES = {
     "vo_1x9": SearchConfig(grid_v=1, grid_s=9, window_frames=16),
     "vo_9x1": SearchConfig(grid_v=9, grid_s=1, window_frames=16),
     "vo_16x16": SearchConfig(grid_v=16, grid_s=16, window_frames=20),
+    # neither grid_s nor the VD table width (24 columns) is a power of two: the kernel divides
+    "vo_24x12": SearchConfig(grid_v=24, grid_s=12, window_frames=18),
     "vo_32x32_w30": SearchConfig(grid_v=32, grid_s=32, window_frames=30),
     "vo_offset0": SearchConfig(grid_v=12, grid_s=12, window_frames=20, target_offset=0),
     "gps_traverse": SearchConfig(grid_v=8, grid_s=24, window_frames=40, target_mode="traverse",
