@@ -301,7 +301,8 @@ def run_b200(args):
         traj_pin.copy_(traj, non_blocking=True)
 
     e2e_note = "serial per step: H2D, plan + search + write-back (+ gather), D2H on one stream"
-    if world == 1:
+    stream = None
+    if world == 1 or peer is not None:
         # software-pipelined across steps, as a caller streaming drives through the API would run
         # it: two resident drive buffers; the timed interval of step s carries the H2D of step
         # s + 1's inputs, the compute of step s and the D2H of step s - 1's results, on three
@@ -310,7 +311,18 @@ def run_b200(args):
         # intervals runs with all streams idle).  The last step's D2H is timed by the drain.
         from vehiclemodelvisualodometry_b200 import DriveStream
 
-        stream = DriveStream(cfg, drives, blend_gps=False)       # the public streaming API
+        factory = None
+        if peer is not None:
+            # N > 1: the stream's two pipelines write their records into the two gather buffers, with
+            # the result mirrors in force while their graphs are captured (the fused gather)
+            def factory(b, d):
+                peer[b].enable()
+                try:
+                    return DrivePipeline(cfg, d, blend_gps=False, records=local[b])
+                finally:
+                    peer[b].disable()
+
+        stream = DriveStream(cfg, drives, blend_gps=False, pipe_factory=factory)   # the public streaming API
         inputs = {"vo": vo_pin, "time": t_pin}
         stream.prime(inputs)                                     # inputs of the very first step
         torch.cuda.synchronize(dev)
@@ -325,7 +337,8 @@ def run_b200(args):
 
         e2e_ms = timed(e2e_step, args.steps, args.warmup, drain=e2e_drain) / args.steps
         e2e_note = ("pipelined across steps on three streams: each timed interval = H2D(step s+1) || "
-                    "plan + search + write-back(step s) || D2H(step s-1), joined before the interval ends")
+                    "plan + search + write-back(step s)" + (" with the fused gather" if peer is not None else "") +
+                    " || D2H(step s-1), joined before the interval ends")
         torch.cuda.synchronize(dev)
         chk = stream.host[(stream.n - 1) & 1][0].numpy().view(_lib.RESULT_DTYPE).reshape(-1)
         assert np.array_equal(chk["best_idx"], pipe.result_records()["best_idx"]), "e2e records differ"
@@ -367,7 +380,7 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
         if peer is not None:
-            del pipes, pipe
+            del pipes, pipe, stream
             for pg in peer:
                 pg.close()
         dist.destroy_process_group()

@@ -422,9 +422,13 @@ class DriveStream:
 
     ``inputs`` are dicts of pinned host tensors keyed like ``DriveSet`` (``vo``, ``gps``, ``imu``,
     ``time``), shaped like ``template``'s.  ``run`` wraps the stepping for an iterable of batches.
+
+    ``pipe_factory(b, drives_b)`` may build the pipeline of buffer ``b`` itself -- e.g. with its
+    records in a gather buffer and the result mirrors of ``scheduler.PeerGather`` in force while the
+    graph is captured (the multi-GPU form; bench.py, N > 1).
     """
 
-    def __init__(self, cfg: SearchConfig, template: DriveSet, blend_gps: bool = True):
+    def __init__(self, cfg: SearchConfig, template: DriveSet, blend_gps: bool = True, pipe_factory=None):
         dev = template.device
         self.dev = dev
         self.sets: List[DriveSet] = []
@@ -437,7 +441,8 @@ class DriveStream:
                          imu=None if template.imu is None else template.imu.clone(),
                          drive_offsets=list(template.drive_offsets),
                          d_drive_offsets=template.d_drive_offsets, dt=template.dt)
-            pipe = DrivePipeline(cfg, d, blend_gps=blend_gps)
+            pipe = (pipe_factory(len(self.pipes), d) if pipe_factory is not None
+                    else DrivePipeline(cfg, d, blend_gps=blend_gps))
             self.sets.append(d)
             self.pipes.append(pipe)
             self.host.append((torch.empty(tuple(pipe.records.shape), dtype=torch.uint8).pin_memory(),
