@@ -1,6 +1,6 @@
 """Runs the fused search a few times on one bench workload (target for ncu / sanitizer runs).
 
-    python tools/profile_search.py [workload] [launches]
+    python tools/profile_search.py [workload] [launches] [frames] [seed offset]
 """
 import os
 import sys
@@ -19,7 +19,8 @@ launches = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 n_frames, cfg = bench.make_cfg(workload)
 if len(sys.argv) > 3:
     n_frames = int(sys.argv[3])
-batch = synthetic_drives(1, n_frames, seed=bench.BASE_SEED)
+seed_off = int(sys.argv[4]) if len(sys.argv) > 4 else 0      # drive base + seed_off (bench.py: rank)
+batch = synthetic_drives(1, n_frames, seed=bench.BASE_SEED + seed_off)
 t, vo, _, _ = batch.drive(0)
 drives = DriveSet.from_arrays([t], [batch.dt], vo=[vo])
 plan = plan_windows(cfg, drives)

@@ -50,14 +50,24 @@ template <> struct Num<float> {
 };
 
 // ---- warp primitives -------------------------------------------------------------------
-template <typename T>
+// Inclusive scan over aligned groups of 2^STEPS lanes (the whole warp by default), Sklansky form:
+// in step s the upper half of every aligned block of 2^(s+1) lanes adds the total of its lower
+// half.  Same five shuffle + add steps as Hillis-Steele, but the association of the additions is
+// anchored at lane 0 of the group instead of at the receiving lane, which gives two properties the
+// search relies on:
+//   * every op is sign-symmetric, so negated inputs give exactly negated outputs (mirror hypotheses
+//     tie exactly);
+//   * if the inputs are zero from lane m on, every lane >= m - 1 holds the SAME value, bit for bit
+//     (x + 0 = x), and the lanes below 2^s never see steps >= s -- so a hypothesis that stops after
+//     m <= G steps gets identical sums from a G-lane group as from the whole warp (the packed
+//     float64 re-score of vmvo_deferred_rescore_kernel).
+template <typename T, int STEPS = 5>
 __device__ __forceinline__ T warp_scan_add(T v, int lane) {
-  // Hillis-Steele inclusive scan; every op is sign-symmetric, so negated inputs give
-  // exactly negated outputs (mirror hypotheses tie exactly).
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    T t = __shfl_up_sync(FULL, v, o);
-    if (lane >= o) v = Num<T>::add(v, t);
+  for (int s = 0; s < STEPS; ++s) {
+    const int src = (((lane >> s) << s) - 1) & 31;   // last lane of the block to the left
+    T t = __shfl_sync(FULL, v, src);
+    if ((lane >> s) & 1) v = Num<T>::add(v, t);
   }
   return v;
 }
@@ -102,7 +112,8 @@ struct GridCtl {
 template <typename T>
 struct Pose { T x, y, th; };
 
-template <typename T>
+// (STEPS < 5: independent rounds in aligned groups of 2^STEPS lanes, one carry per group)
+template <typename T, int STEPS = 5>
 __device__ __forceinline__ Pose<T> warp_model_round(T v, T s_deg, bool active, T dt, T L, T ratio,
                                                     Pose<T>& carry, int lane) {
   using N = Num<T>;
@@ -111,7 +122,7 @@ __device__ __forceinline__ Pose<T> warp_model_round(T v, T s_deg, bool active, T
     T delta = N::div(N::mul(s_deg, N::deg2rad()), ratio);
     inc_th = N::mul(N::mul(N::div(v, L), N::tan_(delta)), dt);
   }
-  T th = N::add(carry.th, warp_scan_add(inc_th, lane));
+  T th = N::add(carry.th, warp_scan_add<T, STEPS>(inc_th, lane));
   T ix = (T)0, iy = (T)0;
   if (active && v != (T)0) {
     T sn, cs;
@@ -121,11 +132,12 @@ __device__ __forceinline__ Pose<T> warp_model_round(T v, T s_deg, bool active, T
   }
   Pose<T> p;
   p.th = th;
-  p.x = N::add(carry.x, warp_scan_add(ix, lane));
-  p.y = N::add(carry.y, warp_scan_add(iy, lane));
-  carry.th = __shfl_sync(FULL, p.th, 31);
-  carry.x = __shfl_sync(FULL, p.x, 31);
-  carry.y = __shfl_sync(FULL, p.y, 31);
+  p.x = N::add(carry.x, warp_scan_add<T, STEPS>(ix, lane));
+  p.y = N::add(carry.y, warp_scan_add<T, STEPS>(iy, lane));
+  const int last = lane | ((1 << STEPS) - 1);
+  carry.th = __shfl_sync(FULL, p.th, last);
+  carry.x = __shfl_sync(FULL, p.x, last);
+  carry.y = __shfl_sync(FULL, p.y, last);
   return p;
 }
 

@@ -255,17 +255,39 @@ __device__ __forceinline__ Band make_band(const BandWin& w, float vmax, float th
 }
 
 // ---- float64 cost of one hypothesis, one warp, one step per lane ---------------------------
+// the cost term of step k (state after the step against target k - target_offset; mpc.py:70-78)
+template <bool DUAL, bool IMU>
+__device__ __forceinline__ double step_term(const SearchParams& p, const double* tgt, int P, int k,
+                                            const Pose<double>& pz, double s, double wA, double wB) {
+  const double* tAx = tgt;
+  const double* tAy = tgt + P;
+  const double* tBx = tgt + 2 * P;
+  const double* tBy = tgt + 3 * P;
+  const double* tI = tgt + (DUAL ? 4 : 2) * P;
+  const int t = k - p.target_offset;
+  double ex = dsub(pz.x, tAx[t]), ey = dsub(pz.y, tAy[t]);
+  double e = dadd(dmul(ex, ex), dmul(ey, ey));
+  double term = (wA == 1.0) ? e : dmul(wA, e);
+  if (DUAL) {
+    ex = dsub(pz.x, tBx[t]);
+    ey = dsub(pz.y, tBy[t]);
+    e = dadd(dmul(ex, ex), dmul(ey, ey));
+    term = dadd(term, (wB == 1.0) ? e : dmul(wB, e));
+  }
+  if (IMU) {
+    double d = remainder(dsub(pz.th, tI[t]), kTwoPi);
+    term = dadd(term, dmul(p.w_imu, dmul(d, d)));
+  }
+  if (p.k_steer != 0.0) term = dadd(term, dmul(p.k_steer, dmul(s, s)));
+  return term;
+}
+
 template <bool DUAL, bool IMU>
 __device__ double warp_cost64(const SearchParams& p, const WinInfo& wi, const double* tgt, int P,
                               int h, int lane, double wA, double wB, Pose<double>* first) {
   const int i = div_sh(h, p.gs, p.gs_sh), j = h - i * p.gs;
   GridCtl g{wi.v_seed, wi.s_seed, wi.dt, grid_rate(p.max_accel, i, p.gv),
             grid_rate(p.max_rate, j, p.gs), p.max_steer};
-  const double* tAx = tgt;
-  const double* tAy = tgt + P;
-  const double* tBx = tgt + 2 * P;
-  const double* tBy = tgt + 3 * P;
-  const double* tI = tgt + (DUAL ? 4 : 2) * P;
   Pose<double> carry{0.0, 0.0, 0.0};
   double J = 0.0;
   const int N = wi.n_steps;
@@ -280,27 +302,80 @@ __device__ double warp_cost64(const SearchParams& p, const WinInfo& wi, const do
       first->y = __shfl_sync(FULL, pz.y, 0);
       first->th = __shfl_sync(FULL, pz.th, 0);
     }
-    double term = 0.0;
-    if (active) {
-      const int t = k - p.target_offset;
-      double ex = dsub(pz.x, tAx[t]), ey = dsub(pz.y, tAy[t]);
-      double e = dadd(dmul(ex, ex), dmul(ey, ey));
-      term = (wA == 1.0) ? e : dmul(wA, e);
-      if (DUAL) {
-        ex = dsub(pz.x, tBx[t]);
-        ey = dsub(pz.y, tBy[t]);
-        e = dadd(dmul(ex, ex), dmul(ey, ey));
-        term = dadd(term, (wB == 1.0) ? e : dmul(wB, e));
-      }
-      if (IMU) {
-        double d = remainder(dsub(pz.th, tI[t]), kTwoPi);
-        term = dadd(term, dmul(p.w_imu, dmul(d, d)));
-      }
-      if (p.k_steer != 0.0) term = dadd(term, dmul(p.k_steer, dmul(s, s)));
-    }
+    const double term = active ? step_term<DUAL, IMU>(p, tgt, P, k, pz, s, wA, wB) : 0.0;
     J = dadd(J, warp_sum(term));
   }
   return J;
+}
+
+// ---- the same cost for several hypotheses that all stop within G = 2^LG steps, one warp -----------
+// (the near-ties of a slow vehicle: a braking row, every steering rate).  Lane group c (G lanes; 32 / G
+// groups: four hypotheses that stop within 8 steps, or two within 16) rolls hypothesis c through its
+// first G steps -- one pass through tan / sincos for all of them -- with the scans confined to the
+// group; from step G on the pose no longer changes.  Every value is bit-identical to warp_cost64's:
+// the group scan IS the warp scan on lanes 0..G-1 (warp_scan_add), the lanes beyond the last moving
+// step hold copies of its sums, a later round adds +0 to the carry, and the terms go through the same
+// step_term and the same butterfly.  h_grp: the hypothesis of this lane's group, or -1 (computed like
+// hypothesis 0 and ignored by the caller: without branches the butterflies of a round interleave).
+// Precondition (checked by the caller): V_k = 0 for every k > G of every hypothesis given.
+template <bool DUAL, bool IMU, int LG>
+__device__ __forceinline__ void warp_cost64_pack(const SearchParams& p, const WinInfo& wi,
+                                                 const double* tgt, int P, int h_grp, int lane,
+                                                 double wA, double wB, double (&cost)[32 >> LG],
+                                                 Pose<double> (&first)[32 >> LG]) {
+  constexpr int G = 1 << LG, NC = 32 >> LG;
+  const int N = wi.n_steps;
+  const int kk = (lane & (G - 1)) + 1;
+  const bool act = h_grp >= 0 && kk <= N;
+  const int hh = h_grp >= 0 ? h_grp : 0;
+  const int i = div_sh(hh, p.gs, p.gs_sh), j = hh - i * p.gs;
+  GridCtl g{wi.v_seed, wi.s_seed, wi.dt, grid_rate(p.max_accel, i, p.gv),
+            grid_rate(p.max_rate, j, p.gs), p.max_steer};
+  double v = 0.0, s = 0.0;
+  if (act) g.at(kk, &v, &s);
+  Pose<double> carry{0.0, 0.0, 0.0};
+  const Pose<double> pz = warp_model_round<double, LG>(v, s, act, wi.dt, p.L, p.ratio, carry, lane);
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    first[c].x = __shfl_sync(FULL, pz.x, G * c);
+    first[c].y = __shfl_sync(FULL, pz.y, G * c);
+    first[c].th = __shfl_sync(FULL, pz.th, G * c);
+    cost[c] = 0.0;
+  }
+  for (int base = 0; base < N; base += 32) {
+    const int k = base + lane + 1;
+    const bool active = k <= N;
+    double term[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int src = G * c + (k < G ? k : G) - 1;
+      Pose<double> q;
+      q.x = __shfl_sync(FULL, pz.x, src);
+      q.y = __shfl_sync(FULL, pz.y, src);
+      q.th = __shfl_sync(FULL, pz.th, src);
+      if (base > 0) {   // warp_cost64's later rounds: carry + (a scan of zeros)
+        q.x = dadd(q.x, 0.0);
+        q.y = dadd(q.y, 0.0);
+        q.th = dadd(q.th, 0.0);
+      }
+      double sk = 0.0;
+      if (p.k_steer != 0.0) {   // kernel-uniform
+        const int hc = __shfl_sync(FULL, hh, G * c);
+        const int jc = hc - div_sh(hc, p.gs, p.gs_sh) * p.gs;
+        const GridCtl gc{wi.v_seed, wi.s_seed, wi.dt, 0.0, grid_rate(p.max_rate, jc, p.gs), p.max_steer};
+        double v_unused;
+        gc.at(k, &v_unused, &sk);
+      }
+      term[c] = active ? step_term<DUAL, IMU>(p, tgt, P, active ? k : 1, q, sk, wA, wB) : 0.0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) term[c] = dadd(term[c], __shfl_xor_sync(FULL, term[c], o));
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) cost[c] = dadd(cost[c], term[c]);
+  }
 }
 
 // ---- FP32 scan of one item: steering rate j, accelerations m0 .. m0+C-1 of the VD table ------
@@ -1311,14 +1386,18 @@ vmvo_window_search_kernel(const SearchParams p) {
 }
 
 // ---- second kernel: the float64 re-scores of the deferred windows -------------------------------
-// One CTA of eight warps per slot; the warps share the window's candidate list round-robin, each
-// candidate through the same warp_cost64 as in the search kernel (the targets are read from the
-// slot instead of shared memory -- same values, same arithmetic, same cost).
+// One CTA of eight warps per slot.  The slot (header, float64 targets, list: a few KB) is copied to
+// shared memory first, and the warps share the list four entries at a time, each through the same
+// arithmetic as in the search kernel: warp_cost64, or warp_cost64_pack when all four stop within 8
+// or 16 steps -- which is what the near-ties of a slow vehicle do (same values, same operations,
+// same cost: test_deferred_windows_give_the_same_records).  Measured alternatives: 4 or 2 warps per
+// slot (6 / 12 slots per SM) and a persistent grid are slower.
 constexpr int kDeferWarps = 8;
 
 template <bool DUAL, bool IMU>
-__global__ void __launch_bounds__(32 * kDeferWarps)
+__global__ void __launch_bounds__(32 * kDeferWarps, 3)
 vmvo_deferred_rescore_kernel(const SearchParams p) {
+  extern __shared__ __align__(16) unsigned char s_slot[];
   __shared__ double s_cost[kDeferWarps], s_pose[kDeferWarps][3];
   __shared__ int s_h[kDeferWarps], s_n[kDeferWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1328,7 +1407,13 @@ vmvo_deferred_rescore_kernel(const SearchParams p) {
   const int n_arr = 2 + (DUAL ? 2 : 0) + (IMU ? 1 : 0);
   const double wA = p.use_vo ? p.w_vo : p.w_gps, wB = p.w_gps;
   for (unsigned s = blockIdx.x; s < n; s += gridDim.x) {
-    const unsigned char* slot = p.defer_buf + (size_t)s * p.defer_slot_bytes;
+    {
+      const uint4* src = reinterpret_cast<const uint4*>(p.defer_buf + (size_t)s * p.defer_slot_bytes);
+      uint4* dst = reinterpret_cast<uint4*>(s_slot);
+      for (int q = threadIdx.x; q < p.defer_slot_bytes / 16; q += 32 * kDeferWarps) dst[q] = src[q];
+    }
+    __syncthreads();
+    const unsigned char* slot = s_slot;
     const DeferHdr* dh = reinterpret_cast<const DeferHdr*>(slot);
     const double* tgt = reinterpret_cast<const double*>(slot + kDeferHdrBytes);
     const uint2* cand = reinterpret_cast<const uint2*>(slot + kDeferHdrBytes + (size_t)n_arr * P * 8);
@@ -1343,12 +1428,7 @@ vmvo_deferred_rescore_kernel(const SearchParams p) {
       best_cost = dh->best_cost;
       best_first = Pose<double>{dh->bpose[0], dh->bpose[1], dh->bpose[2]};
     }
-    for (int e = warp; e < count; e += kDeferWarps) {
-      const uint2 ce = cand[e];
-      if (__uint_as_float(ce.y) > fminf(U, Uw)) continue;   // warp-uniform; NaN stays in
-      const int h = (int)ce.x;
-      Pose<double> first;
-      const double c64 = warp_cost64<DUAL, IMU>(p, dh->wi, tgt, P, h, lane, wA, wB, &first);
+    auto take = [&](int h, double c64, const Pose<double>& first) {
       ++n_res;
       if (best_h < 0 || c64 < best_cost || (c64 == best_cost && h < best_h)) {
         best_h = h;
@@ -1356,6 +1436,64 @@ vmvo_deferred_rescore_kernel(const SearchParams p) {
         best_first = first;
       }
       Uw = fminf(Uw, __double2float_ru(c64));
+    };
+    // a warp takes four consecutive list entries at a time, one per group of eight lanes
+    const int N = dh->n_steps;
+    for (int e0 = 4 * warp; e0 < count; e0 += 4 * kDeferWarps) {
+      const int e = e0 + (lane >> 3);
+      int h_grp = -1;
+      if (e < count) {
+        const uint2 ce = cand[e];
+        if (!(__uint_as_float(ce.y) > fminf(U, Uw))) h_grp = (int)ce.x;   // NaN stays in
+      }
+      // packable: none of the four still moves after step 8 (or 16); each group checks its own,
+      // eight steps per turn, with the very control formula the rollout uses
+      bool late8 = false, late16 = false;
+      if (h_grp >= 0) {
+        const int i = div_sh(h_grp, p.gs, p.gs_sh);
+        const GridCtl g{dh->wi.v_seed, dh->wi.s_seed, dh->wi.dt, grid_rate(p.max_accel, i, p.gv), 0.0,
+                        p.max_steer};
+        for (int k = 9 + (lane & 7); k <= N; k += 8) {
+          double v, s_unused;
+          g.at(k, &v, &s_unused);
+          late8 |= v != 0.0;
+          late16 |= v != 0.0 && k > 16;
+        }
+      }
+      if (!__any_sync(FULL, h_grp >= 0)) continue;
+      if (!__any_sync(FULL, late8)) {
+        double c64[4];
+        Pose<double> first[4];
+        warp_cost64_pack<DUAL, IMU, 3>(p, dh->wi, tgt, P, h_grp, lane, wA, wB, c64, first);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int hc = __shfl_sync(FULL, h_grp, 8 * c);
+          if (hc >= 0) take(hc, c64[c], first[c]);
+        }
+      } else if (!__any_sync(FULL, late16)) {
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {      // entries (0, 1), then (2, 3): one per 16 lanes
+          const int h16 = __shfl_sync(FULL, h_grp, 8 * (2 * half + (lane >> 4)));
+          if (!__any_sync(FULL, h16 >= 0)) continue;
+          double c64[2];
+          Pose<double> first[2];
+          warp_cost64_pack<DUAL, IMU, 4>(p, dh->wi, tgt, P, h16, lane, wA, wB, c64, first);
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int hc = __shfl_sync(FULL, h16, 16 * c);
+            if (hc >= 0) take(hc, c64[c], first[c]);
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          const int hc = __shfl_sync(FULL, h_grp, 8 * c);
+          if (hc < 0) continue;              // warp-uniform
+          Pose<double> first;
+          const double c64 = warp_cost64<DUAL, IMU>(p, dh->wi, tgt, P, hc, lane, wA, wB, &first);
+          take(hc, c64, first);
+        }
+      }
     }
     if (lane == 0) {
       s_h[warp] = best_h;
@@ -1419,7 +1557,8 @@ static int launch_search_v(vmvo_ctx* ctx, const SearchParams& p, cudaStream_t st
   int rc = check_launch(ctx, "vmvo_window_search_kernel");
   if (rc || !p.defer_buf) return rc;
   long long g2 = p.defer_slots < (long long)ctx->sm_count * 16 ? p.defer_slots : (long long)ctx->sm_count * 16;
-  vmvo_deferred_rescore_kernel<DUAL, IMU><<<(unsigned)(g2 > 0 ? g2 : 1), 32 * kDeferWarps, 0, st>>>(p);
+  vmvo_deferred_rescore_kernel<DUAL, IMU><<<(unsigned)(g2 > 0 ? g2 : 1), 32 * kDeferWarps,
+                                            p.defer_slot_bytes, st>>>(p);
   return check_launch(ctx, "vmvo_deferred_rescore_kernel");
 }
 
