@@ -184,3 +184,38 @@ def test_deferred_windows_give_the_same_records(cuda_device, monkeypatch, defer_
     for f in ("best_idx", "n_steps", "status", "best_cost", "x1", "y1", "theta1", "v_seed", "s_seed"):
         np.testing.assert_array_equal(rec[f], base[f])
     assert_records_match(rec, oracle_windows(cfg, time, 0.05, vo))
+
+
+@pytest.mark.parametrize("case", ["w30", "w60_two_rounds", "vo_gps_imu", "ksteer"])
+def test_every_window_deferred_matches_in_kernel_rescore(cuda_device, monkeypatch, case):
+    """VMVO_DEFER_MIN=1 sends EVERY window's list through vmvo_deferred_rescore_kernel; index, cost and
+    first pose must equal the in-kernel re-score bit for bit, whichever of its three paths a list
+    entry takes (warp_cost64, the 16-lane and the 8-lane packed form), with one or two rounds of 32
+    steps and with every cost term.  A stop-and-go drive: its optima include rows that stop within
+    8 steps, within 16, and rows that never stop."""
+    from oracle import c_oracle
+
+    cfg = {
+        "w30": SearchConfig(grid_v=32, grid_s=16, window_frames=30),
+        "w60_two_rounds": SearchConfig(grid_v=32, grid_s=8, window_frames=60),
+        "vo_gps_imu": SearchConfig(grid_v=32, grid_s=8, window_frames=30, w_vo=1.0, w_gps=0.3, w_imu=20.0),
+        "ksteer": SearchConfig(grid_v=32, grid_s=8, window_frames=40, k_steer=2e-6),
+    }[case]
+    batch = synthetic_drives(1, 1500, seed=11)
+    t, vo, gps, imu = batch.drive(0)
+    monkeypatch.setenv("VMVO_DEFER_MIN", "1")
+    rec = _run(cfg, t, batch.dt, vo, gps, imu)
+    monkeypatch.setenv("VMVO_DEFER_MIN", "0")
+    base = _run(cfg, t, batch.dt, vo, gps, imu)
+    a = cfg.max_accel * (2 * (base["best_idx"] // cfg.grid_s) - (cfg.grid_v - 1)) / (cfg.grid_v - 1)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        stop = np.where(a < 0, np.ceil(base["v_seed"] / (-a * batch.dt)), np.inf)
+    assert (stop <= 8).sum() > 50 and ((stop > 8) & (stop <= 16)).sum() > 10 and (stop > 16).sum() > 500
+    for f in ("best_idx", "n_steps", "status", "best_cost", "x1", "y1", "theta1", "v_seed", "s_seed"):
+        np.testing.assert_array_equal(rec[f], base[f])
+    n_win = len(rec)
+    starts = np.arange(n_win, dtype=np.int64)
+    lens = np.full(n_win, cfg.window_frames + 1, np.int32)
+    ref, _ = c_oracle.search(cfg.to_c(), starts, lens, np.zeros(n_win, np.int32), [batch.dt], vo, gps, imu)
+    np.testing.assert_array_equal(rec["best_idx"], ref["best_idx"])
+    np.testing.assert_allclose(rec["best_cost"], ref["best_cost"], rtol=1e-9, atol=1e-18)
