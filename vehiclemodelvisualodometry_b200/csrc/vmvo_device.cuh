@@ -61,8 +61,22 @@ template <> struct Num<float> {
 //     (x + 0 = x), and the lanes below 2^s never see steps >= s -- so a hypothesis that stops after
 //     m <= G steps gets identical sums from a G-lane group as from the whole warp (the packed
 //     float64 re-score of vmvo_deferred_rescore_kernel).
-template <typename T, int STEPS = 5>
+//
+// HS = true: the Hillis-Steele form over the whole warp (additions associated from the receiving
+// lane; sign-symmetric as well).  The dense-grid kernel, whose windows are never parked for the
+// second kernel, re-scores with it: the same instruction count, but the kernel measures 3 % faster
+// (profiles/README.md).  A launch uses ONE form throughout (SearchParams::scan_hs).
+template <typename T, int STEPS = 5, bool HS = false>
 __device__ __forceinline__ T warp_scan_add(T v, int lane) {
+  if (HS) {
+    static_assert(!HS || STEPS == 5, "the Hillis-Steele form is for whole-warp scans");
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      T t = __shfl_up_sync(FULL, v, o);
+      if (lane >= o) v = Num<T>::add(v, t);
+    }
+    return v;
+  }
 #pragma unroll
   for (int s = 0; s < STEPS; ++s) {
     const int src = (((lane >> s) << s) - 1) & 31;   // last lane of the block to the left
@@ -113,7 +127,7 @@ template <typename T>
 struct Pose { T x, y, th; };
 
 // (STEPS < 5: independent rounds in aligned groups of 2^STEPS lanes, one carry per group)
-template <typename T, int STEPS = 5>
+template <typename T, int STEPS = 5, bool HS = false>
 __device__ __forceinline__ Pose<T> warp_model_round(T v, T s_deg, bool active, T dt, T L, T ratio,
                                                     Pose<T>& carry, int lane) {
   using N = Num<T>;
@@ -122,7 +136,7 @@ __device__ __forceinline__ Pose<T> warp_model_round(T v, T s_deg, bool active, T
     T delta = N::div(N::mul(s_deg, N::deg2rad()), ratio);
     inc_th = N::mul(N::mul(N::div(v, L), N::tan_(delta)), dt);
   }
-  T th = N::add(carry.th, warp_scan_add<T, STEPS>(inc_th, lane));
+  T th = N::add(carry.th, warp_scan_add<T, STEPS, HS>(inc_th, lane));
   T ix = (T)0, iy = (T)0;
   if (active && v != (T)0) {
     T sn, cs;
@@ -132,8 +146,8 @@ __device__ __forceinline__ Pose<T> warp_model_round(T v, T s_deg, bool active, T
   }
   Pose<T> p;
   p.th = th;
-  p.x = N::add(carry.x, warp_scan_add<T, STEPS>(ix, lane));
-  p.y = N::add(carry.y, warp_scan_add<T, STEPS>(iy, lane));
+  p.x = N::add(carry.x, warp_scan_add<T, STEPS, HS>(ix, lane));
+  p.y = N::add(carry.y, warp_scan_add<T, STEPS, HS>(iy, lane));
   const int last = lane | ((1 << STEPS) - 1);
   carry.th = __shfl_sync(FULL, p.th, last);
   carry.x = __shfl_sync(FULL, p.x, last);

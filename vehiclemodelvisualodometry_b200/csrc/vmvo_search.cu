@@ -42,6 +42,7 @@ struct SearchParams {
   // threads that share a rate in the TL fill / a column in the VD fill, and log2 of gs, vd_cols and
   // the team's thread count when they are powers of two (-1: divide)
   int n_pass, tl_slices, vd_kpar, gs_sh, vd_sh, t_sh;
+  int scan_hs;           // the launch's float64 prefix sums are Hillis-Steele (the many-pass kernel)
   double w_vo, w_gps, w_imu, k_steer;
   double L, ratio, max_steer, max_accel, max_rate;
   double delta_max, kappa;     // kappa = 2*delta_max / sin(2*delta_max): tan's condition number
@@ -282,7 +283,8 @@ __device__ __forceinline__ double step_term(const SearchParams& p, const double*
   return term;
 }
 
-template <bool DUAL, bool IMU>
+// (HS: the form of the prefix sums, warp_scan_add)
+template <bool DUAL, bool IMU, bool HS = false>
 __device__ double warp_cost64(const SearchParams& p, const WinInfo& wi, const double* tgt, int P,
                               int h, int lane, double wA, double wB, Pose<double>* first) {
   const int i = div_sh(h, p.gs, p.gs_sh), j = h - i * p.gs;
@@ -296,7 +298,7 @@ __device__ double warp_cost64(const SearchParams& p, const WinInfo& wi, const do
     const bool active = k <= N;
     double v = 0.0, s = 0.0;
     if (active) g.at(k, &v, &s);
-    Pose<double> pz = warp_model_round<double>(v, s, active, wi.dt, p.L, p.ratio, carry, lane);
+    Pose<double> pz = warp_model_round<double, 5, HS>(v, s, active, wi.dt, p.L, p.ratio, carry, lane);
     if (base == 0) {
       first->x = __shfl_sync(FULL, pz.x, 0);
       first->y = __shfl_sync(FULL, pz.y, 0);
@@ -1073,7 +1075,7 @@ vmvo_window_search_kernel(const SearchParams p) {
           if (__uint_as_float(ce.y) > fminf(U, Uw)) continue;  // warp-uniform; NaN stays in
           const int h = (int)ce.x;
           Pose<double> first;
-          const double c64 = warp_cost64<DUAL, IMU>(p, wi, tgt, P, h, lane, wA64, wB64, &first);
+          const double c64 = warp_cost64<DUAL, IMU, SKIP>(p, wi, tgt, P, h, lane, wA64, wB64, &first);
           const int best_h = hd->bh[warp];
           const double best_cost = hd->bcost[warp];
           __syncwarp();
@@ -1365,7 +1367,7 @@ vmvo_window_search_kernel(const SearchParams p) {
           const bool active = k <= N;
           double v = 0.0, s = 0.0;
           if (active) g.at(k, &v, &s);
-          Pose<double> pz = warp_model_round<double>(nonfinite ? 0.0 : v, s, active && !nonfinite,
+          Pose<double> pz = warp_model_round<double, 5, SKIP>(nonfinite ? 0.0 : v, s, active && !nonfinite,
                                                      wi.dt, p.L, p.ratio, carry, lane);
           if (active && k <= p.out_stride) {
             const long long o = w * (long long)p.out_stride + (k - 1);
@@ -1461,7 +1463,16 @@ vmvo_deferred_rescore_kernel(const SearchParams p) {
         }
       }
       if (!__any_sync(FULL, h_grp >= 0)) continue;
-      if (!__any_sync(FULL, late8)) {
+      if (p.scan_hs) {     // (a forced deferral of a many-pass launch: its sums are Hillis-Steele)
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          const int hc = __shfl_sync(FULL, h_grp, 8 * c);
+          if (hc < 0) continue;              // warp-uniform
+          Pose<double> first;
+          const double c64 = warp_cost64<DUAL, IMU, true>(p, dh->wi, tgt, P, hc, lane, wA, wB, &first);
+          take(hc, c64, first);
+        }
+      } else if (!__any_sync(FULL, late8)) {
         double c64[4];
         Pose<double> first[4];
         warp_cost64_pack<DUAL, IMU, 3>(p, dh->wi, tgt, P, h_grp, lane, wA, wB, c64, first);
@@ -1530,7 +1541,9 @@ vmvo_deferred_rescore_kernel(const SearchParams p) {
 }
 
 template <int C, int WARPS, int MINB, bool DUAL, bool IMU, typename SF, bool SKIP>
-static int launch_search_v(vmvo_ctx* ctx, const SearchParams& p, cudaStream_t st) {
+static int launch_search_v(vmvo_ctx* ctx, const SearchParams& p_in, cudaStream_t st) {
+  SearchParams p = p_in;
+  p.scan_hs = SKIP ? 1 : 0;      // the many-pass kernel re-scores with Hillis-Steele sums
   auto kern = vmvo_window_search_kernel<C, WARPS, MINB, DUAL, IMU, SF, SKIP>;
   constexpr int kCtaThreads = 32 * WARPS;
   const SmemLayout lay(p.maxp, p.gs, p.vd_cols, p.team_warps, p.load_vo + p.load_gps, DUAL, IMU,
