@@ -14,6 +14,10 @@
 // is, per hypothesis-step: 1 FFMA (heading), sin+cos on the SFU, 4 FP32 ops for the position
 // error recurrence and 2 FFMA for the cost.  A thread owns one steering rate j and C = 8
 // consecutive accelerations per pass.
+//
+// Small teams park windows with long candidate lists (near-ties of a slow vehicle) in a slot;
+// vmvo_deferred_rescore_kernel, launched right behind the search, re-scores them with the whole GPU,
+// four hypotheses per warp where they stop within a few steps -- same arithmetic, same records.
 #include "vmvo_device.cuh"
 #include "vmvo_internal.h"
 
