@@ -129,3 +129,55 @@ def test_sharded_search_gathers_over_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def _sklansky(values, steps):
+    """The association of warp_scan_add (csrc/vmvo_device.cuh), restated lane by lane in float64:
+    in step s the lanes whose bit s is set add the value of the last lane of the aligned block of
+    2^s lanes to their left."""
+    v = np.array(values, dtype=np.float64)
+    for s in range(steps):
+        prev = v.copy()
+        for lane in range(len(v)):
+            if (lane >> s) & 1:
+                v[lane] = prev[lane] + prev[((lane >> s) << s) - 1]
+    return v
+
+
+def test_sklansky_scan_properties_the_packed_rescore_relies_on():
+    """(1) it is an inclusive prefix sum; (2) inputs that are zero from lane m on leave the SAME
+    bits in every lane >= m - 1; (3) a group of 8 (16) lanes performs exactly the whole-warp scan's
+    operations on lanes 0..7 (0..15); (4) negated inputs give exactly negated outputs."""
+    rng = np.random.default_rng(5)
+    for trial in range(200):
+        a = rng.normal(0, 1, 32) * 10.0 ** rng.integers(-6, 3)
+        full = _sklansky(a, 5)
+        np.testing.assert_allclose(full, np.cumsum(a), rtol=0, atol=1e-14 * np.abs(a).sum())
+        assert np.array_equal(_sklansky(-a, 5), -full)
+        for m in (1, 2, 3, 5, 8, 11, 16):
+            z = a.copy()
+            z[m:] = 0.0
+            out = _sklansky(z, 5)
+            assert np.all(out[m - 1:] == out[m - 1]), (trial, m)
+            for lg in (3, 4):
+                g = 1 << lg
+                if m <= g:
+                    assert np.array_equal(_sklansky(z[:g], lg), out[:g]), (trial, m, lg)
+    # ... which the Hillis-Steele form does not have: (a0 + a1) + a2 at lane 2, but a later lane
+    # may see a0 + (a1 + a2)
+    def hillis_steele(values):
+        v = np.array(values, dtype=np.float64)
+        o = 1
+        while o < len(v):
+            prev = v.copy()
+            for lane in range(o, len(v)):
+                v[lane] = prev[lane] + prev[lane - o]
+            o <<= 1
+        return v
+    differs = 0
+    for trial in range(200):
+        z = np.zeros(32)
+        z[:3] = rng.normal(0, 1, 3)
+        out = hillis_steele(z)
+        differs += int(not np.all(out[2:] == out[2]))
+    assert differs > 0
