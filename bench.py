@@ -1,23 +1,36 @@
 #!/usr/bin/env python
 """Throughput of the VMVO window search: bicycle-model hypothesis-steps per second.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
 
-A step is one pass of the hot path over one batch of synthetic drives: window planning,
-the fused grid search and the write-back (plus, at N > 1, the all-gather of the 64-byte
-window records over NCCL).  At N = 1 the workload is BASELINE.json configs[1]: one
-10 000-frame drive, 32x32 hypothesis grid, 30-step windows (9 940 windows, 3.05e8
-hypothesis-steps).  At N > 1 every rank searches its own drive of that shape (weak scaling).
+A step is one pass of the hot path over one batch of synthetic drives: window planning, the fused
+grid search (with the float64 re-scores of parked windows) and the write-back.
 
-Rank 0 prints ONE JSON line (see the driver's contract in the task statement).  Keys beyond
-the contract: "roofline" (SFU-issue bound, with the HBM and FP32 figures beside it),
-"cpu_baseline" (the C/OpenMP oracle port on all host cores), "windows_per_s", and
-"dense_grid" (BASELINE configs[2], 256x256 x 60 steps: the compute-bound stress the
-roofline fraction is normally quoted on).
+N = 1: the workload is BASELINE.json configs[1] -- one 10 000-frame drive, 32x32 hypothesis grid,
+30-step windows (9 940 windows, 3.05e8 hypothesis-steps) -- or, with ``--workload
+config3_dense_256x256_w60``, configs[2] (4 096 windows of a 256x256 grid over 60 steps, 1.6e10).
 
---impl reference times the CPU implementation of the same path on the host cores: the
-reference itself is pure Python and does not travel to the GPU box, so this is the oracle
-port (oracle/vmvo_oracle.c, OpenMP over windows) on the same config.
+N > 1 (weak scaling): N drives of that shape (seeds base + 0..N-1) are POOLED: every rank holds all
+pose streams (they are tiny), the global window list is dealt to the ranks block-cyclically by the
+window scheduler (scheduler.py), every rank searches its share, the 64-byte records reach every rank
+from inside the search kernel (peer stores over NVLink), and each rank's write-back -- of its share of
+the frames -- consumes ALL ranks' records behind the arrival words the kernels exchange
+(vmvo_exchange, include/vmvo_b200.h).  So the exchange is on the critical path of the timed step and
+nothing else is: no collective, no host barrier.  ``value`` = hypothesis-steps of all N drives / the
+slowest rank's time.
+
+Rank 0 prints ONE JSON line (the driver's contract).  Keys beyond the contract: "roofline" (FP32
+issue / FMA pipe, with the SFU and HBM figures beside it), "cpu_baseline", "windows_per_s",
+"e2e_serial", "config3" (BASELINE configs[2] as a first-class measured workload with its own
+roofline / e2e / cpu_baseline; N = 1), "config4" / "config5" (BASELINE configs[3], [4]: batches of
+drives dealt over the N ranks, strong scaling against a one-GPU run of the same batch inside the
+same process group).
+
+--impl reference times the CPU implementation of the same path on the host cores: the reference
+itself is pure Python and does not exist on the GPU box, so this is the oracle port
+(oracle/vmvo_oracle.c, OpenMP over windows) on the same config; the numbers of the unmodified Python
+reference, measured in the build container by oracle/time_reference_cpu.py, ride along as
+``cpu_baseline.reference_python``.
 """
 from __future__ import annotations
 
@@ -44,14 +57,13 @@ BASE_SEED = 1658384707877 % (2 ** 32)
 # ops (tan = sin + cos + rcp) and 25 FP32 flops
 MUFU_PER_HSTEP = 5
 FLOP_PER_HSTEP = 25
-# (what the kernel executes per hypothesis-step depends on the scan it selects:
-# search.executed_mufu_per_hypothesis_step)
 
 WORKLOADS = {
     # name: (frames per drive, grid_v, grid_s, window steps)
     "config2_single_drive_10k_32x32_w30": (10000, 32, 32, 30),
     "config3_dense_256x256_w60": (4216, 256, 256, 60),
 }
+DEAL_BLOCK = 32          # windows per block of the block-cyclic deal (N > 1)
 
 
 def parse_args():
@@ -61,7 +73,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="config2_single_drive_10k_32x32_w30", choices=sorted(WORKLOADS))
-    ap.add_argument("--no-extras", action="store_true", help="skip dense-grid, probes and CPU baseline")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip config 3/4/5, the next-row kernels, the probes and the CPU baseline")
     return ap.parse_args()
 
 
@@ -70,6 +83,22 @@ def make_cfg(workload):
 
     n, gv, gs, w = WORKLOADS[workload]
     return n, SearchConfig(grid_v=gv, grid_s=gs, window_frames=w)
+
+
+def config_of(workload, n_frames, cfg, world=1):
+    """The ``config`` object: the same keys in both arms."""
+    return {"workload": workload, "frames_per_drive": n_frames, "drives": world,
+            "grid": [cfg.grid_v, cfg.grid_s], "window_steps": cfg.window_frames,
+            "windows": world * cfg.window_count(n_frames), "base_seed": BASE_SEED,
+            "cache": "256 MiB L2 flush between timed steps"}
+
+
+def load_json(*parts):
+    try:
+        with open(os.path.join(ROOT, *parts)) as f:
+            return json.load(f)
+    except Exception:
+        return {}
 
 
 # ---- clocks ----------------------------------------------------------------------------------
@@ -128,264 +157,204 @@ class ClockSampler:
         return out
 
 
-# ---- the B200 arm --------------------------------------------------------------------------------
-def run_b200(args):
-    import torch
-    import torch.distributed as dist
+# ---- timing ----------------------------------------------------------------------------------
+class Timer:
+    """CUDA events on the launching stream around each step, an L2 flush (256 MiB written) before
+    each, a barrier + synchronize on both sides, the MAX over ranks of the summed step times."""
 
-    from vehiclemodelvisualodometry_b200 import (DrivePipeline, DriveSet, _lib, grid_search, plan_windows)
-    from vehiclemodelvisualodometry_b200 import build as vbuild
-    from vehiclemodelvisualodometry_b200.synthetic import synthetic_drives
+    def __init__(self, dev, world):
+        import torch
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus and world > 1:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a B200: no CUDA device visible (there is no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    if rank == 0 and vbuild.is_stale():
-        vbuild.build_library()
-    if world > 1:
-        dist.barrier()
-    ctx = _lib.context(local_rank)
+        self.dev, self.world = dev, world
+        self.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # 2x the 126 MB L2
 
-    n_frames, cfg = make_cfg(args.workload)
-    batch = synthetic_drives(1, n_frames, seed=BASE_SEED + rank)
-    time_h, vo_h, gps_h, imu_h = batch.drive(0)
-    drives = DriveSet.from_arrays([time_h], [batch.dt], vo=[vo_h], device=dev)
-    plan = plan_windows(cfg, drives)
-    n_win = plan.n_windows
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # 2x the 126 MB L2
-    # The only exchange of the path is the per-window records.  Preferred: fused into the search --
-    # every rank's gather buffer is mapped into its peers (CUDA IPC) and the kernel's epilogue
-    # stores each record into all of them over NVLink (scheduler.PeerGather); no second kernel has
-    # to squeeze in beside the persistent search, which owns every SM.  Fallback: an NCCL
-    # all-gather of the record buffer, overlapped with the next pass' search.  Two buffer sets
-    # either way, so that step s + 1 never overwrites records of step s in flight.
-    n_buf = 2 if world > 1 else 1
-    peer = None
-    gather_kind = "none (one GPU)"
-    if world > 1 and not os.environ.get("VMVO_BENCH_GATHER", "").lower().startswith("nccl"):
-        try:
-            from vehiclemodelvisualodometry_b200.scheduler import PeerGather
+    def sync(self):
+        import torch
+        import torch.distributed as dist
 
-            peer = [PeerGather(n_win, dev) for _ in range(n_buf)]
-            gather_kind = "fused: records stored into every peer's buffer by the search kernel (CUDA IPC, NVLink)"
-        except Exception as exc:       # no peer access on this box: use the collective
-            peer = None
-            print(f"[bench] peer buffers unavailable ({exc}); using the NCCL all-gather", file=sys.stderr)
-    ok = torch.tensor([1 if (peer is not None or world == 1) else 0], device=dev)
-    if world > 1:
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)          # all ranks take the same path
-        if int(ok.item()) == 0 and peer is not None:
-            for pg in peer:
-                pg.close()
-            peer = None
-    if peer is not None:
-        gathered = [pg.buffer for pg in peer]
-        local = [pg.local for pg in peer]
-        pipes = []
-        for b in range(n_buf):
-            peer[b].enable()           # the graph captures the mirrors in force
-            pipes.append(DrivePipeline(cfg, drives, blend_gps=False, records=local[b]))
-            peer[b].disable()
-    else:
-        if world > 1:
-            gather_kind = "NCCL all_gather_into_tensor, overlapped with the next search"
-        gathered = [torch.empty((world * n_win, 64), dtype=torch.uint8, device=dev) for _ in range(n_buf)]
-        local = [g[rank * n_win:(rank + 1) * n_win] for g in gathered]
-        # the public batched API: plan + search + write-back captured once as CUDA graphs
-        pipes = [DrivePipeline(cfg, drives, blend_gps=False, records=local[b], split=world > 1)
-                 for b in range(n_buf)]
-    pipe = pipes[0]
-    state = {"n": 0, "work": None}
-
-    def step():
-        if world == 1:
-            return pipe.run()
-        b = state["n"] & 1
-        state["n"] += 1
-        if peer is not None:
-            return pipes[b].run()          # the records reach every rank from inside the search
-        pipes[b].run_search()
-        if state["work"] is not None:      # the previous pass's gather had this search to hide behind
-            state["work"].wait()
-        # the only exchange of the path: per-window records to every rank, on NCCL's stream,
-        # while the write-back (which needs the local records only) and the next search proceed
-        state["work"] = dist.all_gather_into_tensor(gathered[b], local[b], async_op=True)
-        traj = pipes[b].run_write_back()
-        return local[b], traj
-
-    def drain():
-        if state["work"] is not None:
-            state["work"].wait()
-            state["work"] = None
-
-    def timed(fn, k, w, drain=drain):
-        for _ in range(w):
-            flush.zero_()
-            fn()
-        drain()
-        torch.cuda.synchronize()
-        if world > 1:
+        torch.cuda.synchronize(self.dev)
+        if self.world > 1:
             dist.barrier()
-        torch.cuda.synchronize()
+        torch.cuda.synchronize(self.dev)
+
+    def __call__(self, fn, k, w, drain=None, collective=True):
+        import torch
+        import torch.distributed as dist
+
+        for _ in range(w):
+            self.flush.zero_()
+            fn()
+        if drain:
+            drain()
+        self.sync() if collective else torch.cuda.synchronize(self.dev)
         evs = []
         for _ in range(k):
-            flush.zero_()  # evict the pose stream and the records from L2 between steps
+            self.flush.zero_()  # evict the pose stream and the records from L2 between steps
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             fn()
             b.record()
             evs.append((a, b))
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        drain()          # the last gather completes inside the timed total
-        b.record()
-        evs.append((a, b))
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        if drain:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            drain()          # e.g. the last step's device-to-host copy completes inside the timed total
+            b.record()
+            evs.append((a, b))
+        self.sync() if collective else torch.cuda.synchronize(self.dev)
         ms = sum(a.elapsed_time(b) for a, b in evs)
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if self.world > 1 and collective:
+            t = torch.tensor([ms], dtype=torch.float64, device=self.dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         return ms
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    total_ms = timed(step, args.steps, args.warmup)
-    # graph replays do not pass through the library's launch counter: count the captured kernels
-    launches = DrivePipeline.KERNELS_PER_PASS * args.steps
+
+def records_equal(a, b):
+    """Byte equality of two record buffers except n_rescored (a run-to-run diagnostic)."""
+    import torch
+
+    x, y = a.reshape(-1, 64).clone(), b.reshape(-1, 64).clone()
+    x[:, 12:16] = 0
+    y[:, 12:16] = 0
+    return bool(torch.equal(x, y))
+
+
+# ---- one workload through the pipeline ---------------------------------------------------------
+def pooled_drives(workload, world, dev, seed0=BASE_SEED):
+    from vehiclemodelvisualodometry_b200 import DriveSet
+    from vehiclemodelvisualodometry_b200.synthetic import synthetic_drives
+
+    n_frames, cfg = make_cfg(workload)
+    t, vo, dt = [], [], []
+    for d in range(world):
+        b = synthetic_drives(1, n_frames, seed=seed0 + d)
+        th, voh, _, _ = b.drive(0)
+        t.append(th)
+        vo.append(voh)
+        dt.append(b.dt)
+    return n_frames, cfg, DriveSet.from_arrays(t, dt, vo=vo, device=dev), np.concatenate(t), np.concatenate(vo)
+
+
+def measure_workload(workload, dev, world, rank, timer, steps, warmup, seed0=BASE_SEED):
+    """Device-resident step time, search-kernel time, end-to-end (pipelined and serial) for one
+    workload; at world > 1 through the window scheduler and the fused exchange."""
+    import torch
+
+    from vehiclemodelvisualodometry_b200 import DrivePipeline, DriveStream, _lib, grid_search
+    from vehiclemodelvisualodometry_b200.scheduler import PeerGather, shard_range
+
+    n_frames, cfg, drives, time_h, vo_h = pooled_drives(workload, world, dev, seed0)
+    F = drives.n_frames
+    n_win = world * cfg.window_count(n_frames)
+    frame_range = shard_range(F, world, rank) if world > 1 else None
+    record_range = shard_range(n_win, world, rank) if world > 1 else None
+    sets = []
+
+    def make_pipe(d, b_unused=None):
+        if world == 1:
+            return DrivePipeline(cfg, d, blend_gps=False)
+        g = PeerGather(n_win, dev, block=DEAL_BLOCK)
+        sets.append(g)
+        return DrivePipeline(cfg, d, blend_gps=False, gather=g, frame_range=frame_range,
+                             record_range=record_range)
+
+    # two buffer sets used alternately at N > 1 (what makes the flag exchange race-free)
+    pipes = [make_pipe(drives) for _ in range(2 if world > 1 else 1)]
+    state = {"n": 0}
+
+    def step():
+        p = pipes[state["n"] % len(pipes)]
+        state["n"] += 1
+        return p.run()
+
+    total_ms = timer(step, steps, warmup)
+    ms_per_step = total_ms / steps
     step()
-    drain()
-    torch.cuda.synchronize()
-    rec = pipe.result_records()
-    if world > 1:
-        # what arrived: every rank's slot of this rank's gather buffer against that rank's own records
-        torch.cuda.synchronize()
-        dist.barrier()
-        last = (state["n"] - 1) & 1
-        check = torch.empty((world * n_win, 64), dtype=torch.uint8, device=dev)
-        dist.all_gather_into_tensor(check, local[last].contiguous())
-        torch.cuda.synchronize()
-        if not torch.equal(check, gathered[last]):
-            raise SystemExit(f"rank {rank}: gathered records differ from the ranks' own ({gather_kind})")
+    torch.cuda.synchronize(dev)
+    last = pipes[(state["n"] - 1) % len(pipes)]
+    rec = last.result_records()
     hsteps = int(cfg.grid_v) * int(cfg.grid_s) * int(rec["n_steps"].astype(np.int64).sum())
-    ms_per_step = total_ms / args.steps
-    value = hsteps * world / (ms_per_step * 1e-3)
+    out = {"workload": workload, "cfg": cfg, "n_frames": n_frames, "n_win": n_win, "hsteps": hsteps,
+           "ms_per_step": ms_per_step, "value": hsteps / (ms_per_step * 1e-3),
+           "rescored_per_window": float(rec["n_rescored"].mean()),
+           "launches_per_step": DrivePipeline.KERNELS_PER_PASS}
 
-    # search kernel alone (the dominant kernel): average launch duration for the roofline
-    kern_ms = timed(lambda: grid_search(cfg, drives, plan, out=local[0]), args.steps, 2) / args.steps
+    # the search alone on one GPU over the same windows: kernel time for the roofline, and (N > 1)
+    # what every rank's gathered buffer must hold
+    alone = torch.empty((n_win, 64), dtype=torch.uint8, device=dev)
+    grid_search(cfg, drives, last.plan, out=alone)
+    torch.cuda.synchronize(dev)
+    only = torch.cuda.CUDAGraph()            # the search launches alone (memset, search, deferred
+    with torch.cuda.graph(only):             # re-scores), replayed: no host time between the events
+        grid_search(cfg, drives, last.plan, out=alone)
+    kk = max(3, min(steps, 50))
+    kern_ms = timer(only.replay, kk, 2, collective=False) / kk
+    out["kernel_ms_all_windows_one_gpu"] = kern_ms
+    if world > 1:
+        torch.cuda.synchronize(dev)
+        if not records_equal(alone, last.records):
+            raise SystemExit(f"rank {rank}: the gathered records differ from a one-GPU search of the pool")
+        bad = [g.timed_out() for g in sets]
+        if any(bad):
+            raise SystemExit(f"rank {rank}: an arrival wait timed out ({bad})")
+        out["exchange"] = ("fused: block-cyclic deal (block %d), records stored into every peer's gather "
+                           "buffer by the search kernel (CUDA IPC, NVLink), arrival words published and "
+                           "awaited by the write-back kernel; verified against a one-GPU search of all "
+                           "%d windows on every rank" % (DEAL_BLOCK, n_win))
+    else:
+        out["exchange"] = "none (one GPU)"
 
-    # end to end through the public API with HOST buffers: H2D of the pose stream and stamps,
-    # plan + search + write-back, D2H of the records and the written-back trajectory
+    # end to end through the public API with HOST buffers: H2D of the pose streams and stamps,
+    # plan + search + write-back, D2H of this rank's records and frames
     vo_pin = torch.from_numpy(np.ascontiguousarray(vo_h)).pin_memory()
     t_pin = torch.from_numpy(np.ascontiguousarray(time_h)).pin_memory()
-    rec_pin = torch.empty((n_win, 64), dtype=torch.uint8).pin_memory()
-    traj_pin = torch.empty((4, n_frames), dtype=torch.float64).pin_memory()
+    inputs = {"vo": vo_pin, "time": t_pin}
+    stream = DriveStream(cfg, drives, blend_gps=False, pipe_factory=lambda b, d: make_pipe(d))
+    stream.prime(inputs)
+    torch.cuda.synchronize(dev)
+    e2e_ms = timer(lambda: stream.step(inputs), steps, warmup,
+                   drain=lambda: stream.drain() if stream.n > 0 else None) / steps
+    torch.cuda.synchronize(dev)
+    rlo, rhi = record_range or (0, n_win)
+    chk = stream.host[(stream.n - 1) & 1][0].numpy().view(_lib.RESULT_DTYPE).reshape(-1)
+    assert np.array_equal(chk["best_idx"], rec["best_idx"][rlo:rhi]), "e2e records differ"
+    h2d = int(vo_pin.numel() * 4 + t_pin.numel() * 8)
+    d2h = stream.d2h_bytes()
+    out["e2e"] = {"value": hsteps / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                  "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                  "schedule": "streaming API (DriveStream), pipelined across steps on three streams: each "
+                              "timed interval = H2D(step s+1) || plan + search + write-back(step s)"
+                              + (" with the fused exchange" if world > 1 else "") +
+                              " || D2H(step s-1), joined before the interval ends"}
 
-    def e2e_step():
-        drives.vo.copy_(vo_pin, non_blocking=True)
-        drives.time.copy_(t_pin, non_blocking=True)
-        records, traj = step()
-        rec_pin.copy_(records, non_blocking=True)
-        traj_pin.copy_(traj, non_blocking=True)
+    # the same, one call at a time on one stream: H2D, compute, D2H strictly in sequence (the two
+    # buffer sets still alternate: at N > 1 that is what keeps the exchange race-free)
+    ser = {"n": 0}
 
-    e2e_note = "serial per step: H2D, plan + search + write-back (+ gather), D2H on one stream"
-    stream = None
-    if world == 1 or peer is not None:
-        # software-pipelined across steps, as a caller streaming drives through the API would run
-        # it: two resident drive buffers; the timed interval of step s carries the H2D of step
-        # s + 1's inputs, the compute of step s and the D2H of step s - 1's results, on three
-        # streams that all start at the interval's first event and are joined before its last one
-        # (so every interval pays for one full H2D and one full D2H; the L2 flush between
-        # intervals runs with all streams idle).  The last step's D2H is timed by the drain.
-        from vehiclemodelvisualodometry_b200 import DriveStream
+    def serial_step():
+        b = ser["n"] & 1
+        ser["n"] += 1
+        stream._h2d(b, inputs)
+        stream.pipes[b].run()
+        stream._d2h(b)
 
-        factory = None
-        if peer is not None:
-            # N > 1: the stream's two pipelines write their records into the two gather buffers, with
-            # the result mirrors in force while their graphs are captured (the fused gather)
-            def factory(b, d):
-                peer[b].enable()
-                try:
-                    return DrivePipeline(cfg, d, blend_gps=False, records=local[b])
-                finally:
-                    peer[b].disable()
-
-        stream = DriveStream(cfg, drives, blend_gps=False, pipe_factory=factory)   # the public streaming API
-        inputs = {"vo": vo_pin, "time": t_pin}
-        stream.prime(inputs)                                     # inputs of the very first step
-        torch.cuda.synchronize(dev)
-
-        def e2e_step():  # noqa: F811
-            stream.step(inputs)
-
-        def e2e_drain():
-            if stream.n > 0:
-                stream.drain()
-            drain()
-
-        e2e_ms = timed(e2e_step, args.steps, args.warmup, drain=e2e_drain) / args.steps
-        e2e_note = ("pipelined across steps on three streams: each timed interval = H2D(step s+1) || "
-                    "plan + search + write-back(step s)" + (" with the fused gather" if peer is not None else "") +
-                    " || D2H(step s-1), joined before the interval ends")
-        torch.cuda.synchronize(dev)
-        chk = stream.host[(stream.n - 1) & 1][0].numpy().view(_lib.RESULT_DTYPE).reshape(-1)
-        assert np.array_equal(chk["best_idx"], pipe.result_records()["best_idx"]), "e2e records differ"
-    else:
-        e2e_ms = timed(e2e_step, args.steps, args.warmup) / args.steps
-    extras = {}
-    if rank == 0 and world == 1 and not args.no_extras:
-        extras["dense_grid"] = dense_grid(ctx, dev, timed, args)
-        extras["prep"] = prep_rows(ctx, dev, timed)
-        extras["formats"] = formats_rows(ctx, dev, timed)
-    clocks = sampler.stop() if rank == 0 else None
-
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32 scan + f64 re-score",
-        "data": "synthetic (urban stop-and-go drives shaped like BDD sequences, seeds base+rank)",
-        "config": {"workload": args.workload, "frames_per_drive": n_frames, "drives_per_gpu": 1,
-                   "grid": [cfg.grid_v, cfg.grid_s], "window_steps": cfg.window_frames,
-                   "windows_per_gpu": n_win, "hypothesis_steps_per_gpu": hsteps,
-                   "cache": "256 MiB L2 flush between timed steps", "base_seed": BASE_SEED},
-        "windows_per_s": n_win * world / (ms_per_step * 1e-3),
-        "gather": gather_kind,
-        "gpu_launches": int(launches),
-        "e2e": {"value": hsteps * world / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": int(vo_pin.numel() * 4 + t_pin.numel() * 8),
-                "d2h_bytes_per_step": int(rec_pin.numel() + traj_pin.numel() * 8),
-                "schedule": e2e_note},
-        "clocks": clocks,
-        "rescored_per_window": float(rec["n_rescored"].mean()),
-    }
-
-    if rank == 0:
-        line["roofline"] = roofline(ctx, dev, hsteps, kern_ms, n_frames, n_win, clocks, args, cfg)
-        line.update(extras)
-        if world == 1 and not args.no_extras:
-            line["cpu_baseline"] = cpu_baseline(args.workload, budget_s=12.0)
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        if peer is not None:
-            del pipes, pipe, stream
-            for pg in peer:
-                pg.close()
-        dist.destroy_process_group()
+    ser_ms = timer(serial_step, steps, warmup) / steps
+    out["e2e_serial"] = {"value": hsteps / (ser_ms * 1e-3), "unit": UNIT, "ms_per_step": ser_ms,
+                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                         "schedule": "one call at a time, one stream: H2D -> plan + search + write-back -> D2H"}
+    out["_keep"] = (pipes, stream, sets, only)       # closed by the caller after the last collective
+    return out
 
 
+def close_sets(res):
+    pipes, stream, sets, only = res.pop("_keep")
+    del pipes, stream, only
+    for g in sets:
+        g.close()
+
+
+# ---- roofline --------------------------------------------------------------------------------
 def probe_peak(ctx, dev, kind, ops_per_iter):
     """Measured issue peak of one pipe: ops/s over the whole chip."""
     import torch
@@ -409,59 +378,164 @@ def probe_peak(ctx, dev, kind, ops_per_iter):
     return blocks * threads * iters * ops_per_iter / (best * 1e-3)
 
 
-def roofline(ctx, dev, hsteps, kern_ms, n_frames, n_win, clocks, args, cfg):
+_PEAKS = {}
+
+
+def pipe_peaks(ctx, dev):
+    """MUFU / FFMA / DFMA lane-operations per second, measured live once per process."""
+    if not _PEAKS:
+        _PEAKS.update(mufu=probe_peak(ctx, dev, 0, 16), ffma=probe_peak(ctx, dev, 1, 16),
+                      dfma=probe_peak(ctx, dev, 2, 8))
+    return _PEAKS
+
+
+def roofline(ctx, dev, res, clocks, extras=True):
+    """What binds the search kernel: FP32 issue (the FMA pipe).  ``frac`` = FP32-pipe lane-operations
+    the kernel EXECUTES per launch (from the committed ncu instruction counts of this workload,
+    profiles/kernel_counts_r02.json; a packed FFMA2 / FADD2 / FMUL2 counts as two) divided by the
+    kernel's launch time and by the FFMA lane-operation rate measured live.  Beside it: the same
+    with each opcode weighted by its measured issue cost on the FMA pipe (``frac_pipe_time``), the
+    algorithmic FP32 figure (25 flops per hypothesis-step), and both SFU figures."""
     import torch
 
     from vehiclemodelvisualodometry_b200.search import executed_mufu_per_hypothesis_step
 
-    EXEC_MUFU_PER_HSTEP = executed_mufu_per_hypothesis_step(cfg)
-
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
+    cfg, hsteps, kern_ms = res["cfg"], res["hsteps"], res["kernel_ms_all_windows_one_gpu"]
+    peaks = load_json("MEASURED_PEAKS.json")
+    counts = load_json("profiles", "kernel_counts_r02.json").get(res["workload"], {})
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     sm_max = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
-    nominal_mufu = sms * 16 * sm_max * 1e6
-    out = {"bound": "sfu", "kernel": "vmvo_window_search_kernel", "unit": "GMUFU-op/s",
-           "kernel_ms_per_launch": kern_ms,
+    nominal_fp32 = sms * 128 * sm_max * 1e6          # FP32 lane-operations per second
+    sec = kern_ms * 1e-3
+    out = {"bound": "fp32", "kernel": "vmvo_window_search_kernel (+ vmvo_deferred_rescore_kernel)",
+           "unit": "G FP32 lane-op/s", "kernel_ms_per_launch": kern_ms,
+           "algorithmic_flop_per_hypothesis_step": FLOP_PER_HSTEP,
            "algorithmic_mufu_per_hypothesis_step": MUFU_PER_HSTEP,
-           "executed_mufu_per_hypothesis_step": EXEC_MUFU_PER_HSTEP}
-    achieved = hsteps * MUFU_PER_HSTEP / (kern_ms * 1e-3)
-    out["achieved"] = achieved / 1e9
-    out["peak_nominal"] = nominal_mufu / 1e9
-    if not args.no_extras:
-        mufu = probe_peak(ctx, dev, 0, 16)
-        ffma = probe_peak(ctx, dev, 1, 16)
-        dfma = probe_peak(ctx, dev, 2, 8)
-        out["peak"] = mufu / 1e9
-        out["peak_source"] = "measured live: vmvo_peak_probe MUFU.SIN/COS issue rate, whole chip"
+           "executed_mufu_per_hypothesis_step": executed_mufu_per_hypothesis_step(cfg)}
+    if extras:
+        pk = pipe_peaks(ctx, dev)
+        ffma, mufu = pk["ffma"], pk["mufu"]
+        out["peak_source"] = ("measured live: vmvo_peak_probe FFMA issue rate over the whole chip "
+                              "(MEASURED_PEAKS.json holds only HBM and bf16 figures)")
         out["fp32_tflops_measured"] = 2 * ffma / 1e12
-        out["fp64_tflops_measured"] = 2 * dfma / 1e12
-        out["fp32_frac_algorithmic"] = hsteps * FLOP_PER_HSTEP / (kern_ms * 1e-3) / (2 * ffma)
+        out["fp64_tflops_measured"] = 2 * pk["dfma"] / 1e12
+        out["mufu_gops_measured"] = mufu / 1e9
     else:
-        out["peak"] = nominal_mufu / 1e9
-        out["peak_source"] = "nominal: SMs x 16 MUFU lanes x max SM clock"
-    out["frac"] = out["achieved"] / out["peak"]
-    out["frac_executed"] = out["frac"] * EXEC_MUFU_PER_HSTEP / MUFU_PER_HSTEP
+        ffma, mufu = nominal_fp32, sms * 16 * sm_max * 1e6
+        out["peak_source"] = "nominal: SMs x 128 FP32 lanes (16 MUFU lanes) x max SM clock"
+    out["peak"] = ffma / 1e9
+    out["peak_nominal"] = nominal_fp32 / 1e9
+    out["frac_algorithmic_fp32"] = hsteps * FLOP_PER_HSTEP / sec / (2 * ffma)
+    out["sfu_frac_algorithmic"] = hsteps * MUFU_PER_HSTEP / sec / mufu
+    out["sfu_frac_executed"] = hsteps * out["executed_mufu_per_hypothesis_step"] / sec / mufu
+    if counts:
+        lane_ops = counts["fp32_lane_ops_per_hypothesis_step"] * hsteps
+        out["executed_fp32_lane_ops_per_hypothesis_step"] = counts["fp32_lane_ops_per_hypothesis_step"]
+        out["achieved"] = lane_ops / sec / 1e9
+        out["frac"] = lane_ops / sec / ffma
+        out["frac_pipe_time"] = counts["fma_pipe_clk_per_hypothesis_step"] * hsteps / 32 / sec / (sms * 4 * sm_max * 1e6)
+        out["counts_source"] = counts.get("source")
+    else:
+        out["achieved"] = hsteps * FLOP_PER_HSTEP / 2 / sec / 1e9
+        out["frac"] = out["frac_algorithmic_fp32"]
+        out["counts_source"] = "no ncu counts committed for this workload: frac is the algorithmic figure"
     # HBM side, for the record: one read of the pose stream + one 64-byte record per window
-    algo_bytes = n_frames * 16 + n_win * (64 + 16)
+    algo_bytes = res["n_frames"] * 16 * max(1, res["n_win"] // max(1, cfg.window_count(res["n_frames"]))) \
+        + res["n_win"] * (64 + 16)
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    out["hbm"] = {"algorithmic_bytes_per_launch": algo_bytes,
-                  "achieved_gbs": algo_bytes / (kern_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
-                  "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback",
-                  "frac": algo_bytes / (kern_ms * 1e-3) / 1e9 / hbm_peak}
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
-    except Exception:
-        pass
-    out["traffic"] = traffic
+    out["hbm"] = {"algorithmic_bytes_per_launch": algo_bytes, "achieved_gbs": algo_bytes / sec / 1e9,
+                  "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback",
+                  "frac": algo_bytes / sec / 1e9 / hbm_peak}
+    out["traffic"] = counts.get("dram_bytes_per_launch") if counts else \
+        load_json("profiles", "traffic.json").get(res["workload"])
     return out
 
 
-def prep_rows(ctx, dev, timed):
+# ---- BASELINE configs[3] / [4]: batches of drives dealt over the ranks ---------------------------
+def batch_config(name, cfg, n_drives, n_frames, dev, world, rank, timer, sensors, note):
+    """One pass over a batch of drives: plan + search of this rank's share of the global window list
+    with the fused exchange + write-back of this rank's frames.  Strong scaling: the batch is fixed,
+    and rank 0 also runs the whole batch alone (the one-GPU time of the same batch)."""
+    import torch
+    import torch.distributed as dist
+
+    from vehiclemodelvisualodometry_b200 import DrivePipeline, DriveSet, grid_search
+    from vehiclemodelvisualodometry_b200.scheduler import PeerGather, shard_range
+    from vehiclemodelvisualodometry_b200.synthetic import synthetic_drives
+
+    b = synthetic_drives(n_drives, n_frames, seed=BASE_SEED + 1000 + n_drives)
+    kw = {"vo": list(b.vo)}
+    if "gps" in sensors:
+        kw["gps"] = list(b.gps)
+    if "imu" in sensors:
+        kw["imu"] = list(b.imu)
+    drives = DriveSet.from_arrays(list(b.time), [b.dt] * n_drives, device=dev, **kw)
+    del b
+    n_win = n_drives * cfg.window_count(n_frames)
+    gather = PeerGather(n_win, dev, block=DEAL_BLOCK) if world > 1 else None
+    pipe = DrivePipeline(cfg, drives, blend_gps="gps" in sensors, gather=gather, use_graph=False,
+                         frame_range=shard_range(drives.n_frames, world, rank) if world > 1 else None)
+    k = 2
+    ms = timer(pipe.run, k, 1) / k
+    torch.cuda.synchronize(dev)
+    rec = pipe.result_records()
+    hsteps = int(cfg.grid_v) * int(cfg.grid_s) * int(rec["n_steps"].astype(np.int64).sum())
+    out = {"workload": name, "drives": n_drives, "frames_per_drive": n_frames,
+           "grid": [cfg.grid_v, cfg.grid_s], "window_steps": cfg.window_frames, "sensors": sensors,
+           "windows": n_win, "hypothesis_steps": hsteps, "ms_per_step": ms,
+           "value": hsteps / (ms * 1e-3), "unit": UNIT, "windows_per_s": n_win / (ms * 1e-3),
+           "rescored_per_window": float(rec["n_rescored"].mean()), "note": note}
+    if world > 1:
+        # the same batch on ONE GPU (rank 0 alone; the others wait), and the gathered records checked
+        alone = torch.empty((n_win, 64), dtype=torch.uint8, device=dev)
+        one_ms = None
+        if rank == 0:
+            one_ms = timer(lambda: grid_search(cfg, drives, pipe.plan, out=alone), 1, 1, collective=False)
+        else:
+            grid_search(cfg, drives, pipe.plan, out=alone)
+        torch.cuda.synchronize(dev)
+        if not records_equal(alone, pipe.records):
+            raise SystemExit(f"rank {rank}: {name}: gathered records differ from a one-GPU search")
+        if gather.timed_out():
+            raise SystemExit(f"rank {rank}: {name}: an arrival wait timed out")
+        t = torch.tensor([one_ms or 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        one_ms = float(t.item())
+        # (the one-GPU figure is the search alone; the N-GPU step also carries plan + write-back)
+        out["one_gpu_search_ms"] = one_ms
+        out["scaling_efficiency_vs_one_gpu_search"] = one_ms / (world * ms)
+        out["records_verified"] = True
+        del pipe
+        gather.close()
+    return out
+
+
+def config45(dev, world, rank, timer):
+    from vehiclemodelvisualodometry_b200 import SearchConfig
+
+    out = {}
+    # BASELINE configs[3]: 512 drives x 6 000 frames, W = 60, 32x32 and 128x128
+    c32 = SearchConfig(grid_v=32, grid_s=32, window_frames=60)
+    out["config4_512_drives_32x32_w60"] = batch_config(
+        "config4_512_drives_6000f_32x32_w60", c32, 512, 6000, dev, world, rank, timer, ["vo"],
+        "BASELINE configs[3] in full: 512 drives x 6 000 frames (3.0e6 windows)")
+    c128 = SearchConfig(grid_v=128, grid_s=128, window_frames=60)
+    out["config4_64_drives_128x128_w60"] = batch_config(
+        "config4_64_of_512_drives_6000f_128x128_w60", c128, 64, 6000, dev, world, rank, timer, ["vo"],
+        "BASELINE configs[3] at 128x128, time-boxed: 64 of the 512 drives (1/8 of the batch; windows are "
+        "independent, so the full batch is 8 passes like this one)")
+    # BASELINE configs[4]: 1 024 drives x 20 000 frames, 128x128, W = 60, VO + GPS + IMU -- time-boxed
+    c5 = SearchConfig(grid_v=128, grid_s=128, window_frames=60, w_vo=1.0, w_gps=0.5, w_imu=40.0)
+    r = batch_config("config5_16_of_1024_drives_20000f_128x128_w60_vo_gps_imu", c5, 16, 20000, dev, world,
+                     rank, timer, ["vo", "gps", "imu"],
+                     "BASELINE configs[4], time-boxed: 16 of the 1 024 drives (1/64 of the batch)")
+    r["full_batch_extrapolated_s"] = r["ms_per_step"] * 64 / 1e3
+    out["config5_fused_vo_gps_imu"] = r
+    return out
+
+
+# ---- next rows (SURVEY 8f) ---------------------------------------------------------------------
+def prep_rows(ctx, dev, timer):
     """VO and GPS pre-processing of 64 drives x 10 000 frames, device resident.
     HBM-bound streaming work; algorithmic bytes per frame: VO 96 in (x, y, 3x3 R, stamp) + 40 out,
     GPS 32 in (lat, lon, speed, stamp) + 40 out."""
@@ -484,24 +558,19 @@ def prep_rows(ctx, dev, timed):
     vo_out = torch.empty((5, F), dtype=torch.float64, device=dev)
     gps_out, status, scratch = gps_prepare_device(off, D, F, lat, lon, speed, stamp)
     k = 5
-    vo_ms = timed(lambda: vo_prepare_device(off, D, F, x, y, rot, stamp, out=vo_out), k, 1) / k
-    gps_ms = timed(lambda: gps_prepare_device(off, D, F, lat, lon, speed, stamp, out=gps_out,
+    vo_ms = timer(lambda: vo_prepare_device(off, D, F, x, y, rot, stamp, out=vo_out), k, 1) / k
+    gps_ms = timer(lambda: gps_prepare_device(off, D, F, lat, lon, speed, stamp, out=gps_out,
                                               scratch=scratch, status=status), k, 1) / k
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm = peaks.get("hbm_gbs", 6650.0)
+    hbm = load_json("MEASURED_PEAKS.json").get("hbm_gbs", 6650.0)
     vo_gbs, gps_gbs = F * 136 / (vo_ms * 1e-3) / 1e9, F * 72 / (gps_ms * 1e-3) / 1e9
     return {"workload": "64 drives x 10000 frames", "vo_ms": vo_ms, "gps_ms": gps_ms,
             "vo_frames_per_s": F / (vo_ms * 1e-3), "gps_frames_per_s": F / (gps_ms * 1e-3),
             "vo_hbm": {"achieved_gbs": vo_gbs, "peak_gbs": hbm, "frac": vo_gbs / hbm},
             "gps_hbm": {"achieved_gbs": gps_gbs, "peak_gbs": hbm, "frac": gps_gbs / hbm},
-            "note": "GPS includes the per-drive sequential path sum and de-duplication scan (one warp per drive)"}
+            "note": "GPS includes the per-drive sequential path sum and de-duplication scan"}
 
 
-def formats_rows(ctx, dev, timed):
+def formats_rows(ctx, dev, timer):
     """the reference's two CSV files of 64 drives x 10 000 rows, bytes resident in HBM
     -> numeric columns (and the 3x3 rot matrices) resident in HBM, through parse_staged (row index,
     field split, number conversion; includes the one host round trip that sizes the outputs).
@@ -530,19 +599,14 @@ def formats_rows(ctx, dev, timed):
     pd.DataFrame({"Timestamp": stamp, "Latitude": lat, "Longitude": lon, "heading": heading,
                   "speed": speed}).to_csv(b1, index=False)
     pd.DataFrame({"x": list(x), "y": list(y), "z": list(x * 0), "rot": [r for r in rot]}).to_csv(b2, index=False)
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm = peaks.get("hbm_gbs", 6650.0)
+    hbm = load_json("MEASURED_PEAKS.json").get("hbm_gbs", 6650.0)
     out = {"workload": f"{D} drives x {n} rows per file"}
     for name, text, cols, rc, sc in (("log", b1.getvalue(), LOG_COLUMNS, None, "Timestamp"),
                                      ("cache", b2.getvalue(), CACHE_COLUMNS, "rot", None)):
         blob = text.encode()
         st = stage_csv_files([blob] * D, dev)
         k = 5
-        ms = timed(lambda: parse_staged(st, cols, rc, sc), k, 2) / k
+        ms = timer(lambda: parse_staged(st, cols, rc, sc), k, 2) / k
         written = D * n * 8 * (len(cols) + (9 if rc else 0))
         gbs = (st.n_bytes + written) / (ms * 1e-3) / 1e9
         t0 = time.perf_counter()
@@ -559,30 +623,114 @@ def formats_rows(ctx, dev, timed):
     return out
 
 
-def dense_grid(ctx, dev, timed, args):
-    """BASELINE configs[2]: 256x256 grid, 60-step windows, 4096 windows (1.6e10 hyp-steps)."""
+def facade_latency(dev):
+    """BicycleModel.run through the reference-shaped facade (one H2D + launch + D2H per call) beside
+    the reference's own 15 us per call (vmvo/bicycle_model.py:40-78)."""
+    from vehiclemodelvisualodometry_b200 import BicycleModel, State
+
+    m = BicycleModel(state=State(x=0.0, y=0.0, theta=0.0, velocity=5.0, steering_angle=0.0))
+    for _ in range(20):
+        m.run(10.0, 5.0, 0.05)
+    n = 200
+    t0 = time.perf_counter()
+    for _ in range(n):
+        m.run(10.0, 5.0, 0.05)
+    one = (time.perf_counter() - t0) / n * 1e6
+    m.set_state(State(x=0.0, y=0.0, theta=0.0, velocity=5.0, steering_angle=0.0))
+    t0 = time.perf_counter()
+    for _ in range(20):
+        m.set_state(State(x=0.0, y=0.0, theta=0.0, velocity=5.0, steering_angle=0.0))
+        m.run_sequence([10.0] * 60, [5.0] * 60, 0.05)
+    seq = (time.perf_counter() - t0) / 20 / 60 * 1e6
+    return {"bicycle_model_run_us_per_call": one, "run_sequence_60_us_per_step": seq,
+            "reference_python_us_per_call": 15.0,
+            "note": "the scalar facade pays one H2D + launch + D2H per call; scalar callers are not what the "
+                    "GPU path is for (the batched rollout_batch / grid search are)"}
+
+
+# ---- the B200 arm ---------------------------------------------------------------------------------
+def run_b200(args):
     import torch
+    import torch.distributed as dist
 
-    from vehiclemodelvisualodometry_b200 import DriveSet, grid_search, plan_windows
-    from vehiclemodelvisualodometry_b200.synthetic import synthetic_drives
-
-    name = "config3_dense_256x256_w60"
-    n_frames, cfg = make_cfg(name)
-    batch = synthetic_drives(1, n_frames, seed=BASE_SEED + 3)
-    t, vo, _, _ = batch.drive(0)
-    drives = DriveSet.from_arrays([t], [batch.dt], vo=[vo], device=dev)
-    plan = plan_windows(cfg, drives)
-    out = torch.empty((plan.n_windows, 64), dtype=torch.uint8, device=dev)
-    k = 3
-    ms = timed(lambda: grid_search(cfg, drives, plan, out=out), k, 1) / k
     from vehiclemodelvisualodometry_b200 import _lib
+    from vehiclemodelvisualodometry_b200 import build as vbuild
 
-    rec = out.cpu().numpy().view(_lib.RESULT_DTYPE).reshape(-1)
-    hsteps = cfg.grid_v * cfg.grid_s * int(rec["n_steps"].astype(np.int64).sum())
-    return {"workload": name, "windows": plan.n_windows, "hypothesis_steps": hsteps, "kernel_ms": ms,
-            "value": hsteps / (ms * 1e-3), "unit": UNIT,
-            "achieved_gmufu": hsteps * MUFU_PER_HSTEP / (ms * 1e-3) / 1e9,
-            "rescored_per_window": float(rec["n_rescored"].mean())}
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: no CUDA device visible (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0 and vbuild.is_stale():
+        vbuild.build_library()
+    if world > 1:
+        dist.barrier()
+    ctx = _lib.context(local_rank)
+    timer = Timer(dev, world)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    res = measure_workload(args.workload, dev, world, rank, timer, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    cfg, n_frames = res["cfg"], res["n_frames"]
+
+    extras = {}
+    if not args.no_extras:
+        if world == 1:
+            other = [w for w in sorted(WORKLOADS) if w != args.workload]
+            for w in other:                      # the other single-GPU config as a first-class object
+                r2 = measure_workload(w, dev, 1, 0, timer, 3 if "config3" in w else 20, 2)
+                key = "config3" if "config3" in w else "config2"
+                obj = {k: r2[k] for k in ("workload", "n_win", "hsteps", "ms_per_step", "value",
+                                          "rescored_per_window", "e2e", "e2e_serial")}
+                obj.update(unit=UNIT, windows_per_s=r2["n_win"] / (r2["ms_per_step"] * 1e-3),
+                           config=config_of(w, r2["n_frames"], r2["cfg"]),
+                           roofline=roofline(ctx, dev, r2, clocks),
+                           cpu_baseline=cpu_baseline(w, budget_s=8.0))
+                close_sets(r2)
+                extras[key] = obj
+            extras["prep"] = prep_rows(ctx, dev, timer)
+            extras["formats"] = formats_rows(ctx, dev, timer)
+            extras["facade"] = facade_latency(dev)
+        extras.update(config45(dev, world, rank, timer))
+
+    line = {
+        "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 scan + f64 re-score",
+        "data": "synthetic (urban stop-and-go drives shaped like BDD sequences, seeds base + drive)",
+        "config": config_of(args.workload, n_frames, cfg, world),
+        "windows_per_s": res["n_win"] / (res["ms_per_step"] * 1e-3),
+        "exchange": res["exchange"],
+        "gpu_launches": int(res["launches_per_step"] * args.steps),
+        "e2e": res["e2e"], "e2e_serial": res["e2e_serial"],
+        "clocks": clocks,
+        "rescored_per_window": res["rescored_per_window"],
+    }
+    if rank == 0:
+        line["roofline"] = roofline(ctx, dev, res, clocks, extras=not args.no_extras)
+        line.update(extras)
+        if world == 1 and not args.no_extras:
+            line["cpu_baseline"] = cpu_baseline(args.workload, budget_s=12.0)
+            try:
+                pk = pipe_peaks(ctx, dev)
+                line["peaks_probe"] = {"mufu_gops": pk["mufu"] / 1e9, "ffma_glaneops": pk["ffma"] / 1e9,
+                                       "dfma_glaneops": pk["dfma"] / 1e9}
+            except Exception:
+                pass
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+    close_sets(res)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 # ---- CPU legs -------------------------------------------------------------------------------------
@@ -614,24 +762,46 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
+def reference_python():
+    """The unmodified Python reference, timed in the BUILD CONTAINER by oracle/time_reference_cpu.py
+    (it cannot travel to the GPU box); the committed numbers ride along, labelled."""
+    d = load_json("profiles", "reference_cpu_r02.json")
+    if not d:
+        return None
+    g, s = d.get("grid_through_bicycle_model_run", {}), d.get("slsqp_as_is", {})
+    return {"where": d.get("where"), "cores": d.get("host_cores"), "drive": d.get("drive"),
+            "grid_through_BicycleModel_run_hypothesis_steps_per_s": g.get("hypothesis_steps_per_s"),
+            "grid_through_BicycleModel_run_hypothesis_steps_per_s_per_core": g.get("hypothesis_steps_per_s_per_core"),
+            "slsqp_as_is_windows_per_s": s.get("windows_per_s"),
+            "slsqp_as_is_model_steps_per_s": s.get("model_steps_per_s"),
+            "source": "profiles/reference_cpu_r02.json (oracle/time_reference_cpu.py)"}
+
+
 def cpu_baseline(workload, budget_s=12.0):
     cores = host_threads()
-    cpu_pass(workload, BASE_SEED, max_windows=256, threads=cores)  # warm the library and the threads
     n_frames, cfg = make_cfg(workload)
     total_win = n_frames - 2 * cfg.window_frames
+    per_win = cfg.grid_v * cfg.grid_s * cfg.window_frames
+    s0, t0, _ = cpu_pass(workload, BASE_SEED, max_windows=64, threads=cores)   # warms library and threads
+    # a pass sized to ~1/3 of the budget, at least 64 windows, at most the whole workload
+    want = int(max(64, min(total_win, (s0 / t0) * (budget_s / 3) / per_win)))
     steps = sec = 0.0
     passes = nwin = 0
     t_end = time.perf_counter() + budget_s
-    while passes < 3 or time.perf_counter() < t_end:
-        s1, t1, nwin = cpu_pass(workload, BASE_SEED, threads=cores)
+    while passes < 2 or time.perf_counter() < t_end:
+        s1, t1, nwin = cpu_pass(workload, BASE_SEED, max_windows=want, threads=cores)
         steps += s1
         sec += t1
         passes += 1
         if passes >= 200:
             break
-    return {"value": steps / sec, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{passes} passes over all {nwin} of {total_win} windows of {workload}; "
-                      f"oracle/vmvo_oracle.c (float64, OpenMP over windows), {sec:.1f} s of search time"}
+    out = {"value": steps / sec, "unit": UNIT, "cores": cores, "kind": "port",
+           "sample": f"{passes} passes over {nwin} of {total_win} windows of {workload}, evenly spaced; "
+                     f"oracle/vmvo_oracle.c (float64, OpenMP over windows), {sec:.1f} s of search time"}
+    rp = reference_python()
+    if rp:
+        out["reference_python"] = rp
+    return out
 
 
 def run_reference(args):
@@ -657,18 +827,23 @@ def run_reference(args):
     value = tot_steps / tot_sec
     sample = (f"{nwin} of {total_win} windows per step, evenly spaced; oracle/vmvo_oracle.c "
               f"(float64, OpenMP over windows)")
+    cb = {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+    rp = reference_python()
+    if rp:
+        cb["reference_python"] = rp
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_sec / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic (same generator and seed as the b200 arm)",
-        "config": {"workload": args.workload, "frames_per_drive": n_frames,
-                   "grid": [cfg.grid_v, cfg.grid_s], "window_steps": cfg.window_frames},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "data": "synthetic (same generator and seeds as the b200 arm)",
+        "config": config_of(args.workload, n_frames, cfg, max(1, args.gpus)),
+        "cpu_baseline": cb,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "the reference is pure Python (15 us per model step, ~6.7e4 steps/s/core, SURVEY.md F8) "
-                "and cannot travel to the GPU box; this arm is its C restatement on all host threads",
+        "note": "this arm is the repo's own C/OpenMP restatement of the path (kind = port) on all host "
+                "threads, NOT the Python reference: the reference is pure Python (~15 us per model step), "
+                "does not exist on the GPU box, and its own numbers (build container) are under "
+                "cpu_baseline.reference_python",
     }
     print(json.dumps(line), flush=True)
 

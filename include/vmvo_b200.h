@@ -12,9 +12,9 @@
  *     caller (e.g. torch.Tensor.data_ptr()); the library allocates nothing persistent
  *     except the opaque vmvo_ctx (work counters, the scratch of deferred windows, error text);
  *   - calls are stream-ordered on the caller's `stream` (a cudaStream_t passed as void*)
- *     and asynchronous; one host thread per ctx.  Searches of one ctx share its deferred-window
- *     scratch: issue them on one stream (or on streams that do not run them at the same time);
- *     for searches that overlap in time use one ctx per stream;
+ *     and asynchronous; one host thread per ctx at a time.  Every search launch owns its scratch
+ *     (queue head, deferred-window slots) until it has completed, so searches of one ctx may
+ *     overlap on different streams; the calling thread's current device is left as it was;
  *   - return value: vmvo_status (0 = ok); vmvo_last_error(ctx) gives the text.
  *   - pose streams are float4 (x [m], y [m], theta [rad], v [m/s]) per frame (double4 in the
  *     _f64 entry points), all drives concatenated; `d_drive_offsets[n_drives + 1]` delimits them; `d_time` is float64 [s].
@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define VMVO_ABI_VERSION 1
+#define VMVO_ABI_VERSION 2
 
 typedef struct vmvo_ctx vmvo_ctx;
 
@@ -49,7 +49,9 @@ enum { VMVO_PRIMARY_VO = 0, VMVO_PRIMARY_GPS = 1 };
 enum {
   VMVO_WIN_EMPTY = 1,     /* fewer than two targets, N == 0  (vmvo/utils/mpc.py:42-43)      */
   VMVO_WIN_NONFINITE = 2, /* NaN/Inf among the window's inputs: argmin degenerates to 0     */
-  VMVO_WIN_TOO_LONG = 4   /* more poses than cfg.max_window_poses: window not searched      */
+  VMVO_WIN_TOO_LONG = 4,  /* more poses than cfg.max_window_poses: window not searched      */
+  VMVO_WIN_NO_FRAMES = 8  /* no pose in the window's extent (set with EMPTY): the reference's
+                             assert "No frames found", vmvo/schema.py:122                    */
 };
 
 /* per-file status bits of vmvo_csv_parse_f64 */
@@ -170,19 +172,56 @@ int vmvo_grid_search_debug_f32(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_
                                const double* d_seeds, vmvo_window_result* d_results,
                                float* d_scan_cost, float* d_scan_err, void* stream);
 
-/* ---- the result gather, fused into the search ---------------------------------
- * The only exchange of the multi-GPU path is the per-window records.  Instead of a collective
- * after the kernel, the search's epilogue can store each record a second, third, ... time:
- * while mirrors are set, record w of every vmvo_grid_search_* call is written to d_results[w]
- * AND to ((vmvo_window_result*)mirrors[q])[mirror_offset + w] for q < n_mirrors.  With mirrors
- * pointing into peer GPUs' gather buffers (mapped through CUDA IPC, below) the records travel
- * over NVLink as plain stores while the kernel is still searching, and no second kernel runs.
- * The stores are visible to the peers once the kernel has completed on this GPU (stream /
- * event / barrier order, as after any kernel).  h_mirrors is a HOST array of device pointers;
- * n_mirrors = 0 clears.  Launch-time state: a CUDA graph captures the mirrors in force.      */
+/* ---- sharding the window list over the GPUs of a box, and the one exchange ------
+ * Windows are independent (optimize_trajectory_v2.py:48-146 is a loop over them), so R ranks share
+ * one GLOBAL window list (the plan of all drives, resident on every rank) with no data-path
+ * collective: the windows are dealt block-cyclically -- window w belongs to rank (w / block) %
+ * world -- and every rank searches its own.  The only exchange is the 64-byte records, and it is
+ * fused into the kernels that produce and consume them:
+ *   - d_results is a gather buffer with one record per GLOBAL window on every rank; the epilogue
+ *     of the search stores record w into its own buffer AND into peer_records[q][w] of every
+ *     peer (buffers mapped through CUDA IPC, below): plain 64-byte stores over NVLink while the
+ *     kernel is still searching;
+ *   - arrival: every sharded search advances the step counter epoch[0] (device memory, so that a
+ *     replayed CUDA graph counts on).  After its last record store a rank PUBLISHES: one
+ *     st.release.sys of the step number into the word it owns in every peer's flag array
+ *     (peer_flags[q]; stream order puts it behind every record store of the step).  A consumer
+ *     WAITS: it spins (ld.acquire.sys) on local_flags[q], q != rank, until each holds the step
+ *     number.  vmvo_exchange_publish / vmvo_exchange_wait are the stand-alone forms;
+ *     vmvo_write_back_range fuses both into the kernel that consumes the records, so the step
+ *     needs no collective, no extra launch and no host barrier.  A wait gives up after ~10 s
+ *     (a dead peer must not hang the GPU) and sets epoch[1] != 0.
+ * Two buffer sets (records + flags + epoch) used alternately make this race-free without any
+ * other synchronisation: a rank starts step s+2 only after its step s+1 wait, i.e. after every
+ * peer has finished reading buffer set s%2.
+ * All pointers are device pointers; the struct itself is host memory, read at launch time.   */
 #define VMVO_MAX_MIRRORS 16
-int vmvo_set_result_mirrors(vmvo_ctx* ctx, int32_t n_mirrors, void* const* h_mirrors,
-                            int64_t mirror_offset);
+typedef struct vmvo_exchange {
+  int32_t world;         /* ranks sharing the window list (1: no sharding, no exchange)           */
+  int32_t rank;
+  int32_t block;         /* windows per block of the deal, a power of two; 0: the call's windows
+                            are all this rank's (contiguous shards: pass offset pointers)        */
+  int32_t n_peers;       /* valid entries below: world - 1, or 0 (no mirrors, no flags)           */
+  void* peer_records[VMVO_MAX_MIRRORS];      /* peers' gather buffers, indexed like d_results     */
+  uint32_t* peer_flags[VMVO_MAX_MIRRORS];    /* the word this rank owns in each peer's flags      */
+  const uint32_t* local_flags;               /* this rank's flag array [world]                    */
+  uint32_t* epoch;                           /* [0] step counter, [1] wait-timeout indicator      */
+} vmvo_exchange;
+
+/* The fused search over this rank's share of the n_windows GLOBAL windows (plan arrays and
+ * d_results cover all of them).  stream_f64 as in vmvo_grid_search_chained; d_seeds (VMVO_SEED_GIVEN)
+ * and d_run_offsets / n_runs (VMVO_SEED_CHAINED: whole runs are dealt, run r to rank r % world) may
+ * be NULL / 0 otherwise.  ex == NULL or ex->world <= 1: every window, no exchange.             */
+int vmvo_grid_search_sharded(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n_windows,
+                             const int64_t* d_win_start, const int32_t* d_win_len,
+                             const int32_t* d_win_drive, const double* d_dt_per_drive,
+                             const void* d_vo, const void* d_gps, const void* d_imu,
+                             int32_t stream_f64, const double* d_seeds, int64_t n_runs,
+                             const int64_t* d_run_offsets, vmvo_window_result* d_results,
+                             const vmvo_exchange* ex, void* stream);
+/* Arrival word of the current step to every peer / wait for every peer's (see above).          */
+int vmvo_exchange_publish(vmvo_ctx* ctx, const vmvo_exchange* ex, void* stream);
+int vmvo_exchange_wait(vmvo_ctx* ctx, const vmvo_exchange* ex, void* stream);
 /* A device buffer other processes of the box can map: cudaMalloc + cudaIpcGetMemHandle.
  * h_handle receives the 64-byte IPC handle (host memory) to send to the peers.               */
 int vmvo_peer_buffer_create(vmvo_ctx* ctx, int64_t bytes, void** d_ptr, uint8_t* h_handle);
@@ -208,6 +247,20 @@ int vmvo_write_back_f64(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int32_t n_dri
                         const double* d_dt_per_drive, const double* d_vo, const double* d_gps,
                         const vmvo_window_result* d_results, double* d_out_x, double* d_out_y,
                         double* d_out_theta, double* d_out_vel, void* stream);
+
+/* The same write-back for frames [frame_lo, frame_hi) only (outputs stay [total_frames]; other
+ * frames are not touched), reading the records of ALL windows from a gather buffer: the consumer of
+ * the sharded search.  stream_f64 selects float4 / double4 pose streams.  With ex != NULL and
+ * ex->n_peers > 0 the kernel first publishes this rank's arrival word and then waits for every
+ * peer's before it reads a record (vmvo_exchange above): the whole exchange rides on the two
+ * kernels of the step.                                                                          */
+int vmvo_write_back_range(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int32_t n_drives,
+                          int64_t total_frames, int64_t frame_lo, int64_t frame_hi,
+                          const int64_t* d_drive_offsets, const int64_t* d_window_offsets,
+                          const double* d_dt_per_drive, const void* d_vo, const void* d_gps,
+                          int32_t stream_f64, const vmvo_window_result* d_results, double* d_out_x,
+                          double* d_out_y, double* d_out_theta, double* d_out_vel,
+                          const vmvo_exchange* ex, void* stream);
 
 /* ---- a1, a2: batched model rollout --------------------------------------------------
  * Replaces BicycleModel.run / run_sequence (vmvo/bicycle_model.py:40-92) for n_seq
@@ -325,6 +378,10 @@ int vmvo_tan_steer_f32(vmvo_ctx* ctx, int64_t n, const float* d_delta, float* d_
  * operations; d_sink receives one float per thread.                                     */
 int vmvo_peak_probe(vmvo_ctx* ctx, int32_t kind, int32_t blocks, int32_t threads,
                     int32_t iters, float* d_sink, void* stream);
+/* Test / tuning hook, NOT part of the product surface: overrides one of the launch heuristics of
+ * this ctx ("team_warps", "fast_scan", "cand_cap", "defer_min", "max_ctas_per_sm"); value < 0
+ * restores the library's own choice.  The environment is never consulted.                      */
+int vmvo_debug_set_tuning(vmvo_ctx* ctx, const char* key, int32_t value);
 /* kernels launched by this ctx since creation (for bench.py's gpu_launches)             */
 int64_t vmvo_launch_count(const vmvo_ctx* ctx);
 

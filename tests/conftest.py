@@ -28,3 +28,21 @@ def cuda_device(built_library):
         pytest.fail("a test marked gpu ran without a CUDA device")
     torch.cuda.set_device(0)
     return torch.device("cuda", 0)
+
+
+@pytest.fixture
+def tuning(cuda_device):
+    """``tuning(key, value)``: the library's test hook (vmvo_debug_set_tuning) on device 0's ctx;
+    every override is back at the library's own choice when the test ends."""
+    from vehiclemodelvisualodometry_b200 import _lib
+
+    ctx = _lib.context(0)
+    used = set()
+
+    def set_(key, value):
+        used.add(key)
+        ctx.set_tuning(key, value)
+
+    yield set_
+    for key in used:
+        ctx.set_tuning(key, -1)

@@ -41,13 +41,13 @@ def test_stationary_vehicle_all_tied_lowest_index_wins(cuda_device):
     assert np.all(rec["n_rescored"] >= 1) and np.all(rec["n_rescored"] <= 4)
 
 
-def test_candidate_list_overflow_is_flushed(cuda_device, monkeypatch):
+def test_candidate_list_overflow_is_flushed(cuda_device, tuning):
     """More candidates than list entries: the list is re-scored and refilled until drained."""
     cfg = SearchConfig(grid_v=32, grid_s=32, window_frames=30)
     batch = synthetic_drives(1, 160, seed=5)
     full = _run(cfg, batch.time[0], batch.dt, batch.vo[0])
     assert full["n_rescored"].max() >= 2
-    monkeypatch.setenv("VMVO_CAND_CAP", "1")
+    tuning("cand_cap", 1)
     rec = _run(cfg, batch.time[0], batch.dt, batch.vo[0])
     ref = oracle_windows(cfg, batch.time[0], batch.dt, batch.vo[0])
     assert_records_match(rec, ref)
@@ -143,6 +143,76 @@ def test_window_longer_than_capacity_is_flagged(cuda_device):
     assert np.all(rec["status"] == 4) and np.all(rec["best_idx"] == -1)
 
 
+def test_window_without_frames_is_flagged_and_raises_like_reference(cuda_device):
+    """A window whose extent holds no pose (unsorted stamps can produce one): status EMPTY | NO_FRAMES,
+    not TOO_LONG, and the facade raises the reference's assert (vmvo/schema.py:122)."""
+    from vehiclemodelvisualodometry_b200 import WindowPlan, _lib
+
+    cfg = SearchConfig(grid_v=4, grid_s=4, window_frames=10)
+    batch = synthetic_drives(1, 40, seed=6)
+    drives = DriveSet.from_arrays([batch.time[0]], [batch.dt], vo=[batch.vo[0]])
+    plan = plan_windows(cfg, drives)
+    assert plan.n_windows == 20
+    lens = plan.win_len.clone()
+    lens[[3, 11]] = 0
+    lens[7] = -5
+    hand = WindowPlan(window_offsets=plan.window_offsets, d_window_offsets=plan.d_window_offsets,
+                      win_start=plan.win_start, win_len=lens, win_drive=plan.win_drive)
+    rec = grid_search(cfg, drives, hand).records()
+    ok = grid_search(cfg, drives, plan).records()
+    none = np.array([3, 7, 11])
+    assert np.all(rec["status"][none] == (_lib.WIN_EMPTY | _lib.WIN_NO_FRAMES))
+    assert np.all(rec["best_idx"][none] == -1) and np.all(rec["n_steps"][none] == 0)
+    rest = np.setdiff1d(np.arange(20), none)
+    for f in ("best_idx", "n_steps", "status", "best_cost"):
+        np.testing.assert_array_equal(rec[f][rest], ok[f][rest])
+
+
+def test_searches_of_one_ctx_overlap_on_two_streams(cuda_device):
+    """Every search launch owns its scratch (queue head, deferred-window slots) until it has
+    completed: two searches of ONE ctx issued on two streams, both with many parked windows, must
+    give the records each gives alone -- launch after launch."""
+    cfg = SearchConfig(grid_v=16, grid_s=32, window_frames=30)
+    rng = np.random.default_rng(17)
+    sets = []
+    for speed in (0.9, 1.2):            # crawling vehicles: near-ties, long candidate lists
+        t, vo = _straight(600, speed)
+        vo[:, :2] += rng.normal(0, 0.05, (600, 2)).astype(np.float32)
+        vo[:, 3] += rng.normal(0, 0.05, 600).astype(np.float32)
+        d = DriveSet.from_arrays([t], [0.05], vo=[vo])
+        sets.append((d, plan_windows(cfg, d)))
+    alone = [grid_search(cfg, d, p).records() for d, p in sets]
+    assert all(a["n_rescored"].max() >= 16 for a in alone)
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    outs = [[], []]
+    for rep in range(12):
+        for q, (d, p) in enumerate(sets):
+            with torch.cuda.stream(streams[q]):
+                outs[q].append(grid_search(cfg, d, p))
+    torch.cuda.synchronize()
+    for q in range(2):
+        for o in outs[q]:
+            r = o.records()
+            for f in ("best_idx", "n_steps", "status", "best_cost", "x1", "y1", "theta1"):
+                np.testing.assert_array_equal(r[f], alone[q][f])
+
+
+def test_entry_points_leave_the_current_device_alone(cuda_device):
+    """An operator called for another device runs there and restores the caller's current device."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two devices")
+    cfg = SearchConfig(grid_v=8, grid_s=8, window_frames=10)
+    batch = synthetic_drives(1, 60, seed=2)
+    torch.cuda.set_device(0)
+    d1 = DriveSet.from_arrays([batch.time[0]], [batch.dt], vo=[batch.vo[0]], device=torch.device("cuda", 1))
+    with torch.cuda.device(1):
+        want = grid_search(cfg, d1, plan_windows(cfg, d1)).records()
+    assert torch.cuda.current_device() == 0
+    ref = oracle_windows(cfg, batch.time[0], batch.dt, batch.vo[0])
+    assert_records_match(want, ref)
+
+
 def test_high_speed_large_heading(cuda_device):
     """30 m/s seed, full lock available: headings of several radians, largest FP32 error band."""
     cfg = SearchConfig(grid_v=16, grid_s=32, window_frames=60)
@@ -160,8 +230,8 @@ def test_high_speed_large_heading(cuda_device):
 
 
 @pytest.mark.parametrize("defer_min", ["0", "1", "3"])
-def test_deferred_windows_give_the_same_records(cuda_device, monkeypatch, defer_min):
-    """Windows with long candidate lists park them for the second kernel (VMVO_DEFER_MIN entries or
+def test_deferred_windows_give_the_same_records(cuda_device, tuning, defer_min):
+    """Windows with long candidate lists park them for the second kernel (tuning hook defer_min entries or
     more; 0 = never, 1 = every window): index, cost and first pose must not depend on which kernel
     did the float64 re-scores.  Slow stretches (near-ties over the steering rates) included."""
     cfg = SearchConfig(grid_v=16, grid_s=32, window_frames=30)
@@ -176,9 +246,9 @@ def test_deferred_windows_give_the_same_records(cuda_device, monkeypatch, defer_
     fast[:, :2] += slow[-1, :2] - fast[0, :2]
     vo = np.concatenate([slow, fast]).astype(np.float32)
     time = np.concatenate([t, t[-1] + 0.05 + np.arange(200) * 0.05])
-    monkeypatch.setenv("VMVO_DEFER_MIN", defer_min)
+    tuning("defer_min", int(defer_min))
     rec = _run(cfg, time, 0.05, vo)
-    monkeypatch.setenv("VMVO_DEFER_MIN", "0")
+    tuning("defer_min", 0)
     base = _run(cfg, time, 0.05, vo)
     assert base["n_rescored"].max() >= 16
     for f in ("best_idx", "n_steps", "status", "best_cost", "x1", "y1", "theta1", "v_seed", "s_seed"):
@@ -187,8 +257,8 @@ def test_deferred_windows_give_the_same_records(cuda_device, monkeypatch, defer_
 
 
 @pytest.mark.parametrize("case", ["w30", "w60_two_rounds", "vo_gps_imu", "ksteer", "many_pass_kernel"])
-def test_every_window_deferred_matches_in_kernel_rescore(cuda_device, monkeypatch, case):
-    """VMVO_DEFER_MIN=1 sends EVERY window's list through vmvo_deferred_rescore_kernel; index, cost and
+def test_every_window_deferred_matches_in_kernel_rescore(cuda_device, tuning, case):
+    """defer_min = 1 sends EVERY window's list through vmvo_deferred_rescore_kernel; index, cost and
     first pose must equal the in-kernel re-score bit for bit, whichever of its three paths a list
     entry takes (warp_cost64, the 16-lane and the 8-lane packed form), with one or two rounds of 32
     steps and with every cost term.  A stop-and-go drive: its optima include rows that stop within
@@ -206,9 +276,9 @@ def test_every_window_deferred_matches_in_kernel_rescore(cuda_device, monkeypatc
     }[case]
     batch = synthetic_drives(1, 1500 if case != "many_pass_kernel" else 700, seed=11)
     t, vo, gps, imu = batch.drive(0)
-    monkeypatch.setenv("VMVO_DEFER_MIN", "1")
+    tuning("defer_min", 1)
     rec = _run(cfg, t, batch.dt, vo, gps, imu)
-    monkeypatch.setenv("VMVO_DEFER_MIN", "0")
+    tuning("defer_min", 0)
     base = _run(cfg, t, batch.dt, vo, gps, imu)
     a = cfg.max_accel * (2 * (base["best_idx"] // cfg.grid_s) - (cfg.grid_v - 1)) / (cfg.grid_v - 1)
     with np.errstate(divide="ignore", invalid="ignore"):

@@ -25,10 +25,10 @@ CASES = {
 
 @pytest.mark.parametrize("scan", ["fast", "generic"])
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_band_contains_float64_cost(cuda_device, name, scan, monkeypatch):
+def test_band_contains_float64_cost(cuda_device, name, scan, tuning):
     """scan = fast: the packed FP32x2 / rotation scan (used when there is no IMU term and
     V_w >= 0); generic: the one-hypothesis-per-lane-slot scan (forced by a test knob)."""
-    monkeypatch.setenv("VMVO_FAST_SCAN", "1" if scan == "fast" else "0")
+    tuning("fast_scan", 1 if scan == "fast" else 0)
     cfg = CASES[name]
     spec = spec_of(cfg)
     n = 2 * cfg.horizon() + 12

@@ -101,10 +101,10 @@ def test_mixed_stream_dtypes_are_rejected(cuda_device):
 
 
 @pytest.mark.parametrize("fast", ["0", "1"])
-def test_both_scan_paths_match_oracle(cuda_device, monkeypatch, fast):
+def test_both_scan_paths_match_oracle(cuda_device, tuning, fast):
     """Both scans (the packed / rotation one is the default on large grids only) on a 32x32 VO
     search."""
-    monkeypatch.setenv("VMVO_FAST_SCAN", fast)
+    tuning("fast_scan", int(fast))
     cfg = SearchConfig(grid_v=32, grid_s=32, window_frames=30)
     batch = synthetic_drives(1, 110, seed=71)
     drives = DriveSet.from_arrays([batch.time[0]], [batch.dt], vo=[batch.vo[0]])
@@ -112,8 +112,8 @@ def test_both_scan_paths_match_oracle(cuda_device, monkeypatch, fast):
     assert_records_match(rec, oracle_windows(cfg, batch.time[0], batch.dt, batch.vo[0]))
 
 
-def test_negative_speed_seed_uses_generic_scan(cuda_device, monkeypatch):
-    monkeypatch.setenv("VMVO_FAST_SCAN", "1")
+def test_negative_speed_seed_uses_generic_scan(cuda_device, tuning):
+    tuning("fast_scan", 1)
     # V_w < 0 (a caller-supplied seed): hypotheses start clamped and move later, so the
     # affine-heading scan does not apply; results must still match
     cfg = SearchConfig(grid_v=16, grid_s=16, window_frames=20, seed_mode="given")

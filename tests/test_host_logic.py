@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol(built_library):
     lib = ctypes.CDLL(built_library)
     for name in declared:
         assert hasattr(lib, name), name
-    assert _lib.load().vmvo_abi_version() == 1
+    assert _lib.load().vmvo_abi_version() == 2
 
 
 def test_struct_layouts_match_the_header():
@@ -112,6 +112,13 @@ got = scheduler.search_sharded(fake_search, n, torch.device("cpu"))
 rec = got.numpy().view(_lib.RESULT_DTYPE).reshape(-1)
 assert rec.shape == (n,) and np.array_equal(rec["best_idx"], want["best_idx"])
 assert np.array_equal(rec["best_cost"], want["best_cost"])
+# the block-cyclic deal with the collective form of the exchange (gather_dealt)
+def fake_dealt(mine, buf):      # stands in for grid_search(..., out=buf, exchange=...)
+    buf[torch.from_numpy(mine)] = torch.from_numpy(want[mine].view(np.uint8).reshape(len(mine), 64))
+for block in (1, 4, 16, 64):
+    got = scheduler.search_dealt(fake_dealt, n, torch.device("cpu"), block=block)
+    rec = got.numpy().view(_lib.RESULT_DTYPE).reshape(-1)
+    assert np.array_equal(rec["best_idx"], want["best_idx"]) and np.array_equal(rec["best_cost"], want["best_cost"])
 dist.destroy_process_group()
 print("rank", sys.argv[1], "ok")
 """
@@ -129,6 +136,77 @@ def test_sharded_search_gathers_over_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_schema_types_behave_like_the_reference():
+    """Trajectory.__len__ / __getitem__ / to_numpy and states_list_to_trajectory of the PRODUCT
+    (vmvo/schema.py:30-57,130-147): against the stamps frozen from the reference (golden B5_times)
+    and, where the reference tree is present, against the reference's own classes."""
+    from oracle import ref_bridge
+    from tests.helpers import load_golden, unhex
+    from vehiclemodelvisualodometry_b200 import State, Trajectory, states_list_to_trajectory
+
+    g = load_golden()
+    states = [State(x=i, y=-0.5 * i, theta=0.1 * i, velocity=1 + i, steering_angle=3 * i) for i in range(7)]
+    tt = states_list_to_trajectory(states, 12.5, 0.05)
+    assert tt.time == unhex(g["schema"]["B5_times"]).tolist()          # stamps start AT start_time (quirk D5)
+    assert tt.x == [float(i) for i in range(7)] and tt.velocity == [1.0 + i for i in range(7)]
+    assert isinstance(tt.x, list) and len(tt) == 7
+    assert states_list_to_trajectory([], 3.0, 0.1).time == []
+    a = tt.to_numpy()
+    assert a.shape == (7, 5) and a.dtype == np.float64
+    for c, name in enumerate(("x", "y", "theta", "velocity", "time")):
+        assert a[:, c].tolist() == getattr(tt, name)
+    assert tt[2] == (2.0, -1.0, 0.2, 3.0, tt.time[2])
+    assert tt[-1][0] == 6.0
+    sl = tt[1:4]
+    assert sl[0] == [1.0, 2.0, 3.0] and len(sl) == 5 and sl[4] == tt.time[1:4]
+    assert repr(tt) == str(tt) == "Trajectory(len=7)"
+    short = Trajectory(x=[0, 1, 2], y=[0, 0, 0], theta=[0, 0], velocity=[1, 1, 1], time=[0, 1, 2])
+    assert len(short) == 3                                             # len is the length of x (GPS theta is one short)
+    with pytest.raises(ValueError):
+        short.to_numpy()                                               # ragged columns: NumPy refuses, as in the reference
+    if ref_bridge.available():
+        ref = ref_bridge.load()
+        rstates = [ref.schema.State(**s.model_dump()) for s in states]
+        rt = ref.schema.states_list_to_trajectory(rstates, 12.5, 0.05)
+        assert dict(rt) == dict(tt)
+        assert np.array_equal(rt.to_numpy(), a) and rt[2] == tt[2] and rt[1:4] == tt[1:4]
+        assert len(rt) == len(tt) and repr(rt) == repr(tt)
+        rshort = ref.schema.Trajectory(**dict(short))
+        assert len(rshort) == 3
+        with pytest.raises(ValueError):
+            rshort.to_numpy()
+
+
+def test_block_cyclic_deal_matches_the_kernel_queue():
+    """scheduler.deal_* against the index arithmetic of the search kernel's queue
+    (csrc/vmvo_search.cu next_window): item r of rank q is window ((r >> s) * world + q) << s | low
+    bits, items run while the window exists; every window is dealt exactly once."""
+    from vehiclemodelvisualodometry_b200 import scheduler
+
+    for n in (0, 1, 31, 32, 33, 1000, 9940, 79520):
+        for world in (1, 2, 3, 4, 8):
+            for block in (1, 2, 32, 64):
+                sh = block.bit_length() - 1
+                seen = np.zeros(n, dtype=np.int64)
+                for rank in range(world):
+                    nb = -(-n // block)
+                    mine = (nb - rank + world - 1) // world if nb > rank else 0
+                    got = []
+                    for r in range(mine * block):             # the host's n_local
+                        b = r >> sh
+                        w = ((b * world + rank) << sh) + (r - (b << sh))
+                        if w >= n:
+                            break
+                        got.append(w)
+                    want = scheduler.deal_indices(n, block, world, rank)
+                    assert np.array_equal(got, want), (n, world, block, rank)
+                    assert len(want) == scheduler.deal_count(n, block, world, rank)
+                    assert np.all(scheduler.deal_owner(want, block, world) == rank)
+                    seen[want] += 1
+                assert np.all(seen == 1)
+    assert [scheduler.shard_range(10, 4, r) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
 
 
 def _sklansky(values, steps):

@@ -1,4 +1,4 @@
-"""Times the search kernel for each team size on one workload (VMVO_TEAM_WARPS override)."""
+"""Times the search kernel for each team size on one workload (tuning hook team_warps)."""
 import os
 import sys
 
@@ -8,7 +8,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
-from vehiclemodelvisualodometry_b200 import DriveSet, grid_search, plan_windows  # noqa: E402
+from vehiclemodelvisualodometry_b200 import DriveSet, _lib, grid_search, plan_windows  # noqa: E402
 from vehiclemodelvisualodometry_b200.synthetic import synthetic_drives  # noqa: E402
 
 workload = sys.argv[1] if len(sys.argv) > 1 else "config2_single_drive_10k_32x32_w30"
@@ -21,7 +21,7 @@ drives = DriveSet.from_arrays([t], [batch.dt], vo=[vo])
 plan = plan_windows(cfg, drives)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for tw in (1, 2, 4, 8):
-    os.environ["VMVO_TEAM_WARPS"] = str(tw)
+    _lib.context(0).set_tuning("team_warps", tw)
     for _ in range(3):
         so = grid_search(cfg, drives, plan)
     torch.cuda.synchronize()

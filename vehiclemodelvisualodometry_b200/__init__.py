@@ -9,7 +9,7 @@ from .bicycle_model import BicycleModel, rollout_batch  # noqa: F401
 from .search import (DrivePipeline, DriveSet, DriveStream, SearchConfig, SearchOutput, WindowPlan,  # noqa: F401
                      grid_search, hypothesis_steps, optimize_drives, plan_windows, write_back)
 from .mpc import grid_run, mpc_run, sequence_cost, traverse_trajectory  # noqa: F401
-from .optimize import DEFAULT_CFG, REFERENCE_CFG, optimize_trajectory  # noqa: F401
+from .optimize import DEFAULT_CFG, REFERENCE_CFG, VO_CFG, optimize_trajectory  # noqa: F401
 from .dataset import (load_android_drive, load_android_drives_device, optimize_android_drives,  # noqa: F401
                       parse_csv_files, prepare_android_drives, read_csv)
 

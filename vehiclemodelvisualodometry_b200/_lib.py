@@ -5,6 +5,7 @@ CUDA device is present, every operator raises -- there is no CPU fallback.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import os
 import threading
@@ -17,7 +18,7 @@ from . import build as _build
 _c_i32, _c_i64, _c_f64, _c_f32, _c_vp = C.c_int32, C.c_int64, C.c_double, C.c_float, C.c_void_p
 
 VMVO_OK = 0
-WIN_EMPTY, WIN_NONFINITE, WIN_TOO_LONG = 1, 2, 4
+WIN_EMPTY, WIN_NONFINITE, WIN_TOO_LONG, WIN_NO_FRAMES = 1, 2, 4, 8
 FAIL_NONE, FAIL_STEER, FAIL_ACCEL = 0, 1, 2
 CSV_BAD_NUMBER, CSV_TOO_MANY_FIELDS, CSV_BAD_ROT, CSV_UNSORTED = 1, 2, 4, 8
 CSV_SLOT_ROT, CSV_MAX_COLS = 1000, 64
@@ -37,6 +38,19 @@ class SearchCfg(C.Structure):
         ("horizon_time", _c_f64), ("w_vo", _c_f64), ("w_gps", _c_f64), ("w_imu", _c_f64),
         ("k_steer", _c_f64), ("wheel_base", _c_f64), ("steering_ratio", _c_f64),
         ("max_steer", _c_f64), ("max_accel", _c_f64), ("max_steer_rate", _c_f64),
+    ]
+
+
+MAX_MIRRORS = 16
+
+
+class Exchange(C.Structure):
+    """struct vmvo_exchange: the window deal and the record exchange of one sharded call."""
+
+    _fields_ = [
+        ("world", _c_i32), ("rank", _c_i32), ("block", _c_i32), ("n_peers", _c_i32),
+        ("peer_records", _c_vp * MAX_MIRRORS), ("peer_flags", _c_vp * MAX_MIRRORS),
+        ("local_flags", _c_vp), ("epoch", _c_vp),
     ]
 
 
@@ -94,7 +108,15 @@ _SIGNATURES = {
                                       _c_vp]),
     "vmvo_csv_parse_f64": (C.c_int, [_c_vp, _c_vp, _c_i32, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp,
                                      _c_i32, _c_i32, _c_vp, _c_vp, _c_vp, _c_vp]),
-    "vmvo_set_result_mirrors": (C.c_int, [_c_vp, _c_i32, _c_vp, _c_i64]),
+    "vmvo_grid_search_sharded": (C.c_int, [_c_vp, C.POINTER(SearchCfg), _c_i64, _c_vp, _c_vp, _c_vp, _c_vp,
+                                           _c_vp, _c_vp, _c_vp, _c_i32, _c_vp, _c_i64, _c_vp, _c_vp,
+                                           C.POINTER(Exchange), _c_vp]),
+    "vmvo_exchange_publish": (C.c_int, [_c_vp, C.POINTER(Exchange), _c_vp]),
+    "vmvo_exchange_wait": (C.c_int, [_c_vp, C.POINTER(Exchange), _c_vp]),
+    "vmvo_write_back_range": (C.c_int, [_c_vp, C.POINTER(SearchCfg), _c_i32, _c_i64, _c_i64, _c_i64, _c_vp,
+                                        _c_vp, _c_vp, _c_vp, _c_vp, _c_i32, _c_vp, _c_vp, _c_vp, _c_vp,
+                                        _c_vp, C.POINTER(Exchange), _c_vp]),
+    "vmvo_debug_set_tuning": (C.c_int, [_c_vp, C.c_char_p, _c_i32]),
     "vmvo_peer_buffer_create": (C.c_int, [_c_vp, _c_i64, C.POINTER(_c_vp), _c_vp]),
     "vmvo_peer_buffer_destroy": (C.c_int, [_c_vp, _c_vp]),
     "vmvo_peer_buffer_open": (C.c_int, [_c_vp, _c_vp, C.POINTER(_c_vp)]),
@@ -137,7 +159,7 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)  # AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args
-        if lib.vmvo_abi_version() != 1:
+        if lib.vmvo_abi_version() != 2:
             raise RuntimeError("libvmvo_b200.so ABI version mismatch; rebuild")
         _lib = lib
         return lib
@@ -165,6 +187,22 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self.lib.vmvo_launch_count(self.handle))
+
+    def set_tuning(self, key: str, value: int) -> None:
+        """Test / tuning hook (``vmvo_debug_set_tuning``); a negative value restores the default."""
+        self.check(self.lib.vmvo_debug_set_tuning(self.handle, key.encode(), int(value)),
+                   "vmvo_debug_set_tuning")
+
+    @contextlib.contextmanager
+    def tuning(self, **overrides):
+        """``with ctx.tuning(defer_min=1): ...`` -- overrides in force inside the block only."""
+        for k, v in overrides.items():
+            self.set_tuning(k, v)
+        try:
+            yield self
+        finally:
+            for k in overrides:
+                self.set_tuning(k, -1)
 
     def close(self):
         if self.handle:

@@ -65,6 +65,58 @@ __global__ void plan_windows_kernel(int window_mode, int window_frames, double h
   }
 }
 
+// ---- the record exchange: arrival words between the ranks of a box (vmvo_exchange) ---------------
+// What a kernel needs of a vmvo_exchange.  publish: st.release.sys of the step number into the word
+// this rank owns in every peer's flag array -- issued by a kernel that follows, in stream order,
+// every kernel that stored records of the step, so the release is cumulative over those stores.
+// wait: ld.acquire.sys on this rank's own flag array until every peer's word has reached the step.
+struct ExchangeDev {
+  int world, rank, n_peers;
+  unsigned* peer_flags[VMVO_MAX_MIRRORS];
+  const unsigned* local_flags;
+  unsigned* epoch;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+constexpr unsigned long long kWaitTimeoutNs = 10ull * 1000 * 1000 * 1000;
+
+__device__ __forceinline__ void exchange_publish(const ExchangeDev& ex, int t) {
+  if (t < ex.n_peers) {
+    const unsigned e = *reinterpret_cast<volatile unsigned*>(ex.epoch);
+    __threadfence_system();
+    st_release_sys(ex.peer_flags[t], e);
+  }
+}
+// thread t < world waits for rank t's word (its own: nothing to wait for)
+__device__ __forceinline__ void exchange_wait(const ExchangeDev& ex, int t) {
+  if (t < ex.world && t != ex.rank) {
+    const unsigned e = *reinterpret_cast<volatile unsigned*>(ex.epoch);
+    const unsigned long long t0 = global_ns();
+    while ((int)(ld_acquire_sys(ex.local_flags + t) - e) < 0) {
+      if (global_ns() - t0 > kWaitTimeoutNs) {      // a dead peer must not hang this GPU
+        atomicExch(ex.epoch + 1, 1u + (unsigned)t);
+        break;
+      }
+      __nanosleep(32);
+    }
+  }
+}
+
+__global__ void exchange_publish_kernel(const ExchangeDev ex) { exchange_publish(ex, threadIdx.x); }
+__global__ void exchange_wait_kernel(const ExchangeDev ex) { exchange_wait(ex, threadIdx.x); }
+
 // ---- a12: write-back and blends -----------------------------------------------------------------
 // One thread per frame.  Frame m of a drive takes x,y from the LAST window that covers it:
 // the largest i <= min(m, n_w - 1) with m - i < N_i (optimize_trajectory_v2.py:122-123 executed
@@ -76,13 +128,22 @@ __global__ void write_back_kernel(int gv, int gs, double L, double ratio, double
                                   double max_accel, double max_rate, int max_steps, int n_drives,
                                   const long long* drive_off, const long long* win_off,
                                   const double* dt_drive, const Pose4* vo, const Pose4* gps,
-                                  const vmvo_window_result* results, long long total_frames,
-                                  double* out_x, double* out_y, double* out_th, double* out_v) {
+                                  const vmvo_window_result* results, long long frame_lo,
+                                  long long frame_hi, double* out_x, double* out_y, double* out_th,
+                                  double* out_v, const ExchangeDev ex) {
+  // the consumer end of the record exchange: block 0 tells every peer that this rank's records of
+  // the step are complete (the searches precede this kernel in the stream), then every block waits
+  // for the peers' words before it reads a record
+  if (ex.n_peers > 0) {
+    if (blockIdx.x == 0) exchange_publish(ex, threadIdx.x);
+    exchange_wait(ex, threadIdx.x);
+    __syncthreads();
+  }
   const int lane = threadIdx.x & 31;
-  const long long f_base = (blockIdx.x * (long long)blockDim.x + threadIdx.x) - lane;
-  if (f_base >= total_frames) return;  // whole warp out of range
+  const long long f_base = frame_lo + (blockIdx.x * (long long)blockDim.x + threadIdx.x) - lane;
+  if (f_base >= frame_hi) return;  // whole warp out of range
   const long long f = f_base + lane;
-  const bool in_range = f < total_frames;
+  const bool in_range = f < frame_hi;
   int d = 0;
   long long m = 0, w0 = 0, nw = 0;
   double x = 0, y = 0, th = 0, v = 0;
@@ -333,21 +394,26 @@ extern "C" int vmvo_ctx_create(int device, vmvo_ctx** out) {
   vmvo_ctx* ctx = new vmvo_ctx();
   ctx->device = device;
   ctx->launches = 0;
-  ctx->n_mirrors = 0;
-  ctx->mirror_off = 0;
-  ctx->n_defer = 0;
   ctx->err[0] = 0;
-  ctx->d_work_counter = nullptr;
+  ctx->d_counters = nullptr;
+  ctx->slot_mutex = new std::mutex();
+  ctx->tune = vmvo_tuning{-1, -1, -1, -1, -1};
+  for (int q = 0; q < kLaunchSlots; ++q) ctx->slots[q] = vmvo_launch_slot{nullptr, nullptr, 0, nullptr, false, false};
+  DeviceGuard guard(device);
   cudaDeviceProp prop;
-  if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess ||
-      cudaMalloc(&ctx->d_work_counter, 64 * 2 * sizeof(unsigned long long)) != cudaSuccess) {
-    delete ctx;
+  bool ok = guard.err == cudaSuccess && cudaGetDeviceProperties(&prop, device) == cudaSuccess &&
+            cudaMalloc(&ctx->d_counters, kLaunchSlots * 2 * sizeof(unsigned long long)) == cudaSuccess;
+  for (int q = 0; ok && q < kLaunchSlots; ++q) {
+    ctx->slots[q].d_counters = ctx->d_counters + 2 * q;
+    ok = cudaEventCreateWithFlags(&ctx->slots[q].done, cudaEventDisableTiming) == cudaSuccess;
+  }
+  if (!ok) {
+    vmvo_ctx_destroy(ctx);
     return VMVO_ERR_CUDA;
   }
   ctx->sm_count = prop.multiProcessorCount;
   if (prop.major != 10) {
-    cudaFree(ctx->d_work_counter);
-    delete ctx;
+    vmvo_ctx_destroy(ctx);
     return VMVO_ERR_UNSUPPORTED;  // built for sm_100a only
   }
   *out = ctx;
@@ -356,34 +422,37 @@ extern "C" int vmvo_ctx_create(int device, vmvo_ctx** out) {
 
 extern "C" int vmvo_ctx_destroy(vmvo_ctx* ctx) {
   if (!ctx) return VMVO_OK;
-  cudaSetDevice(ctx->device);
-  cudaFree(ctx->d_work_counter);
-  for (int q = 0; q < ctx->n_defer; ++q) cudaFree(ctx->d_defer[q]);
+  {
+    DeviceGuard guard(ctx->device);
+    cudaFree(ctx->d_counters);
+    for (int q = 0; q < kLaunchSlots; ++q) {
+      if (ctx->slots[q].d_defer) cudaFree(ctx->slots[q].d_defer);
+      if (ctx->slots[q].done) cudaEventDestroy(ctx->slots[q].done);
+    }
+  }
+  delete ctx->slot_mutex;
   delete ctx;
   return VMVO_OK;
 }
 
-// ---- result mirrors and peer buffers (the gather fused into the search) ---------------
-extern "C" int vmvo_set_result_mirrors(vmvo_ctx* ctx, int32_t n_mirrors, void* const* h_mirrors,
-                                       int64_t mirror_offset) {
-  if (!ctx) return VMVO_ERR_BAD_ARG;
-  if (n_mirrors < 0 || n_mirrors > VMVO_MAX_MIRRORS || (n_mirrors > 0 && !h_mirrors) || mirror_offset < 0)
-    return fail(ctx, VMVO_ERR_BAD_ARG, "n_mirrors must be in [0, %d], mirror_offset >= 0", VMVO_MAX_MIRRORS);
-  for (int q = 0; q < n_mirrors; ++q) {
-    if (!h_mirrors[q] || ((uintptr_t)h_mirrors[q] & 15))
-      return fail(ctx, VMVO_ERR_BAD_ARG, "mirror %d is NULL or not 16-byte aligned", q);
-    ctx->mirrors[q] = h_mirrors[q];
-  }
-  ctx->n_mirrors = n_mirrors;
-  ctx->mirror_off = mirror_offset;
+extern "C" int vmvo_debug_set_tuning(vmvo_ctx* ctx, const char* key, int32_t value) {
+  if (!ctx || !key) return VMVO_ERR_BAD_ARG;
+  int* slot = !strcmp(key, "team_warps") ? &ctx->tune.team_warps
+            : !strcmp(key, "fast_scan") ? &ctx->tune.fast_scan
+            : !strcmp(key, "cand_cap") ? &ctx->tune.cand_cap
+            : !strcmp(key, "defer_min") ? &ctx->tune.defer_min
+            : !strcmp(key, "max_ctas_per_sm") ? &ctx->tune.max_ctas_per_sm : nullptr;
+  if (!slot) return fail(ctx, VMVO_ERR_BAD_ARG, "unknown tuning key '%s'", key);
+  *slot = value < 0 ? -1 : value;
   return VMVO_OK;
 }
 
+// ---- peer buffers and arrival words (the exchange fused into the search / write-back) ----
 extern "C" int vmvo_peer_buffer_create(vmvo_ctx* ctx, int64_t bytes, void** d_ptr, uint8_t* h_handle) {
   if (!ctx) return VMVO_ERR_BAD_ARG;
   if (bytes < 1 || !d_ptr || !h_handle) return fail(ctx, VMVO_ERR_BAD_ARG, "bad argument");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-  VMVO_CUDA(ctx, cudaSetDevice(ctx->device));
+  VMVO_ON_DEVICE(ctx);
   void* p = nullptr;
   VMVO_CUDA(ctx, cudaMalloc(&p, (size_t)bytes));
   cudaIpcMemHandle_t h;
@@ -400,7 +469,7 @@ extern "C" int vmvo_peer_buffer_create(vmvo_ctx* ctx, int64_t bytes, void** d_pt
 extern "C" int vmvo_peer_buffer_destroy(vmvo_ctx* ctx, void* d_ptr) {
   if (!ctx) return VMVO_ERR_BAD_ARG;
   if (!d_ptr) return VMVO_OK;
-  VMVO_CUDA(ctx, cudaSetDevice(ctx->device));
+  VMVO_ON_DEVICE(ctx);
   VMVO_CUDA(ctx, cudaFree(d_ptr));
   return VMVO_OK;
 }
@@ -408,7 +477,7 @@ extern "C" int vmvo_peer_buffer_destroy(vmvo_ctx* ctx, void* d_ptr) {
 extern "C" int vmvo_peer_buffer_open(vmvo_ctx* ctx, const uint8_t* h_handle, void** d_ptr) {
   if (!ctx) return VMVO_ERR_BAD_ARG;
   if (!h_handle || !d_ptr) return fail(ctx, VMVO_ERR_BAD_ARG, "bad argument");
-  VMVO_CUDA(ctx, cudaSetDevice(ctx->device));
+  VMVO_ON_DEVICE(ctx);
   cudaIpcMemHandle_t h;
   memcpy(&h, h_handle, sizeof(h));
   VMVO_CUDA(ctx, cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
@@ -418,7 +487,7 @@ extern "C" int vmvo_peer_buffer_open(vmvo_ctx* ctx, const uint8_t* h_handle, voi
 extern "C" int vmvo_peer_buffer_close(vmvo_ctx* ctx, void* d_ptr) {
   if (!ctx) return VMVO_ERR_BAD_ARG;
   if (!d_ptr) return VMVO_OK;
-  VMVO_CUDA(ctx, cudaSetDevice(ctx->device));
+  VMVO_ON_DEVICE(ctx);
   VMVO_CUDA(ctx, cudaIpcCloseMemHandle(d_ptr));
   return VMVO_OK;
 }
@@ -476,7 +545,7 @@ extern "C" int vmvo_plan_windows(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int3
     return fail(ctx, VMVO_ERR_BAD_ARG, "NULL pointer");
   if (cfg->window_mode == VMVO_WINDOW_TIME && !d_time)
     return fail(ctx, VMVO_ERR_BAD_ARG, "time mode needs d_time");
-  VMVO_CUDA(ctx, cudaSetDevice(ctx->device));
+  VMVO_ON_DEVICE(ctx);
   plan_windows_kernel<<<grid_for(n_windows, 256, ctx->sm_count * 8), 256, 0, (cudaStream_t)stream>>>(
       cfg->window_mode, cfg->window_frames, cfg->horizon_time, n_drives,
       (const long long*)d_drive_offsets, (const long long*)d_window_offsets, n_windows, d_time,
@@ -484,33 +553,80 @@ extern "C" int vmvo_plan_windows(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int3
   return check_launch(ctx, "plan_windows_kernel");
 }
 
+static int exchange_dev(vmvo_ctx* ctx, const vmvo_exchange* ex, ExchangeDev* out) {
+  memset(out, 0, sizeof(*out));
+  if (!ex || ex->n_peers <= 0) return VMVO_OK;
+  if (ex->world < 2 || ex->rank < 0 || ex->rank >= ex->world || ex->n_peers != ex->world - 1 ||
+      ex->n_peers > VMVO_MAX_MIRRORS || !ex->local_flags || !ex->epoch)
+    return fail(ctx, VMVO_ERR_BAD_ARG, "exchange: world %d rank %d n_peers %d, or NULL flags / epoch",
+                ex->world, ex->rank, ex->n_peers);
+  out->world = ex->world;
+  out->rank = ex->rank;
+  out->n_peers = ex->n_peers;
+  for (int q = 0; q < ex->n_peers; ++q) {
+    if (!ex->peer_flags[q]) return fail(ctx, VMVO_ERR_BAD_ARG, "exchange: peer flag %d is NULL", q);
+    out->peer_flags[q] = ex->peer_flags[q];
+  }
+  out->local_flags = ex->local_flags;
+  out->epoch = ex->epoch;
+  return VMVO_OK;
+}
+
+extern "C" int vmvo_exchange_publish(vmvo_ctx* ctx, const vmvo_exchange* ex, void* stream) {
+  if (!ctx) return VMVO_ERR_BAD_ARG;
+  ExchangeDev d;
+  int rc = exchange_dev(ctx, ex, &d);
+  if (rc || d.n_peers == 0) return rc;
+  VMVO_ON_DEVICE(ctx);
+  exchange_publish_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d);
+  return check_launch(ctx, "exchange_publish_kernel");
+}
+
+extern "C" int vmvo_exchange_wait(vmvo_ctx* ctx, const vmvo_exchange* ex, void* stream) {
+  if (!ctx) return VMVO_ERR_BAD_ARG;
+  ExchangeDev d;
+  int rc = exchange_dev(ctx, ex, &d);
+  if (rc || d.n_peers == 0) return rc;
+  VMVO_ON_DEVICE(ctx);
+  exchange_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d);
+  return check_launch(ctx, "exchange_wait_kernel");
+}
+
 template <typename Pose4>
 static int write_back_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int32_t n_drives,
-                           int64_t total_frames, const int64_t* d_drive_offsets,
+                           int64_t total_frames, int64_t frame_lo, int64_t frame_hi,
+                           const int64_t* d_drive_offsets,
                            const int64_t* d_window_offsets, const double* d_dt_per_drive,
                            const void* d_vo, const void* d_gps, const vmvo_window_result* d_results,
                            double* d_out_x, double* d_out_y, double* d_out_theta, double* d_out_vel,
-                           void* stream) {
+                           const vmvo_exchange* ex, void* stream) {
   if (!ctx) return VMVO_ERR_BAD_ARG;
   int rc = validate_cfg(ctx, cfg);
   if (rc) return rc;
+  ExchangeDev exd;
+  rc = exchange_dev(ctx, ex, &exd);
+  if (rc) return rc;
   if (n_drives < 1) return fail(ctx, VMVO_ERR_BAD_ARG, "n_drives < 1");
+  if (frame_lo < 0 || frame_hi > total_frames || frame_lo > frame_hi)
+    return fail(ctx, VMVO_ERR_BAD_ARG, "frame range [%lld, %lld) outside [0, %lld)", (long long)frame_lo,
+                (long long)frame_hi, (long long)total_frames);
   if (!d_drive_offsets || !d_window_offsets || !d_dt_per_drive || !d_vo || !d_results || !d_out_x ||
       !d_out_y || !d_out_theta || !d_out_vel)
     return fail(ctx, VMVO_ERR_BAD_ARG, "NULL pointer");
   if (((uintptr_t)d_vo | (uintptr_t)d_gps) & 15)
     return fail(ctx, VMVO_ERR_BAD_ARG, "pose streams must be 16-byte aligned");
-  VMVO_CUDA(ctx, cudaSetDevice(ctx->device));
+  VMVO_ON_DEVICE(ctx);
   cudaStream_t st = (cudaStream_t)stream;
-  const long long total = total_frames;
-  if (total <= 0) return VMVO_OK;
+  const long long total = frame_hi - frame_lo;
+  if (total <= 0 && exd.n_peers == 0) return VMVO_OK;
   const int threads = 256;
-  const long long blocks = (total + threads - 1) / threads;
+  long long blocks = (total + threads - 1) / threads;
+  if (blocks < 1) blocks = 1;          // (an empty share still publishes and waits)
   write_back_kernel<Pose4><<<(unsigned)blocks, threads, 0, st>>>(
       cfg->grid_v, cfg->grid_s, cfg->wheel_base, cfg->steering_ratio, cfg->max_steer, cfg->max_accel,
       cfg->max_steer_rate, cfg->max_window_poses, n_drives, (const long long*)d_drive_offsets,
       (const long long*)d_window_offsets, d_dt_per_drive, (const Pose4*)d_vo, (const Pose4*)d_gps,
-      d_results, total, d_out_x, d_out_y, d_out_theta, d_out_vel);
+      d_results, frame_lo, frame_hi, d_out_x, d_out_y, d_out_theta, d_out_vel, exd);
   return check_launch(ctx, "write_back_kernel");
 }
 
@@ -521,9 +637,9 @@ extern "C" int vmvo_write_back_f32(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, in
                                    const vmvo_window_result* d_results, double* d_out_x,
                                    double* d_out_y, double* d_out_theta, double* d_out_vel,
                                    void* stream) {
-  return write_back_impl<float4>(ctx, cfg, n_drives, total_frames, d_drive_offsets, d_window_offsets,
-                                 d_dt_per_drive, d_vo, d_gps, d_results, d_out_x, d_out_y,
-                                 d_out_theta, d_out_vel, stream);
+  return write_back_impl<float4>(ctx, cfg, n_drives, total_frames, 0, total_frames, d_drive_offsets,
+                                 d_window_offsets, d_dt_per_drive, d_vo, d_gps, d_results, d_out_x,
+                                 d_out_y, d_out_theta, d_out_vel, nullptr, stream);
 }
 
 extern "C" int vmvo_write_back_f64(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int32_t n_drives,
@@ -533,9 +649,25 @@ extern "C" int vmvo_write_back_f64(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, in
                                    const vmvo_window_result* d_results, double* d_out_x,
                                    double* d_out_y, double* d_out_theta, double* d_out_vel,
                                    void* stream) {
-  return write_back_impl<double4>(ctx, cfg, n_drives, total_frames, d_drive_offsets, d_window_offsets,
-                                  d_dt_per_drive, d_vo, d_gps, d_results, d_out_x, d_out_y,
-                                  d_out_theta, d_out_vel, stream);
+  return write_back_impl<double4>(ctx, cfg, n_drives, total_frames, 0, total_frames, d_drive_offsets,
+                                  d_window_offsets, d_dt_per_drive, d_vo, d_gps, d_results, d_out_x,
+                                  d_out_y, d_out_theta, d_out_vel, nullptr, stream);
+}
+
+extern "C" int vmvo_write_back_range(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int32_t n_drives,
+                                     int64_t total_frames, int64_t frame_lo, int64_t frame_hi,
+                                     const int64_t* d_drive_offsets, const int64_t* d_window_offsets,
+                                     const double* d_dt_per_drive, const void* d_vo, const void* d_gps,
+                                     int32_t stream_f64, const vmvo_window_result* d_results,
+                                     double* d_out_x, double* d_out_y, double* d_out_theta,
+                                     double* d_out_vel, const vmvo_exchange* ex, void* stream) {
+  return stream_f64
+             ? write_back_impl<double4>(ctx, cfg, n_drives, total_frames, frame_lo, frame_hi,
+                                        d_drive_offsets, d_window_offsets, d_dt_per_drive, d_vo, d_gps,
+                                        d_results, d_out_x, d_out_y, d_out_theta, d_out_vel, ex, stream)
+             : write_back_impl<float4>(ctx, cfg, n_drives, total_frames, frame_lo, frame_hi,
+                                       d_drive_offsets, d_window_offsets, d_dt_per_drive, d_vo, d_gps,
+                                       d_results, d_out_x, d_out_y, d_out_theta, d_out_vel, ex, stream);
 }
 
 template <typename T>
@@ -547,7 +679,7 @@ static int rollout_impl(vmvo_ctx* ctx, int64_t n_seq, int32_t n_steps, const T* 
   if (n_seq == 0) return VMVO_OK;
   if (!d_state0 || !d_fail || (n_steps > 0 && (!d_steer || !d_vel || !d_out)))
     return fail(ctx, VMVO_ERR_BAD_ARG, "NULL pointer");
-  VMVO_CUDA(ctx, cudaSetDevice(ctx->device));
+  VMVO_ON_DEVICE(ctx);
   const int threads = 128;
   const unsigned blocks = grid_for(n_seq * 32, threads, ctx->sm_count * 16);
   // the model uses the module constants, not the constructor arguments (quirk D2,
@@ -582,7 +714,7 @@ extern "C" int vmvo_sequence_cost_f64(vmvo_ctx* ctx, int64_t n_seq, int32_t n_st
   if (n_seq == 0) return VMVO_OK;
   if (!d_target_xy || !d_cost || (n_steps > 0 && !d_steer))
     return fail(ctx, VMVO_ERR_BAD_ARG, "NULL pointer");
-  VMVO_CUDA(ctx, cudaSetDevice(ctx->device));
+  VMVO_ON_DEVICE(ctx);
   const int threads = 128;
   sequence_cost_kernel<<<grid_for(n_seq * 32, threads, ctx->sm_count * 16), threads, 0,
                          (cudaStream_t)stream>>>(n_seq, n_steps, d_steer, velocity, dt, d_target_xy,
@@ -596,7 +728,7 @@ extern "C" int vmvo_extract_window_f64(vmvo_ctx* ctx, int32_t n, const double* d
   if (!ctx) return VMVO_ERR_BAD_ARG;
   if (n < 1) return fail(ctx, VMVO_ERR_BAD_ARG, "n < 1");
   if (!d_x || !d_y || !d_theta || !d_lx || !d_ly || !d_lth) return fail(ctx, VMVO_ERR_BAD_ARG, "NULL pointer");
-  VMVO_CUDA(ctx, cudaSetDevice(ctx->device));
+  VMVO_ON_DEVICE(ctx);
   extract_window_kernel<<<grid_for(n, 256, ctx->sm_count * 4), 256, 0, (cudaStream_t)stream>>>(
       n, d_x, d_y, d_theta, d_lx, d_ly, d_lth);
   return check_launch(ctx, "extract_window_kernel");
@@ -606,7 +738,7 @@ extern "C" int vmvo_time_extent_f64(vmvo_ctx* ctx, int64_t n, const double* d_ti
                                     double t1, int64_t* d_extent, void* stream) {
   if (!ctx) return VMVO_ERR_BAD_ARG;
   if (n < 0 || !d_extent || (n > 0 && !d_time)) return fail(ctx, VMVO_ERR_BAD_ARG, "bad argument");
-  VMVO_CUDA(ctx, cudaSetDevice(ctx->device));
+  VMVO_ON_DEVICE(ctx);
   time_extent_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(n, d_time, t0, t1, (long long*)d_extent);
   return check_launch(ctx, "time_extent_kernel");
 }
@@ -615,7 +747,7 @@ extern "C" int vmvo_traverse_f64(vmvo_ctx* ctx, int32_t n, const double* d_xy, d
                                  int32_t* d_keep, int32_t* d_count, void* stream) {
   if (!ctx) return VMVO_ERR_BAD_ARG;
   if (n < 0 || !d_count || (n > 0 && (!d_xy || !d_keep))) return fail(ctx, VMVO_ERR_BAD_ARG, "bad argument");
-  VMVO_CUDA(ctx, cudaSetDevice(ctx->device));
+  VMVO_ON_DEVICE(ctx);
   traverse_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(n, d_xy, D, d_keep, d_count);
   return check_launch(ctx, "traverse_kernel");
 }
@@ -625,7 +757,7 @@ extern "C" int vmvo_tan_steer_f32(vmvo_ctx* ctx, int64_t n, const float* d_delta
   if (!ctx) return VMVO_ERR_BAD_ARG;
   if (n < 0 || (n > 0 && (!d_delta || !d_out))) return fail(ctx, VMVO_ERR_BAD_ARG, "bad argument");
   if (n == 0) return VMVO_OK;
-  VMVO_CUDA(ctx, cudaSetDevice(ctx->device));
+  VMVO_ON_DEVICE(ctx);
   tan_steer_kernel<<<grid_for(n, 256, ctx->sm_count * 16), 256, 0, (cudaStream_t)stream>>>(n, d_delta, d_out);
   return check_launch(ctx, "tan_steer_kernel");
 }
@@ -635,7 +767,7 @@ extern "C" int vmvo_peak_probe(vmvo_ctx* ctx, int32_t kind, int32_t blocks, int3
   if (!ctx) return VMVO_ERR_BAD_ARG;
   if (kind < 0 || kind > 2 || blocks < 1 || threads < 32 || threads > 1024 || iters < 1 || !d_sink)
     return fail(ctx, VMVO_ERR_BAD_ARG, "bad probe argument");
-  VMVO_CUDA(ctx, cudaSetDevice(ctx->device));
+  VMVO_ON_DEVICE(ctx);
   peak_probe_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(kind, iters, d_sink);
   return check_launch(ctx, "peak_probe_kernel");
 }

@@ -558,7 +558,7 @@ extern "C" int vmvo_csv_count_rows(vmvo_ctx* ctx, const uint8_t* d_bytes, int32_
   int rc = csv_check(ctx, d_bytes, n_files, h_file_off, h_file_len, d_file_off, d_file_len, d_scratch);
   if (rc) return rc;
   if (!d_row_counts) return fail(ctx, VMVO_ERR_BAD_ARG, "NULL pointer");
-  VMVO_CUDA(ctx, cudaSetDevice(ctx->device));
+  VMVO_ON_DEVICE(ctx);
   cudaStream_t st = (cudaStream_t)stream;
   long long* blk_off = (long long*)d_scratch;
   CsvBlk* blk = (CsvBlk*)(blk_off + n_files + 1);
@@ -588,7 +588,7 @@ extern "C" int vmvo_csv_index_rows(vmvo_ctx* ctx, const uint8_t* d_bytes, int32_
   int rc = csv_check(ctx, d_bytes, n_files, h_file_off, h_file_len, d_file_off, d_file_len, d_scratch);
   if (rc) return rc;
   if (!d_row_off || !d_row_starts) return fail(ctx, VMVO_ERR_BAD_ARG, "NULL pointer");
-  VMVO_CUDA(ctx, cudaSetDevice(ctx->device));
+  VMVO_ON_DEVICE(ctx);
   long long* blk_off = (long long*)d_scratch;
   CsvBlk* blk = (CsvBlk*)(blk_off + n_files + 1);
   const long long nb = csv_blocks(n_files, h_file_len);
@@ -613,7 +613,7 @@ extern "C" int vmvo_csv_parse_f64(vmvo_ctx* ctx, const uint8_t* d_bytes, int32_t
       !d_status || (n_slots > 0 && n_data > 0 && !d_out))
     return fail(ctx, VMVO_ERR_BAD_ARG, "NULL pointer");
   if (sorted_slot >= n_slots) return fail(ctx, VMVO_ERR_BAD_ARG, "sorted_slot out of range");
-  VMVO_CUDA(ctx, cudaSetDevice(ctx->device));
+  VMVO_ON_DEVICE(ctx);
   cudaStream_t st = (cudaStream_t)stream;
   VMVO_CUDA(ctx, cudaMemsetAsync(d_status, 0, sizeof(int32_t) * n_files, st));
   if (n_data == 0) return VMVO_OK;

@@ -6,24 +6,37 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <mutex>
+
 #include "../../include/vmvo_b200.h"
+
+// Per-launch scratch of a search: the work-queue head and the deferred-window slot count (16 bytes,
+// cleared by one memset) and the buffer the deferred windows are parked in.  A slot belongs to ONE
+// launch at a time: it is handed out again only after the event recorded behind that launch has
+// completed, so searches of one ctx on different streams never share scratch.  A launch recorded
+// into a CUDA graph keeps its slot for good (pinned): the graph may be replayed at any time.
+struct vmvo_launch_slot {
+  unsigned long long* d_counters;   // [2]: queue head, deferred-window count
+  unsigned char* d_defer;
+  size_t defer_bytes;
+  cudaEvent_t done;
+  bool used, pinned;
+};
+constexpr int kLaunchSlots = 256;
+
+// test / tuning overrides (vmvo_debug_set_tuning); -1 = the library's own choice
+struct vmvo_tuning {
+  int team_warps, fast_scan, cand_cap, defer_min, max_ctas_per_sm;
+};
 
 struct vmvo_ctx {
   int device;
   int sm_count;
-  // 64 pairs (work-queue head of the persistent search, deferred-window slot count), one pair per
-  // launch in rotation: 16 bytes, cleared by one memset
-  unsigned long long* d_work_counter;
+  unsigned long long* d_counters;   // kLaunchSlots pairs
+  vmvo_launch_slot slots[kLaunchSlots];
+  std::mutex* slot_mutex;
   long long launches;
-  // result mirrors (vmvo_set_result_mirrors): every record is also stored at mirrors[q][off + w]
-  int n_mirrors;
-  void* mirrors[VMVO_MAX_MIRRORS];
-  long long mirror_off;
-  // deferred windows (vmvo_search.cu): candidate lists parked for the second kernel.  Buffers only
-  // grow and old ones stay alive until the ctx is destroyed: captured graphs keep their pointers.
-  unsigned char* d_defer[8];
-  size_t defer_bytes[8];
-  int n_defer;
+  vmvo_tuning tune;
   char err[512];
 };
 
@@ -53,6 +66,26 @@ inline int check_launch(vmvo_ctx* ctx, const char* what) {
     if (e__ != cudaSuccess)                                                         \
       return vmvo::fail(ctx, VMVO_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__)); \
   } while (0)
+
+// Makes ctx->device current for the duration of an entry point and restores the caller's device on
+// the way out (the library never leaves the calling thread's current device changed).
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int dev) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+    else if (err == cudaSuccess) prev = -1;      // already current: nothing to restore
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+#define VMVO_ON_DEVICE(ctx)                                                                   \
+  vmvo::DeviceGuard dev_guard__((ctx)->device);                                               \
+  if (dev_guard__.err != cudaSuccess)                                                         \
+    return vmvo::fail(ctx, VMVO_ERR_CUDA, "cudaSetDevice(%d): %s", (ctx)->device,            \
+                      cudaGetErrorString(dev_guard__.err))
 
 inline int validate_cfg(vmvo_ctx* ctx, const vmvo_search_cfg* c) {
   if (!c) return fail(ctx, VMVO_ERR_BAD_ARG, "cfg is NULL");

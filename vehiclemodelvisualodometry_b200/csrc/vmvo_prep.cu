@@ -247,7 +247,7 @@ extern "C" int vmvo_smooth_f64(vmvo_ctx* ctx, int32_t n_drives, int64_t total_fr
     return fail(ctx, VMVO_ERR_BAD_ARG, "bad argument");
   if (total_frames == 0) return VMVO_OK;
   if (!d_x || !d_y || !d_out_x || !d_out_y) return fail(ctx, VMVO_ERR_BAD_ARG, "NULL pointer");
-  VMVO_CUDA(ctx, cudaSetDevice(ctx->device));
+  VMVO_ON_DEVICE(ctx);
   smooth_kernel<<<blocks_for(total_frames, 256, ctx->sm_count * 8), 256, 0, (cudaStream_t)stream>>>(
       n_drives, (const long long*)d_offsets, total_frames, d_x, d_y, window, 1.0, 1.0, d_out_x, d_out_y);
   return check_launch(ctx, "smooth_kernel");
@@ -266,7 +266,7 @@ extern "C" int vmvo_vo_prepare_f64(vmvo_ctx* ctx, int32_t n_drives, int64_t tota
   if (!d_x || !d_y || !d_rot || !d_stamp_ms || !d_out_x || !d_out_y || !d_out_theta || !d_out_vel ||
       !d_out_time)
     return fail(ctx, VMVO_ERR_BAD_ARG, "NULL pointer");
-  VMVO_CUDA(ctx, cudaSetDevice(ctx->device));
+  VMVO_ON_DEVICE(ctx);
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned g = blocks_for(total_frames, 256, ctx->sm_count * 8);
   vo_prepare_kernel<<<g, 256, 0, st>>>(n_drives, (const long long*)d_offsets, total_frames, d_x, d_y,
@@ -297,7 +297,7 @@ extern "C" int vmvo_gps_prepare_f64(vmvo_ctx* ctx, int32_t n_drives, int64_t tot
       !d_out_theta || !d_out_vel || !d_out_time || !d_status)
     return fail(ctx, VMVO_ERR_BAD_ARG, "NULL pointer");
   if ((uintptr_t)d_scratch & 7) return fail(ctx, VMVO_ERR_BAD_ARG, "scratch must be 8-byte aligned");
-  VMVO_CUDA(ctx, cudaSetDevice(ctx->device));
+  VMVO_ON_DEVICE(ctx);
   cudaStream_t st = (cudaStream_t)stream;
   const long long F = total_frames, M = total_frames + n_drives;
   double* dxy = (double*)d_scratch;          // [2][F]

@@ -73,10 +73,15 @@ struct SearchParams {
   // steering seed of a window is the last steering angle of the previous window's optimum
   const long long* run_offsets;   // [n_runs + 1] window index ranges, or NULL
   long long n_runs;
-  // result mirrors (vmvo_set_result_mirrors): the gather fused into the epilogue
+  // the window deal (vmvo_exchange): queue item r of this rank is global window
+  // ((r >> sh_block_sh) * sh_world + sh_rank) << sh_block_sh | (r & (block - 1)); sh_world <= 1 or
+  // sh_block_sh < 0: item r is window r.  In chained mode whole runs are dealt: r * sh_world + sh_rank.
+  int sh_world, sh_rank, sh_block_sh;
+  long long n_local;     // queue items of this rank (an upper bound: the last block may overhang)
+  // result mirrors: the gather fused into the epilogue (peers' gather buffers, indexed like results)
   int n_mirrors;
-  long long mirror_off;
   vmvo_window_result* mirrors[VMVO_MAX_MIRRORS];
+  unsigned* epoch;       // step counter of the exchange, advanced once per launch (or NULL)
   // deferred windows: candidate lists of at least defer_min entries are parked here (one slot
   // per window) and re-scored by vmvo_deferred_rescore_kernel with the whole GPU
   unsigned char* defer_buf;
@@ -626,7 +631,7 @@ vmvo_window_search_kernel(const SearchParams p) {
   // over NVLink, visible to the peers when the kernel has completed)
   auto store_record = [&](long long w, const vmvo_window_result& r) {
     p.results[w] = r;
-    for (int q = 0; q < p.n_mirrors; ++q) p.mirrors[q][p.mirror_off + w] = r;
+    for (int q = 0; q < p.n_mirrors; ++q) p.mirrors[q][w] = r;
   };
 
   const bool chained = p.run_offsets != nullptr;
@@ -639,9 +644,17 @@ vmvo_window_search_kernel(const SearchParams p) {
       return w + 1;
     }
     hd->first[slot] = 1;
+    const bool dealt = p.sh_world > 1;
     for (;;) {
-      const long long r = (long long)atomicAdd(p.work_counter, 1ULL);
-      if (!chained) return r;
+      long long r = (long long)atomicAdd(p.work_counter, 1ULL);
+      if (!chained) {
+        if (!dealt || p.sh_block_sh < 0) return r < p.n_local ? r : p.n_windows;
+        if (r >= p.n_local) return p.n_windows;
+        const long long b = r >> p.sh_block_sh;
+        const long long w = (((b * p.sh_world + p.sh_rank) << p.sh_block_sh)) + (r - (b << p.sh_block_sh));
+        return w < p.n_windows ? w : p.n_windows;    // (w grows with r: nothing valid follows)
+      }
+      if (dealt) r = r * p.sh_world + p.sh_rank;
       if (r >= p.n_runs) return p.n_windows;
       run_end = p.run_offsets[r + 1];
       if (p.run_offsets[r] < run_end) return p.run_offsets[r];
@@ -651,6 +664,8 @@ vmvo_window_search_kernel(const SearchParams p) {
   // the queue pop and the TMA issue belong to lane 0 of the team's LAST warp: phases A1 / A2 keep
   // warp 0 busy, so in a multi-warp team the atomic and its dependent loads overlap with them
   const bool fetcher = tid == T - 32;
+  // a sharded search advances the exchange's step counter (nothing reads it while a search runs)
+  if (p.epoch && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(p.epoch, 1u);
   if (fetcher) {
     mbar_init(&hd->mbar[0], 1);
     mbar_init(&hd->mbar[1], 1);
@@ -693,7 +708,10 @@ vmvo_window_search_kernel(const SearchParams p) {
     };
 
     if (len > P || len < 1) {  // uniform branch
-      if (tid == 0) write_unsearched(VMVO_WIN_TOO_LONG, 0, CUDART_NAN, CUDART_NAN);
+      // no pose at all (an empty time extent, NaN stamps): "No frames found", schema.py:122
+      if (tid == 0)
+        write_unsearched(len < 1 ? (VMVO_WIN_EMPTY | VMVO_WIN_NO_FRAMES) : VMVO_WIN_TOO_LONG, 0,
+                         CUDART_NAN, CUDART_NAN);
       team.sync();
       continue;
     }
@@ -1538,7 +1556,7 @@ vmvo_deferred_rescore_kernel(const SearchParams p) {
       r.y1 = bwi >= 0 ? s_pose[bwi][1] : CUDART_NAN;
       r.theta1 = bwi >= 0 ? s_pose[bwi][2] : CUDART_NAN;
       p.results[dh->w] = r;
-      for (int q = 0; q < p.n_mirrors; ++q) p.mirrors[q][p.mirror_off + dh->w] = r;
+      for (int q = 0; q < p.n_mirrors; ++q) p.mirrors[q][dh->w] = r;
     }
     __syncthreads();
   }
@@ -1562,13 +1580,11 @@ static int launch_search_v(vmvo_ctx* ctx, const SearchParams& p_in, cudaStream_t
   int per_sm = 0;
   VMVO_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kCtaThreads, smem));
   if (per_sm < 1) return fail(ctx, VMVO_ERR_CUDA, "search kernel does not fit on an SM");
-  if (const char* ov = getenv("VMVO_MAX_CTAS_PER_SM")) {  // experiment knob
-    const int v = atoi(ov);
-    if (v >= 1 && v < per_sm) per_sm = v;
-  }
+  if (ctx->tune.max_ctas_per_sm >= 1 && ctx->tune.max_ctas_per_sm < per_sm) per_sm = ctx->tune.max_ctas_per_sm;
   long long grid = (long long)ctx->sm_count * per_sm;
-  const long long items = p.run_offsets ? p.n_runs : p.n_windows;
-  const long long need = (items + teams - 1) / teams;
+  const long long items = p.n_local;
+  long long need = (items + teams - 1) / teams;
+  if (need < 1) need = 1;      // (an empty share still advances the exchange's step counter)
   if (grid > need) grid = need;
   kern<<<(unsigned)grid, kCtaThreads, smem, st>>>(p);
   int rc = check_launch(ctx, "vmvo_window_search_kernel");
@@ -1586,6 +1602,96 @@ static int launch_search(vmvo_ctx* ctx, const SearchParams& p, cudaStream_t st) 
                     : launch_search_v<C, WARPS, MINB, DUAL, IMU, SF, false>(ctx, p, st);
 }
 
+// ---- per-launch scratch (vmvo_launch_slot, vmvo_internal.h) -----------------------------------------
+// A slot that no launch in flight and no captured graph owns, with a deferred-window buffer of at
+// least `need` bytes when one can be had: a free slot that already has one, else a free slot whose
+// buffer is (re)allocated; without memory the search runs without deferral, which is still correct.
+// While the caller's stream is being captured the event queries and the allocation run with this
+// thread's capture mode relaxed (they touch nothing the capture records).
+struct RelaxedCapture {
+  bool on;
+  cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;
+  explicit RelaxedCapture(bool capturing) : on(capturing) {
+    if (on) cudaThreadExchangeStreamCaptureMode(&mode);
+  }
+  ~RelaxedCapture() {
+    if (on) cudaThreadExchangeStreamCaptureMode(&mode);
+  }
+};
+
+static vmvo_launch_slot* acquire_launch_slot(vmvo_ctx* ctx, size_t need, bool capturing) {
+  std::lock_guard<std::mutex> lock(*ctx->slot_mutex);
+  RelaxedCapture relaxed(capturing);
+  vmvo_launch_slot* fit = nullptr;      // free, buffer large enough (the smallest such)
+  vmvo_launch_slot* bare = nullptr;     // free, no buffer
+  vmvo_launch_slot* small = nullptr;    // free, buffer too small (the largest such)
+  for (int q = 0; q < kLaunchSlots; ++q) {
+    vmvo_launch_slot* sl = &ctx->slots[q];
+    if (sl->pinned) continue;
+    if (sl->used) {
+      if (cudaEventQuery(sl->done) != cudaSuccess) {
+        cudaGetLastError();             // (cudaErrorNotReady is not sticky, but clear it anyway)
+        continue;
+      }
+      sl->used = false;
+    }
+    if (sl->defer_bytes >= need && sl->d_defer) {
+      if (!fit || sl->defer_bytes < fit->defer_bytes) fit = sl;
+    } else if (!sl->d_defer) {
+      if (!bare) bare = sl;
+    } else if (!small || sl->defer_bytes > small->defer_bytes) {
+      small = sl;
+    }
+  }
+  if (need == 0) return bare ? bare : (small ? small : fit);
+  if (fit) return fit;
+  vmvo_launch_slot* sl = bare ? bare : small;
+  if (!sl) return nullptr;
+  if (sl->d_defer) {                    // free slot: nothing in flight reads its buffer
+    cudaFree(sl->d_defer);
+    sl->d_defer = nullptr;
+    sl->defer_bytes = 0;
+  }
+  void* buf = nullptr;
+  if (cudaMalloc(&buf, need) == cudaSuccess) {
+    sl->d_defer = (unsigned char*)buf;
+    sl->defer_bytes = need;
+  } else {
+    cudaGetLastError();                 // no room: search without deferral
+  }
+  return sl;
+}
+
+static void release_launch_slot(vmvo_ctx* ctx, vmvo_launch_slot* sl, cudaStream_t st, bool capturing) {
+  std::lock_guard<std::mutex> lock(*ctx->slot_mutex);
+  if (capturing) {
+    sl->pinned = true;                  // the graph owns it from now on
+  } else {
+    sl->used = cudaEventRecord(sl->done, st) == cudaSuccess;
+    if (!sl->used) {                    // cannot track it: wait it out rather than share it
+      cudaGetLastError();
+      cudaStreamSynchronize(st);
+    }
+  }
+}
+
+static int validate_exchange(vmvo_ctx* ctx, const vmvo_exchange* ex) {
+  if (!ex) return VMVO_OK;
+  if (ex->world < 1 || ex->rank < 0 || ex->rank >= ex->world)
+    return fail(ctx, VMVO_ERR_BAD_ARG, "exchange: rank %d of world %d", ex->rank, ex->world);
+  if (ex->block < 0 || (ex->block > 0 && log2_exact(ex->block) < 0))
+    return fail(ctx, VMVO_ERR_BAD_ARG, "exchange: block %d is not a power of two", ex->block);
+  if (ex->n_peers < 0 || ex->n_peers > VMVO_MAX_MIRRORS || (ex->n_peers > 0 && ex->n_peers != ex->world - 1))
+    return fail(ctx, VMVO_ERR_BAD_ARG, "exchange: n_peers %d (world - 1 = %d, at most %d)", ex->n_peers,
+                ex->world - 1, VMVO_MAX_MIRRORS);
+  for (int q = 0; q < ex->n_peers; ++q)
+    if (!ex->peer_records[q] || ((uintptr_t)ex->peer_records[q] & 15) || !ex->peer_flags[q])
+      return fail(ctx, VMVO_ERR_BAD_ARG, "exchange: peer %d has a NULL or misaligned pointer", q);
+  if (ex->n_peers > 0 && (!ex->local_flags || !ex->epoch))
+    return fail(ctx, VMVO_ERR_BAD_ARG, "exchange: local_flags / epoch is NULL");
+  return VMVO_OK;
+}
+
 static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n_windows,
                             const int64_t* d_win_start, const int32_t* d_win_len,
                             const int32_t* d_win_drive, const double* d_dt_per_drive,
@@ -1593,12 +1699,15 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
                             const double* d_seeds, vmvo_window_result* d_results,
                             double* d_out_poses, double* d_out_steer, double* d_out_vel,
                             int32_t out_stride, float* d_dbg_cost, float* d_dbg_err,
-                            int64_t n_runs, const int64_t* d_run_offsets, void* stream) {
+                            int64_t n_runs, const int64_t* d_run_offsets, const vmvo_exchange* ex,
+                            void* stream) {
   if (!ctx) return VMVO_ERR_BAD_ARG;
   int rc = validate_cfg(ctx, cfg);
   if (rc) return rc;
   if (n_windows < 0) return fail(ctx, VMVO_ERR_BAD_ARG, "n_windows < 0");
   if (n_windows == 0) return VMVO_OK;
+  rc = validate_exchange(ctx, ex);
+  if (rc) return rc;
   if (!d_win_start || !d_win_len || !d_win_drive || !d_dt_per_drive || !d_results)
     return fail(ctx, VMVO_ERR_BAD_ARG, "NULL window plan / dt / result pointer");
   if (cfg->seed_mode == VMVO_SEED_CHAINED && !d_run_offsets)
@@ -1649,21 +1758,15 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
     if (tw == cta_warps || probe.total * (cta_warps / tw) <= 110 * 1024) break;
     tw *= 2;
   }
-  if (const char* ov = getenv("VMVO_TEAM_WARPS")) {  // tuning knob, not part of the ABI
-    const int v = atoi(ov);
-    if ((v == 1 || v == 2 || v == 4 || v == 8 || v == 16) && v <= cta_warps) tw = v;
-  }
+  if (const int v = ctx->tune.team_warps; (v == 1 || v == 2 || v == 4 || v == 8) && v <= cta_warps) tw = v;
   p.team_warps = tw;
   p.cand_cap = kCandPerWarp * tw;
   // the packed / rotation scan: 10 instead of 16 MUFU per 8 hypothesis-steps, at the price of a
   // ~2.5x wider trig term in the band.  Measured: +5 % on 256x256, +2 % on 32x32 (re-scores per
   // window 2.5 -> 2.8); on smaller grids the per-item preamble outweighs the loop.
   p.allow_fast = p.n_items >= 128;
-  if (const char* ov = getenv("VMVO_FAST_SCAN")) p.allow_fast = atoi(ov) != 0;   // test knob
-  if (const char* ov = getenv("VMVO_CAND_CAP")) {  // test knob: forces the list-flush path
-    const int v = atoi(ov);
-    if (v >= 1 && v < p.cand_cap) p.cand_cap = v;
-  }
+  if (ctx->tune.fast_scan >= 0) p.allow_fast = ctx->tune.fast_scan != 0;                 // test hook
+  if (ctx->tune.cand_cap >= 1 && ctx->tune.cand_cap < p.cand_cap) p.cand_cap = ctx->tune.cand_cap;   // test hook
   const int threads = tw * 32;
   // accelerations one pass can touch: items [pass*T, pass*T + T) span at most this many chunks
   int chunks = chunks_per_pass(threads, p.gs);
@@ -1716,19 +1819,32 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
   p.n_windows = n_windows;
   p.dbg_cost = d_dbg_cost;
   p.dbg_err = d_dbg_err;
-  p.n_mirrors = ctx->n_mirrors;
-  p.mirror_off = ctx->mirror_off;
-  for (int q = 0; q < VMVO_MAX_MIRRORS; ++q)
-    p.mirrors[q] = q < ctx->n_mirrors ? (vmvo_window_result*)ctx->mirrors[q] : nullptr;
   p.run_offsets = (const long long*)d_run_offsets;
   p.n_runs = d_run_offsets ? n_runs : 0;
+  // the window deal and the record exchange of this call (vmvo_exchange)
+  const bool dealt = ex && ex->world > 1;
+  p.sh_world = dealt ? ex->world : 1;
+  p.sh_rank = dealt ? ex->rank : 0;
+  p.sh_block_sh = dealt && ex->block > 0 ? log2_exact(ex->block) : -1;
+  p.n_mirrors = ex ? ex->n_peers : 0;
+  for (int q = 0; q < VMVO_MAX_MIRRORS; ++q)
+    p.mirrors[q] = q < p.n_mirrors ? (vmvo_window_result*)ex->peer_records[q] : nullptr;
+  p.epoch = ex ? ex->epoch : nullptr;
+  if (p.run_offsets) {          // whole runs are dealt: run r to rank r % world
+    p.n_local = p.n_runs > p.sh_rank ? (p.n_runs - p.sh_rank + p.sh_world - 1) / p.sh_world : 0;
+  } else if (dealt && p.sh_block_sh >= 0) {
+    const long long nb = (n_windows + ex->block - 1) / ex->block;      // blocks of the global list
+    const long long mine = nb > p.sh_rank ? (nb - p.sh_rank + p.sh_world - 1) / p.sh_world : 0;
+    p.n_local = mine * ex->block;
+  } else {
+    p.n_local = n_windows;
+  }
 
   cudaStream_t st = (cudaStream_t)stream;
-  VMVO_CUDA(ctx, cudaSetDevice(ctx->device));
-  // one of 64 queue heads per launch so launches on different streams do not share one
-  unsigned long long* counter = ctx->d_work_counter + 2 * (ctx->launches & 63);
-  VMVO_CUDA(ctx, cudaMemsetAsync(counter, 0, 2 * sizeof(unsigned long long), st));   // head + slot count
-  p.work_counter = counter;
+  VMVO_ON_DEVICE(ctx);
+  cudaStreamCaptureStatus capture = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &capture);
+  const bool capturing = capture != cudaStreamCaptureStatusNone;
 
   // deferred windows: a slot per window up to a 64 MiB budget.  Not with chained seeds (the next
   // window needs this one's optimum at once), rollout outputs or the debug export.
@@ -1739,41 +1855,30 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
   // ~30 us, a list of 32 near-ties another ~35 us); an eight-warp team on a dense grid re-scores
   // faster than the dump and the CTA of the second kernel would (measured: -5 %).
   p.defer_min = tw <= 2 ? 8 : 0;
-  if (const char* ov = getenv("VMVO_DEFER_MIN")) p.defer_min = atoi(ov);   // test knob; 0 = never
+  if (ctx->tune.defer_min >= 0) p.defer_min = ctx->tune.defer_min;   // test hook; 0 = never
+  size_t slot_bytes = 0, need = 0;
+  long long slots = 0;
   if (p.defer_min > 0 && !d_run_offsets && !d_out_poses && !d_out_steer && !d_out_vel && !d_dbg_cost) {
     const int n_arr = 2 + ((use_vo && use_gps) ? 2 : 0) + (use_imu ? 1 : 0);
-    const size_t slot_bytes = ((size_t)kDeferHdrBytes + (size_t)n_arr * p.maxp * 8 + (size_t)p.cand_cap * 8 + 127) & ~(size_t)127;
-    long long slots = n_windows;
+    slot_bytes = ((size_t)kDeferHdrBytes + (size_t)n_arr * p.maxp * 8 + (size_t)p.cand_cap * 8 + 127) & ~(size_t)127;
+    slots = p.run_offsets ? 0 : (p.n_local < n_windows ? p.n_local : n_windows);
     const long long budget = (64LL << 20) / (long long)slot_bytes;
     if (slots > budget) slots = budget;
-    size_t need = (size_t)slots * slot_bytes;
-    int have = -1;
-    for (int q = 0; q < ctx->n_defer; ++q)
-      if (ctx->defer_bytes[q] >= need) { have = q; break; }
-    if (have < 0) {
-      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-      cudaStreamIsCapturing(st, &cs);
-      if (cs == cudaStreamCaptureStatusNone && ctx->n_defer < 8) {
-        void* buf = nullptr;
-        if (cudaMalloc(&buf, need) == cudaSuccess) {
-          have = ctx->n_defer++;
-          ctx->d_defer[have] = (unsigned char*)buf;
-          ctx->defer_bytes[have] = need;
-        } else {
-          cudaGetLastError();    // no room: search without deferral
-        }
-      } else if (ctx->n_defer > 0) {   // under capture (or out of table entries): the largest buffer there is
-        have = 0;
-        for (int q = 1; q < ctx->n_defer; ++q)
-          if (ctx->defer_bytes[q] > ctx->defer_bytes[have]) have = q;
-        slots = (long long)(ctx->defer_bytes[have] / slot_bytes);
-      }
-    }
-    if (have >= 0 && slots > 0) {
-      p.defer_buf = ctx->d_defer[have];
+    need = (size_t)slots * slot_bytes;
+  }
+  vmvo_launch_slot* ls = acquire_launch_slot(ctx, need, capturing);
+  if (!ls)
+    return fail(ctx, VMVO_ERR_UNSUPPORTED, "%d searches of this ctx are in flight or captured in graphs: "
+                "no launch slot left", kLaunchSlots);
+  VMVO_CUDA(ctx, cudaMemsetAsync(ls->d_counters, 0, 2 * sizeof(unsigned long long), st));   // head + slot count
+  p.work_counter = ls->d_counters;
+  if (need > 0 && ls->d_defer) {
+    if (ls->defer_bytes < need) slots = (long long)(ls->defer_bytes / slot_bytes);
+    if (slots > 0) {
+      p.defer_buf = ls->d_defer;
       p.defer_slots = (int)(slots > 0x7fffffff ? 0x7fffffff : slots);
       p.defer_slot_bytes = (int)slot_bytes;
-      p.defer_count = reinterpret_cast<unsigned*>(counter + 1);
+      p.defer_count = reinterpret_cast<unsigned*>(ls->d_counters + 1);
     }
   }
 
@@ -1783,8 +1888,10 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
                    : launch_search<8, 8, 2, true, false, SF>(ctx, p, st))                \
         : (use_imu ? launch_search<8, 8, 2, false, true, SF>(ctx, p, st)                 \
                    : launch_search<8, 8, 2, false, false, SF>(ctx, p, st)))
-  return f64 ? VMVO_LAUNCH(double) : VMVO_LAUNCH(float);
+  rc = f64 ? VMVO_LAUNCH(double) : VMVO_LAUNCH(float);
 #undef VMVO_LAUNCH
+  release_launch_slot(ctx, ls, st, capturing);
+  return rc;
 }
 
 }  // namespace vmvo
@@ -1800,7 +1907,7 @@ extern "C" int vmvo_grid_search_f32(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, i
                                     int32_t out_stride, void* stream) {
   return grid_search_impl(ctx, cfg, n_windows, d_win_start, d_win_len, d_win_drive, d_dt_per_drive,
                           d_vo, d_gps, d_imu, false, d_seeds, d_results, d_out_poses, d_out_steer,
-                          d_out_vel, out_stride, nullptr, nullptr, 0, nullptr, stream);
+                          d_out_vel, out_stride, nullptr, nullptr, 0, nullptr, nullptr, stream);
 }
 
 extern "C" int vmvo_grid_search_f64(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n_windows,
@@ -1812,7 +1919,7 @@ extern "C" int vmvo_grid_search_f64(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, i
                                     int32_t out_stride, void* stream) {
   return grid_search_impl(ctx, cfg, n_windows, d_win_start, d_win_len, d_win_drive, d_dt_per_drive,
                           d_vo, d_gps, d_imu, true, d_seeds, d_results, d_out_poses, d_out_steer,
-                          d_out_vel, out_stride, nullptr, nullptr, 0, nullptr, stream);
+                          d_out_vel, out_stride, nullptr, nullptr, 0, nullptr, nullptr, stream);
 }
 
 // stream_f64 != 0: the pose streams are double4 / double (as in vmvo_grid_search_f64)
@@ -1828,7 +1935,7 @@ extern "C" int vmvo_grid_search_chained(vmvo_ctx* ctx, const vmvo_search_cfg* cf
   return grid_search_impl(ctx, cfg, n_windows, d_win_start, d_win_len, d_win_drive, d_dt_per_drive,
                           d_vo, d_gps, d_imu, stream_f64 != 0, nullptr, d_results, d_out_poses,
                           d_out_steer, d_out_vel, out_stride, nullptr, nullptr, n_runs, d_run_offsets,
-                          stream);
+                          nullptr, stream);
 }
 
 extern "C" int vmvo_grid_search_debug_f32(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n_windows,
@@ -1840,5 +1947,17 @@ extern "C" int vmvo_grid_search_debug_f32(vmvo_ctx* ctx, const vmvo_search_cfg* 
   if (!d_scan_cost || !d_scan_err) return fail(ctx, VMVO_ERR_BAD_ARG, "debug outputs are NULL");
   return grid_search_impl(ctx, cfg, n_windows, d_win_start, d_win_len, d_win_drive, d_dt_per_drive,
                           d_vo, d_gps, d_imu, false, d_seeds, d_results, nullptr, nullptr, nullptr, 0,
-                          d_scan_cost, d_scan_err, 0, nullptr, stream);
+                          d_scan_cost, d_scan_err, 0, nullptr, nullptr, stream);
+}
+
+extern "C" int vmvo_grid_search_sharded(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n_windows,
+                                        const int64_t* d_win_start, const int32_t* d_win_len,
+                                        const int32_t* d_win_drive, const double* d_dt_per_drive,
+                                        const void* d_vo, const void* d_gps, const void* d_imu,
+                                        int32_t stream_f64, const double* d_seeds, int64_t n_runs,
+                                        const int64_t* d_run_offsets, vmvo_window_result* d_results,
+                                        const vmvo_exchange* ex, void* stream) {
+  return grid_search_impl(ctx, cfg, n_windows, d_win_start, d_win_len, d_win_drive, d_dt_per_drive,
+                          d_vo, d_gps, d_imu, stream_f64 != 0, d_seeds, d_results, nullptr, nullptr,
+                          nullptr, 0, nullptr, nullptr, n_runs, d_run_offsets, ex, stream);
 }

@@ -321,10 +321,10 @@ def optimize_android_drives(folders: Sequence[Union[str, os.PathLike]], config=N
     Returns ``(SearchOutput, trajectory float64 [4, F], WindowPlan, DriveSet)``."""
     from dataclasses import replace
 
-    from .optimize import DEFAULT_CFG, HORIZON_TIME
+    from .optimize import HORIZON_TIME, REFERENCE_CFG
     from .search import optimize_drives
 
-    cfg = config if config is not None else DEFAULT_CFG
+    cfg = config if config is not None else REFERENCE_CFG
     ds, fps = prepare_android_drives(load_android_drives_device(folders), scale, smoothen_window)
     horizons = {int(HORIZON_TIME * f) for f in fps}              # optimize_trajectory_v2.py:35-42
     if len(horizons) != 1:

@@ -2,10 +2,12 @@
 vmvo/scripts/optimize_trajectory_v2.py:24-148.
 
 ``optimize_trajectory(vo_trajectory, gps_trajectory, model)`` keeps the reference's call
-shape and write-back semantics (quirks D4-D7 of DESIGN.md); the per-window SLSQP solve is
-replaced by the hypothesis-grid argmin, and windows, search, write-back and blends all run
-on the GPU.  ``REFERENCE_CFG`` selects the reference's own objective (GPS target,
-arc-length decimation, mpc.py:35-40); the default scores against the raw VO window.
+shape, objective and write-back semantics (quirks D4-D7, D10 of DESIGN.md); the per-window SLSQP
+solve is replaced by the hypothesis-grid argmin, and windows, search, write-back and blends all
+run on the GPU.  The default configuration is ``REFERENCE_CFG`` -- the reference's own objective:
+the GPS sub-trajectory as target, GPS velocity seeds, arc-length decimation (mpc.py:35-40,
+optimize_trajectory_v2.py:57-74).  ``VO_CFG`` (scoring against the raw VO window, the search spec
+of BASELINE's north star) is an explicit opt-in through ``config=``.
 """
 from __future__ import annotations
 
@@ -20,8 +22,9 @@ from .search import DriveSet, SearchConfig, optimize_drives
 
 HORIZON_TIME = 3.0  # s, optimize_trajectory_v2.py:35
 
-DEFAULT_CFG = SearchConfig(window_mode="time", target_mode="time", primary="vo",
-                           w_vo=1.0, w_gps=0.0, w_imu=0.0)
+VO_CFG = SearchConfig(window_mode="time", target_mode="time", primary="vo",
+                      w_vo=1.0, w_gps=0.0, w_imu=0.0)
+DEFAULT_CFG = VO_CFG      # (round-1 name of the VO-scoring configuration; NOT the facade's default)
 REFERENCE_CFG = SearchConfig(window_mode="time", target_mode="traverse", primary="gps",
                              w_vo=0.0, w_gps=1.0, w_imu=0.0)
 
@@ -40,9 +43,13 @@ def _stream(traj: Trajectory, n: int) -> np.ndarray:
 def optimize_trajectory(vo_trajectory: Trajectory, gps_trajectory: Trajectory,
                         model: Optional[BicycleModel] = None,
                         config: Optional[SearchConfig] = None, imu_yaw=None,
-                        return_details: bool = False):
-    """Returns the optimised ``Trajectory`` (a modified copy of ``vo_trajectory``)."""
-    cfg = config if config is not None else DEFAULT_CFG
+                        return_details: bool = False, honour_model_limits: bool = False):
+    """Returns the optimised ``Trajectory`` (a modified copy of ``vo_trajectory``).
+
+    Like the reference, ``model`` is not consulted (quirk D10, optimize_trajectory_v2.py:25,44: a
+    fresh ``BicycleModel()`` with the module constants is used) unless ``honour_model_limits``
+    asks for its steering / acceleration / steering-rate limits to bound the grid."""
+    cfg = config if config is not None else REFERENCE_CFG
     N = min(len(vo_trajectory), len(gps_trajectory))
     gps_time = np.asarray(gps_trajectory.time, dtype=np.float64)
     # optimize_trajectory_v2.py:35-42
@@ -51,8 +58,7 @@ def optimize_trajectory(vo_trajectory: Trajectory, gps_trajectory: Trajectory,
     dt = 1.0 / FPS
     if cfg.window_mode == "time":
         cfg = replace(cfg, horizon_time=HORIZON_TIME, horizon_frames=horizon)
-    if model is not None:
-        # the reference ignores ``model`` (quirk D10); limits are honoured here
+    if model is not None and honour_model_limits:
         cfg = replace(cfg, max_steer=float(model.max_steer), max_accel=float(model.max_accel),
                       max_steer_rate=float(model.max_steer_rate))
 
@@ -69,6 +75,8 @@ def optimize_trajectory(vo_trajectory: Trajectory, gps_trajectory: Trajectory,
                                   stream_dtype=np.float64)
     so, traj, plan = optimize_drives(cfg, drives)
     rec = so.records()
+    if np.any(rec["status"] & 8):
+        raise AssertionError("No frames found")                  # schema.py:122
     if np.any(rec["status"] & 4):
         raise ValueError("a window holds more poses than max_window_poses; raise it in the config")
     if np.any(rec["n_steps"] == 0):

@@ -227,14 +227,41 @@ class SearchOutput:
 
 def grid_search(cfg: SearchConfig, drives: DriveSet, plan: WindowPlan,
                 window_range: Optional[Tuple[int, int]] = None, seeds: Optional[torch.Tensor] = None,
-                want_rollouts: bool = False, out: Optional[torch.Tensor] = None) -> SearchOutput:
+                want_rollouts: bool = False, out: Optional[torch.Tensor] = None,
+                exchange: Optional[_lib.Exchange] = None) -> SearchOutput:
     """The fused search over windows [lo, hi) of the plan (default: all).
 
     ``out``: optional uint8 [n, 64] tensor the records are written into (e.g. this rank's
     slice of the gather buffer, scheduler.py).
+
+    ``exchange`` (``scheduler.PeerGather.exchange``): the multi-GPU form -- this rank searches the
+    windows the block-cyclic deal gives it, ``out`` must be the gather buffer (one record per
+    window of the WHOLE plan) and every record is also stored into the peers' buffers
+    (``vmvo_grid_search_sharded``).
     """
     ctx = _lib.context(drives.device.index)
     c = cfg.to_c()
+    if exchange is not None:
+        if window_range is not None or want_rollouts:
+            raise ValueError("a sharded search covers the whole plan and returns records only")
+        n, dev = plan.n_windows, drives.device
+        if out is None or out.shape != (n, 64) or out.dtype != torch.uint8 or not out.is_contiguous():
+            raise ValueError("a sharded search writes into the gather buffer: out = uint8 [n_windows, 64]")
+        d_seeds = None
+        if seeds is not None:
+            d_seeds = _as_dev(seeds, torch.float64, dev)
+            if d_seeds.shape != (n, 2):
+                raise ValueError("seeds must be [n_windows, 2]")
+        chained = cfg.seed_mode == "chained"
+        if n:
+            ctx.check(ctx.lib.vmvo_grid_search_sharded(
+                ctx.handle, C.byref(c), n, _lib.ptr(plan.win_start), _lib.ptr(plan.win_len),
+                _lib.ptr(plan.win_drive), _lib.ptr(drives.dt), _lib.ptr(drives.vo), _lib.ptr(drives.gps),
+                _lib.ptr(drives.imu), int(drives.f64), _lib.ptr(d_seeds),
+                len(plan.window_offsets) - 1 if chained else 0,
+                _lib.ptr(plan.d_window_offsets) if chained else None, _lib.ptr(out),
+                C.byref(exchange), _lib.stream_ptr(dev)), "vmvo_grid_search_sharded")
+        return SearchOutput(results=out)
     lo, hi = (0, plan.n_windows) if window_range is None else window_range
     n = hi - lo
     dev = drives.device
@@ -301,8 +328,14 @@ def grid_search_debug(cfg: SearchConfig, drives: DriveSet, plan: WindowPlan,
 
 
 def write_back(cfg: SearchConfig, drives: DriveSet, plan: WindowPlan, results: torch.Tensor,
-               blend_gps: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """a12: float64 [4, F] = x, y, theta, velocity (optimize_trajectory_v2.py:32-33,122-137)."""
+               blend_gps: bool = True, out: Optional[torch.Tensor] = None,
+               frame_range: Optional[Tuple[int, int]] = None,
+               exchange: Optional[_lib.Exchange] = None) -> torch.Tensor:
+    """a12: float64 [4, F] = x, y, theta, velocity (optimize_trajectory_v2.py:32-33,122-137).
+
+    ``frame_range`` = (lo, hi): only those frames of ``out`` are written (a rank's share of the
+    trajectory); ``exchange``: the kernel publishes this rank's arrival word and waits for the
+    peers' before reading ``results``, the gather buffer of the sharded search."""
     ctx = _lib.context(drives.device.index)
     c = cfg.to_c()
     if drives.vo is None:
@@ -314,6 +347,16 @@ def write_back(cfg: SearchConfig, drives: DriveSet, plan: WindowPlan, results: t
     elif out.shape != (4, drives.n_frames) or out.dtype != torch.float64 or not out.is_contiguous():
         raise ValueError("out must be a contiguous float64 [4, n_frames] tensor")
     gps = drives.gps if blend_gps else None
+    if frame_range is not None or exchange is not None:
+        lo, hi = (0, drives.n_frames) if frame_range is None else frame_range
+        ctx.check(ctx.lib.vmvo_write_back_range(
+            ctx.handle, C.byref(c), drives.n_drives, drives.n_frames, int(lo), int(hi),
+            _lib.ptr(drives.d_drive_offsets), _lib.ptr(plan.d_window_offsets), _lib.ptr(drives.dt),
+            _lib.ptr(drives.vo), _lib.ptr(gps), int(drives.f64), _lib.ptr(results), _lib.ptr(out[0]),
+            _lib.ptr(out[1]), _lib.ptr(out[2]), _lib.ptr(out[3]),
+            None if exchange is None else C.byref(exchange), _lib.stream_ptr(drives.device)),
+            "vmvo_write_back_range")
+        return out
     name = "vmvo_write_back_f64" if drives.f64 else "vmvo_write_back_f32"
     ctx.check(getattr(ctx.lib, name)(
         ctx.handle, C.byref(c), drives.n_drives, drives.n_frames, _lib.ptr(drives.d_drive_offsets),
@@ -341,19 +384,37 @@ class DrivePipeline:
     The pose streams and stamps are read from ``drives`` at replay time, so new data of the
     same shape can be copied into ``drives.vo`` / ``.gps`` / ``.imu`` / ``.time`` between passes.
     ``records`` (uint8 [n_windows, 64]) may be a slice of a larger gather buffer.
+
+    ``gather`` (a ``scheduler.PeerGather`` over the plan's windows): the multi-GPU form.  Every rank
+    builds the same pipeline over the same drives; a pass searches this rank's share of the global
+    window list, the records reach every rank from inside the search, and the write-back (of
+    ``frame_range``, this rank's share of the frames; default all) consumes ALL ranks' records
+    behind the arrival words -- still four launches and no collective.  Construction and every
+    ``run`` are collective over the gather's group (each pass waits for the peers' records).
     """
 
     KERNELS_PER_PASS = 4
 
     def __init__(self, cfg: SearchConfig, drives: DriveSet, blend_gps: bool = True,
                  records: Optional[torch.Tensor] = None, use_graph: bool = True,
-                 split: bool = False):
+                 split: bool = False, gather=None, frame_range: Optional[Tuple[int, int]] = None,
+                 record_range: Optional[Tuple[int, int]] = None):
         if cfg.seed_mode == "given":
             raise ValueError("DrivePipeline derives seeds from the data (seed_mode data / chained)")
         self.cfg, self.drives, self.blend_gps = cfg, drives, blend_gps
         self.plan = plan_windows(cfg, drives)
         dev = drives.device
         n = self.plan.n_windows
+        self.gather, self.frame_range = gather, frame_range
+        # what a streaming caller reads back per pass (DriveStream): the frames this pipeline writes
+        # and the records of ``record_range`` (default: all)
+        self.record_range = record_range if record_range is not None else (0, n)
+        if gather is not None:
+            if records is not None or split:
+                raise ValueError("with a gather the records live in its buffer and the pass is one graph")
+            if gather.n != n:
+                raise ValueError(f"the gather holds {gather.n} records, the plan has {n} windows")
+            records = gather.buffer
         self.records = records if records is not None else torch.empty((n, 64), dtype=torch.uint8, device=dev)
         self.trajectory = torch.empty((4, drives.n_frames), dtype=torch.float64, device=dev)
         self.graphs = None
@@ -375,11 +436,13 @@ class DrivePipeline:
 
     def _search(self):
         plan_windows(self.cfg, self.drives, into=self.plan)
-        grid_search(self.cfg, self.drives, self.plan, out=self.records)
+        grid_search(self.cfg, self.drives, self.plan, out=self.records,
+                    exchange=None if self.gather is None else self.gather.exchange)
 
     def _write_back(self):
         write_back(self.cfg, self.drives, self.plan, self.records, blend_gps=self.blend_gps,
-                   out=self.trajectory)
+                   out=self.trajectory, frame_range=self.frame_range,
+                   exchange=None if self.gather is None else self.gather.exchange)
 
     def run_search(self) -> torch.Tensor:
         if self.graphs is None:
@@ -445,8 +508,9 @@ class DriveStream:
                     else DrivePipeline(cfg, d, blend_gps=blend_gps))
             self.sets.append(d)
             self.pipes.append(pipe)
-            self.host.append((torch.empty(tuple(pipe.records.shape), dtype=torch.uint8).pin_memory(),
-                              torch.empty(tuple(pipe.trajectory.shape), dtype=torch.float64).pin_memory()))
+            (rlo, rhi), (flo, fhi) = pipe.record_range, pipe.frame_range or (0, d.n_frames)
+            self.host.append((torch.empty((rhi - rlo, 64), dtype=torch.uint8).pin_memory(),
+                              torch.empty((4, fhi - flo), dtype=torch.float64).pin_memory()))
         self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         self.n = 0                      # steps computed so far
         self.loaded = False             # inputs of step self.n are resident
@@ -459,8 +523,17 @@ class DriveStream:
                 getattr(d, name).copy_(src, non_blocking=True)
 
     def _d2h(self, b: int) -> None:
-        self.host[b][0].copy_(self.pipes[b].records, non_blocking=True)
-        self.host[b][1].copy_(self.pipes[b].trajectory, non_blocking=True)
+        pipe = self.pipes[b]
+        (rlo, rhi), fr = pipe.record_range, pipe.frame_range
+        self.host[b][0].copy_(pipe.records[rlo:rhi], non_blocking=True)
+        if fr is None:
+            self.host[b][1].copy_(pipe.trajectory, non_blocking=True)
+        else:                      # this rank's share of the frames: four contiguous row pieces
+            for r in range(4):
+                self.host[b][1][r].copy_(pipe.trajectory[r, fr[0]:fr[1]], non_blocking=True)
+
+    def d2h_bytes(self) -> int:
+        return int(self.host[0][0].numel() + self.host[0][1].numel() * 8)
 
     def prime(self, inputs) -> None:
         """Copy the first batch in (nothing to overlap it with yet)."""
