@@ -278,7 +278,7 @@ def measure_workload(workload, dev, world, rank, timer, steps, warmup, seed0=BAS
     out = {"workload": workload, "cfg": cfg, "n_frames": n_frames, "n_win": n_win, "hsteps": hsteps,
            "ms_per_step": ms_per_step, "value": hsteps / (ms_per_step * 1e-3),
            "rescored_per_window": float(rec["n_rescored"].mean()),
-           "launches_per_step": DrivePipeline.KERNELS_PER_PASS}
+           "launches_per_step": last.kernels_per_pass}
 
     # the search alone on one GPU over the same windows: kernel time for the roofline, and (N > 1)
     # what every rank's gathered buffer must hold

@@ -208,17 +208,21 @@ typedef struct vmvo_exchange {
   uint32_t* epoch;                           /* [0] step counter, [1] wait-timeout indicator      */
 } vmvo_exchange;
 
-/* The fused search over this rank's share of the n_windows GLOBAL windows (plan arrays and
- * d_results cover all of them).  stream_f64 as in vmvo_grid_search_chained; d_seeds (VMVO_SEED_GIVEN)
- * and d_run_offsets / n_runs (VMVO_SEED_CHAINED: whole runs are dealt, run r to rank r % world) may
- * be NULL / 0 otherwise.  ex == NULL or ex->world <= 1: every window, no exchange.             */
-int vmvo_grid_search_sharded(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n_windows,
-                             const int64_t* d_win_start, const int32_t* d_win_len,
+/* The fused search over this rank's share of the n_windows GLOBAL windows of n_drives drives
+ * (d_results, and the plan arrays when given, cover all of them).  d_drive_offsets / d_window_offsets
+ * [n_drives + 1] are the frame and window prefix sums of vmvo_plan_windows.  The plan arrays may be
+ * all NULL in VMVO_WINDOW_FRAMES mode: the kernel then derives each window's extent itself (window i
+ * of a drive = poses i .. i + window_frames, optimize_trajectory_v2.py:48-56) and the step needs no
+ * planning launch.  stream_f64 as in vmvo_grid_search_chained; d_seeds only for VMVO_SEED_GIVEN; with
+ * VMVO_SEED_CHAINED whole drives are dealt (drive d to rank d % world) and walked in order.
+ * ex == NULL or ex->world <= 1: every window, no exchange -- the single-GPU pipeline's entry point. */
+int vmvo_grid_search_sharded(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int32_t n_drives,
+                             const int64_t* d_drive_offsets, const int64_t* d_window_offsets,
+                             int64_t n_windows, const int64_t* d_win_start, const int32_t* d_win_len,
                              const int32_t* d_win_drive, const double* d_dt_per_drive,
                              const void* d_vo, const void* d_gps, const void* d_imu,
-                             int32_t stream_f64, const double* d_seeds, int64_t n_runs,
-                             const int64_t* d_run_offsets, vmvo_window_result* d_results,
-                             const vmvo_exchange* ex, void* stream);
+                             int32_t stream_f64, const double* d_seeds,
+                             vmvo_window_result* d_results, const vmvo_exchange* ex, void* stream);
 /* Arrival word of the current step to every peer / wait for every peer's (see above).          */
 int vmvo_exchange_publish(vmvo_ctx* ctx, const vmvo_exchange* ex, void* stream);
 int vmvo_exchange_wait(vmvo_ctx* ctx, const vmvo_exchange* ex, void* stream);
@@ -379,7 +383,7 @@ int vmvo_tan_steer_f32(vmvo_ctx* ctx, int64_t n, const float* d_delta, float* d_
 int vmvo_peak_probe(vmvo_ctx* ctx, int32_t kind, int32_t blocks, int32_t threads,
                     int32_t iters, float* d_sink, void* stream);
 /* Test / tuning hook, NOT part of the product surface: overrides one of the launch heuristics of
- * this ctx ("team_warps", "fast_scan", "cand_cap", "defer_min", "max_ctas_per_sm"); value < 0
+ * this ctx ("team_warps", "fast_scan", "cand_cap", "defer_min", "max_ctas_per_sm", "defer_warps"); value < 0
  * restores the library's own choice.  The environment is never consulted.                      */
 int vmvo_debug_set_tuning(vmvo_ctx* ctx, const char* key, int32_t value);
 /* kernels launched by this ctx since creation (for bench.py's gpu_launches)             */

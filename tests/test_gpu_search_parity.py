@@ -183,3 +183,29 @@ def test_chained_seed_mode(cuda_device, target_mode, stream):
     assert rec["s_seed"][0] == 0.0 and rec["s_seed"][35] == 0.0 and np.any(rec["s_seed"] != 0.0)
     with pytest.raises(ValueError, match="whole drives"):
         grid_search(cfg, drives, plan, window_range=(0, 20))
+
+
+def test_search_without_planned_extents_matches_planned(cuda_device):
+    """Frames mode: the search kernel derives each window's extent itself (no planning launch);
+    same records as with the plan of vmvo_plan_windows, ragged drives and a drive without windows
+    included; data and chained seeds."""
+    batch = synthetic_drives(4, 100, seed=31)
+    lens = [80, 30, 24, 100]
+    t = [batch.time[d][:n] for d, n in enumerate(lens)]
+    vo = [batch.vo[d][:n] for d, n in enumerate(lens)]
+    for seed_mode in ("data", "chained"):
+        cfg = SearchConfig(grid_v=8, grid_s=16, window_frames=12, seed_mode=seed_mode)
+        drives = DriveSet.from_arrays(t, [batch.dt] * 4, vo=vo)
+        plan = plan_windows(cfg, drives)
+        bare = plan_windows(cfg, drives, extents=False)
+        assert bare.win_start is None and bare.window_offsets == plan.window_offsets == [0, 56, 62, 62, 138]
+        a = grid_search(cfg, drives, plan).records()
+        b = grid_search(cfg, drives, bare).records()
+        for f in ("best_idx", "n_steps", "status", "best_cost", "v_seed", "s_seed", "x1", "y1", "theta1"):
+            np.testing.assert_array_equal(a[f], b[f])
+        if seed_mode == "data":
+            for d in (0, 1, 3):
+                lo, hi = plan.window_offsets[d], plan.window_offsets[d + 1]
+                assert_records_match(b[lo:hi], oracle_windows(cfg, t[d], batch.dt, vo[d]))
+    with pytest.raises(ValueError, match="frames"):
+        plan_windows(SearchConfig(window_mode="time"), drives, extents=False)

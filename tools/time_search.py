@@ -15,28 +15,44 @@ import bench  # noqa: E402
 from vehiclemodelvisualodometry_b200 import DriveSet, SearchConfig, grid_search, plan_windows  # noqa: E402
 from vehiclemodelvisualodometry_b200.synthetic import synthetic_drives  # noqa: E402
 
-which = sys.argv[1:] or ["cfg2", "cfg3"]
+# key=value arguments go to the library's tuning hook (e.g. defer_warps=8); "eager" times eager
+# launches through ctypes instead of a replayed CUDA graph of the search's launches
+tune = dict(a.split("=") for a in sys.argv[1:] if "=" in a)
+eager = "eager" in sys.argv[1:]
+which = [a for a in sys.argv[1:] if "=" not in a and a != "eager"] or ["cfg2", "cfg3"]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+from vehiclemodelvisualodometry_b200 import _lib  # noqa: E402
+for k_, v_ in tune.items():
+    _lib.context(0).set_tuning(k_, int(v_))
 
 
 def timeit(name, cfg, drives, reps):
-    plan = plan_windows(cfg, drives)
+    plan = plan_windows(cfg, drives, extents=False)
+    out = torch.empty((plan.n_windows, 64), dtype=torch.uint8, device="cuda")
     for _ in range(3):
-        so = grid_search(cfg, drives, plan)
+        so = grid_search(cfg, drives, plan, out=out)
     torch.cuda.synchronize()
+    g = None
+    if not eager:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            grid_search(cfg, drives, plan, out=out)
     ms = []
     for _ in range(reps):
         flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        so = grid_search(cfg, drives, plan)
+        if g is None:
+            grid_search(cfg, drives, plan, out=out)
+        else:
+            g.replay()
         b.record()
         torch.cuda.synchronize()
         ms.append(a.elapsed_time(b))
     rec = so.records()
     hs = cfg.grid_v * cfg.grid_s * int(rec["n_steps"].astype(np.int64).sum())
     med = float(np.median(ms))
-    print(f"{name}: {med:.4f} ms (min {min(ms):.4f})  {hs / med / 1e9:.3f} T hyp-steps/s  windows {len(rec)}  "
+    print(f"{name} {tune or ''}: {med:.4f} ms (min {min(ms):.4f})  {hs / med / 1e9:.3f} T hyp-steps/s  windows {len(rec)}  "
           f"rescored mean {rec['n_rescored'].mean():.2f} p99 {np.percentile(rec['n_rescored'], 99):.0f} "
           f"max {rec['n_rescored'].max()}", flush=True)
 

@@ -108,8 +108,8 @@ _SIGNATURES = {
                                       _c_vp]),
     "vmvo_csv_parse_f64": (C.c_int, [_c_vp, _c_vp, _c_i32, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp,
                                      _c_i32, _c_i32, _c_vp, _c_vp, _c_vp, _c_vp]),
-    "vmvo_grid_search_sharded": (C.c_int, [_c_vp, C.POINTER(SearchCfg), _c_i64, _c_vp, _c_vp, _c_vp, _c_vp,
-                                           _c_vp, _c_vp, _c_vp, _c_i32, _c_vp, _c_i64, _c_vp, _c_vp,
+    "vmvo_grid_search_sharded": (C.c_int, [_c_vp, C.POINTER(SearchCfg), _c_i32, _c_vp, _c_vp, _c_i64, _c_vp,
+                                           _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i32, _c_vp, _c_vp,
                                            C.POINTER(Exchange), _c_vp]),
     "vmvo_exchange_publish": (C.c_int, [_c_vp, C.POINTER(Exchange), _c_vp]),
     "vmvo_exchange_wait": (C.c_int, [_c_vp, C.POINTER(Exchange), _c_vp]),

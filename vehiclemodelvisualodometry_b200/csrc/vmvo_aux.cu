@@ -397,14 +397,14 @@ extern "C" int vmvo_ctx_create(int device, vmvo_ctx** out) {
   ctx->err[0] = 0;
   ctx->d_counters = nullptr;
   ctx->slot_mutex = new std::mutex();
-  ctx->tune = vmvo_tuning{-1, -1, -1, -1, -1};
+  ctx->tune = vmvo_tuning{-1, -1, -1, -1, -1, -1, -1, -1};
   for (int q = 0; q < kLaunchSlots; ++q) ctx->slots[q] = vmvo_launch_slot{nullptr, nullptr, 0, nullptr, false, false};
   DeviceGuard guard(device);
   cudaDeviceProp prop;
   bool ok = guard.err == cudaSuccess && cudaGetDeviceProperties(&prop, device) == cudaSuccess &&
-            cudaMalloc(&ctx->d_counters, kLaunchSlots * 2 * sizeof(unsigned long long)) == cudaSuccess;
+            cudaMalloc(&ctx->d_counters, kLaunchSlots * 4 * sizeof(unsigned long long)) == cudaSuccess;
   for (int q = 0; ok && q < kLaunchSlots; ++q) {
-    ctx->slots[q].d_counters = ctx->d_counters + 2 * q;
+    ctx->slots[q].d_counters = ctx->d_counters + 4 * q;
     ok = cudaEventCreateWithFlags(&ctx->slots[q].done, cudaEventDisableTiming) == cudaSuccess;
   }
   if (!ok) {
@@ -441,7 +441,10 @@ extern "C" int vmvo_debug_set_tuning(vmvo_ctx* ctx, const char* key, int32_t val
             : !strcmp(key, "fast_scan") ? &ctx->tune.fast_scan
             : !strcmp(key, "cand_cap") ? &ctx->tune.cand_cap
             : !strcmp(key, "defer_min") ? &ctx->tune.defer_min
-            : !strcmp(key, "max_ctas_per_sm") ? &ctx->tune.max_ctas_per_sm : nullptr;
+            : !strcmp(key, "max_ctas_per_sm") ? &ctx->tune.max_ctas_per_sm
+            : !strcmp(key, "defer_warps") ? &ctx->tune.defer_warps
+            : !strcmp(key, "cta_teams") ? &ctx->tune.cta_teams
+            : !strcmp(key, "pdl") ? &ctx->tune.pdl : nullptr;
   if (!slot) return fail(ctx, VMVO_ERR_BAD_ARG, "unknown tuning key '%s'", key);
   *slot = value < 0 ? -1 : value;
   return VMVO_OK;

@@ -16,7 +16,7 @@
 // completed, so searches of one ctx on different streams never share scratch.  A launch recorded
 // into a CUDA graph keeps its slot for good (pinned): the graph may be replayed at any time.
 struct vmvo_launch_slot {
-  unsigned long long* d_counters;   // [2]: queue head, deferred-window count
+  unsigned long long* d_counters;   // [4]: queue head, deferred-window count, finished windows, -
   unsigned char* d_defer;
   size_t defer_bytes;
   cudaEvent_t done;
@@ -26,13 +26,13 @@ constexpr int kLaunchSlots = 256;
 
 // test / tuning overrides (vmvo_debug_set_tuning); -1 = the library's own choice
 struct vmvo_tuning {
-  int team_warps, fast_scan, cand_cap, defer_min, max_ctas_per_sm;
+  int team_warps, fast_scan, cand_cap, defer_min, max_ctas_per_sm, defer_warps, cta_teams, pdl;
 };
 
 struct vmvo_ctx {
   int device;
   int sm_count;
-  unsigned long long* d_counters;   // kLaunchSlots pairs
+  unsigned long long* d_counters;   // kLaunchSlots x 4
   vmvo_launch_slot slots[kLaunchSlots];
   std::mutex* slot_mutex;
   long long launches;

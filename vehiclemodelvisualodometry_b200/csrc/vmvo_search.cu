@@ -54,9 +54,12 @@ struct SearchParams {
   // max_accel / (gv - 1) and max_rate / (gs - 1) (0 on a one-point axis), and 1 / L
   double acc_step, rate_step;
   float inv_L;
-  const long long* win_start;
-  const int* win_len;
+  const long long* win_start;   // the window plan (vmvo_plan_windows), or all three NULL: frames mode,
+  const int* win_len;           // extents computed by the fetcher from the offsets below
   const int* win_drive;
+  const long long* drive_off;   // [n_drives + 1] frames
+  const long long* win_off;     // [n_drives + 1] windows
+  int n_drives, window_frames;
   const double* dt_drive;
   const void* vo;        // pose streams: float4 or double4 per frame (kernel template SF)
   const void* gps;
@@ -87,6 +90,12 @@ struct SearchParams {
   unsigned char* defer_buf;
   unsigned* defer_count;
   int defer_slots, defer_slot_bytes, defer_min;
+  // the second kernel runs BESIDE the end of the search (programmatic dependent launch): a parked
+  // window is published through defer_ready[slot] and every finished window counts in windows_done,
+  // so the second kernel knows when slot lists are final without waiting for the grid to drain
+  unsigned* defer_ready;               // [defer_slots], cleared with the counters before the launch
+  unsigned long long* windows_done;
+  long long n_todo;                    // windows this launch completes (this rank's share)
   float* dbg_cost;       // optional [n_windows][gv*gs] FP32 scan costs   (tests only)
   float* dbg_err;        // optional [n_windows][gv*gs] error-band widths (tests only)
 };
@@ -411,8 +420,10 @@ __device__ __forceinline__ void scan_item(int N, int gs, int vd_cols, int j, int
   const float* tl = TL + j;
   const float* vd = VD + m0;
   const float2* df = Df;
+  const int tl_step = gs * 4, vd_step = vd_cols * 4;     // byte strides, computed once (not an IMAD per step)
 #pragma unroll 1
-  for (int k = 1; k <= N; ++k, tl += gs, vd += vd_cols) {
+  for (int k = 1; k <= N; ++k, tl = reinterpret_cast<const float*>(reinterpret_cast<const char*>(tl) + tl_step),
+           vd = reinterpret_cast<const float*>(reinterpret_cast<const char*>(vd) + vd_step)) {
     const float tlk = *tl;
     float v[C];
 #pragma unroll
@@ -486,10 +497,11 @@ __device__ __forceinline__ void scan_item_fast(int N, int gs, int vd_cols, int j
   const float* tl = TL + j;
   const float* vd = VD + m0;
   const float2* df = Df;
+  const int tl_step = gs * 4, vd_step = vd_cols * 4;     // byte strides, computed once (not an IMAD per step)
   // sin / cos of the eight headings of step k (advances A, B)
   auto trig = [&](int k, float2 (&c2)[4], float2 (&s2)[4]) {
     const float tlk = *tl;
-    tl += gs;
+    tl = reinterpret_cast<const float*>(reinterpret_cast<const char*>(tl) + tl_step);
     const float kdt2 = (float)k * dt2;
     A = fmaf(vwdt, tlk, A);
     B = fmaf(kdt2, tlk, B);
@@ -510,7 +522,7 @@ __device__ __forceinline__ void scan_item_fast(int N, int gs, int vd_cols, int j
   auto step = [&](int k, const float2 (&c2)[4], const float2 (&s2)[4]) {
     const float4 va = *reinterpret_cast<const float4*>(vd);
     const float4 vb = *reinterpret_cast<const float4*>(vd + 4);
-    vd += vd_cols;
+    vd = reinterpret_cast<const float*>(reinterpret_cast<const char*>(vd) + vd_step);
     const float2 d = *++df;
     float2 dab = pk(0.f, 0.f);
     if (DUAL) dab = Dab[k];
@@ -609,11 +621,30 @@ vmvo_window_search_kernel(const SearchParams p) {
   const double kd = kDegToRad / p.ratio;   // steering-wheel degrees -> road-wheel radians
 
   auto issue_load = [&](long long w, int buf) {  // the fetcher thread only
-    const long long start = p.win_start[w];
-    int len = p.win_len[w];
+    long long start;
+    int len, drv;
+    if (p.win_start) {
+      start = p.win_start[w];
+      len = p.win_len[w];
+      drv = p.win_drive[w];
+    } else {
+      // frames mode without a plan: window i of drive d covers poses i .. min(i + W, n_d - 1)
+      // (optimize_trajectory_v2.py:48-56 with a frame horizon; what plan_windows_kernel writes)
+      int lo = 0, hi = p.n_drives;           // largest d with win_off[d] <= w
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (p.win_off[mid] <= w) lo = mid; else hi = mid;
+      }
+      drv = lo;
+      const long long i = w - p.win_off[drv], f0 = p.drive_off[drv], n = p.drive_off[drv + 1] - f0;
+      long long e = i + p.window_frames + 1;
+      e = e < n ? e : n;
+      start = f0 + i;
+      len = (int)(e - i);
+    }
     hd->wstart[buf] = start;
     hd->wlen[buf] = len;
-    hd->wdt[buf] = p.dt_drive[p.win_drive[w]];
+    hd->wdt[buf] = p.dt_drive[drv];
     len = len < P ? len : P;
     len = len > 0 ? len : 0;
     const unsigned bytes = (unsigned)len * (unsigned)sizeof(Pose4);
@@ -632,6 +663,10 @@ vmvo_window_search_kernel(const SearchParams p) {
   auto store_record = [&](long long w, const vmvo_window_result& r) {
     p.results[w] = r;
     for (int q = 0; q < p.n_mirrors; ++q) p.mirrors[q][w] = r;
+    if (p.defer_ready) {       // one finished window (the second kernel watches the count)
+      __threadfence();
+      atomicAdd(p.windows_done, 1ULL);
+    }
   };
 
   const bool chained = p.run_offsets != nullptr;
@@ -666,6 +701,8 @@ vmvo_window_search_kernel(const SearchParams p) {
   const bool fetcher = tid == T - 32;
   // a sharded search advances the exchange's step counter (nothing reads it while a search runs)
   if (p.epoch && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(p.epoch, 1u);
+  // the CTAs of the second kernel may take over SMs as teams run out of windows
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (fetcher) {
     mbar_init(&hd->mbar[0], 1);
     mbar_init(&hd->mbar[1], 1);
@@ -1338,6 +1375,12 @@ vmvo_window_search_kernel(const SearchParams p) {
 
     // ---- phase D: winner across warps, result record, optional rollout outputs ----------
     team.sync();
+    if (tid == 0 && deferred) {     // the slot is complete (every thread's stores precede the barrier)
+      __threadfence();
+      *reinterpret_cast<volatile unsigned*>(p.defer_ready + hd->slot) = 1u;
+      __threadfence();
+      atomicAdd(p.windows_done, 1ULL);
+    }
     if (tid == 0 && !deferred) {
       int bwi = -1;
       int total = 0;
@@ -1416,21 +1459,61 @@ vmvo_window_search_kernel(const SearchParams p) {
 // or 16 steps -- which is what the near-ties of a slow vehicle do (same values, same operations,
 // same cost: test_deferred_windows_give_the_same_records).  Measured alternatives: 4 or 2 warps per
 // slot (6 / 12 slots per SM) and a persistent grid are slower.
-constexpr int kDeferWarps = 8;
+//
+// The kernel is launched with programmatic stream serialization right behind the search, whose CTAs
+// (one team each) all signal launch_dependents when they start: its CTAs take over an SM's registers
+// as soon as teams there have run out of windows, i.e. they work through the parked windows during
+// the END of the search, when a growing share of the SMs would otherwise idle (the last window of a
+// team ends up to one window time after the queue runs dry).  No CTA relies on the search having
+// completed: CTA b handles slots b, b + grid, ... and waits for each slot's ready word; a slot index
+// is known to stay empty once every window of the launch has finished (windows_done == n_todo) and
+// the allocation count is below it.
 
-template <bool DUAL, bool IMU>
-__global__ void __launch_bounds__(32 * kDeferWarps, 3)
+
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <bool DUAL, bool IMU, int kDeferWarps>
+__global__ void __launch_bounds__(32 * kDeferWarps, 24 / kDeferWarps)
 vmvo_deferred_rescore_kernel(const SearchParams p) {
   extern __shared__ __align__(16) unsigned char s_slot[];
   __shared__ double s_cost[kDeferWarps], s_pose[kDeferWarps][3];
   __shared__ int s_h[kDeferWarps], s_n[kDeferWarps];
+  __shared__ int s_go;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned filled = *p.defer_count;
-  const unsigned n = filled < (unsigned)p.defer_slots ? filled : (unsigned)p.defer_slots;
   const int P = p.maxp;
   const int n_arr = 2 + (DUAL ? 2 : 0) + (IMU ? 1 : 0);
   const double wA = p.use_vo ? p.w_vo : p.w_gps, wB = p.w_gps;
-  for (unsigned s = blockIdx.x; s < n; s += gridDim.x) {
+  for (unsigned s = blockIdx.x; s < (unsigned)p.defer_slots; s += gridDim.x) {
+    if (threadIdx.x == 0) {     // slot s: published, or known to stay empty
+      int go = 0;
+      unsigned long long t0 = 0;
+      for (unsigned spin = 0;; ++spin) {
+        if (ld_acquire_gpu_u32(p.defer_ready + s)) { go = 1; break; }
+        if (ld_acquire_gpu_u64(p.windows_done) >= (unsigned long long)p.n_todo) {
+          go = ld_acquire_gpu_u32(p.defer_ready + s) != 0;     // every list is final now
+          break;
+        }
+        if ((spin & 1023) == 1023) {     // a search that died must not leave this kernel spinning
+          unsigned long long t;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+          if (t0 == 0) t0 = t;
+          else if (t - t0 > 20ull * 1000 * 1000 * 1000) break;
+        }
+        __nanosleep(200);
+      }
+      s_go = go;
+    }
+    __syncthreads();
+    if (!s_go) break;       // (slots are handed out in order: none beyond this one either)
     {
       const uint4* src = reinterpret_cast<const uint4*>(p.defer_buf + (size_t)s * p.defer_slot_bytes);
       uint4* dst = reinterpret_cast<uint4*>(s_slot);
@@ -1560,6 +1643,8 @@ vmvo_deferred_rescore_kernel(const SearchParams p) {
     }
     __syncthreads();
   }
+  // what follows this kernel in the stream follows the search as well
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 template <int C, int WARPS, int MINB, bool DUAL, bool IMU, typename SF, bool SKIP>
@@ -1567,31 +1652,54 @@ static int launch_search_v(vmvo_ctx* ctx, const SearchParams& p_in, cudaStream_t
   SearchParams p = p_in;
   p.scan_hs = SKIP ? 1 : 0;      // the many-pass kernel re-scores with Hillis-Steele sums
   auto kern = vmvo_window_search_kernel<C, WARPS, MINB, DUAL, IMU, SF, SKIP>;
-  constexpr int kCtaThreads = 32 * WARPS;
+  // one team per CTA (team_warps <= WARPS warps): a team that runs out of windows gives its
+  // registers and shared memory back at once, which is what lets the second kernel move in
+  // WARPS warps per CTA, i.e. several teams: CTAs of one two-warp team measured 1.35x slower (a CTA's
+  // warps are dealt to the four SM sub-partitions by warp index, so two-warp CTAs leave two of them idle)
+  const int teams = ctx->tune.cta_teams > 0 ? ctx->tune.cta_teams : WARPS / p.team_warps;
+  const int cta_threads = 32 * p.team_warps * teams;
   const SmemLayout lay(p.maxp, p.gs, p.vd_cols, p.team_warps, p.load_vo + p.load_gps, DUAL, IMU,
                        p.target_mode == VMVO_TARGET_TRAVERSE, (int)(4 * sizeof(SF)));
-  const int teams = WARPS / p.team_warps;
   const int smem = lay.total * teams;
   if (smem > 200 * 1024)
     return fail(ctx, VMVO_ERR_UNSUPPORTED,
                 "window tables need %d bytes of shared memory (max_window_poses %d x grid_s %d): "
                 "reduce max_window_poses or grid_s", smem, p.maxp, p.gs);
   VMVO_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  // the whole carve-out for shared memory: eight small CTAs per SM need ~130 KB between them
+  VMVO_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared));
   int per_sm = 0;
-  VMVO_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kCtaThreads, smem));
+  VMVO_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, cta_threads, smem));
   if (per_sm < 1) return fail(ctx, VMVO_ERR_CUDA, "search kernel does not fit on an SM");
+  // (the kernel is built for 128 registers per thread: 16 warps per SM)
+  const int cap = (WARPS * MINB) / (p.team_warps * teams);
+  if (per_sm > cap) per_sm = cap;
   if (ctx->tune.max_ctas_per_sm >= 1 && ctx->tune.max_ctas_per_sm < per_sm) per_sm = ctx->tune.max_ctas_per_sm;
   long long grid = (long long)ctx->sm_count * per_sm;
-  const long long items = p.n_local;
-  long long need = (items + teams - 1) / teams;
+  long long need = (p.n_local + teams - 1) / teams;
   if (need < 1) need = 1;      // (an empty share still advances the exchange's step counter)
   if (grid > need) grid = need;
-  kern<<<(unsigned)grid, kCtaThreads, smem, st>>>(p);
+  kern<<<(unsigned)grid, cta_threads, smem, st>>>(p);
   int rc = check_launch(ctx, "vmvo_window_search_kernel");
   if (rc || !p.defer_buf) return rc;
   long long g2 = p.defer_slots < (long long)ctx->sm_count * 16 ? p.defer_slots : (long long)ctx->sm_count * 16;
-  vmvo_deferred_rescore_kernel<DUAL, IMU><<<(unsigned)(g2 > 0 ? g2 : 1), 32 * kDeferWarps,
-                                            p.defer_slot_bytes, st>>>(p);
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3((unsigned)(g2 > 0 ? g2 : 1));
+  lc.blockDim = dim3(32 * 8);
+  lc.dynamicSmemBytes = (size_t)p.defer_slot_bytes;
+  lc.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = at;
+  lc.numAttrs = ctx->tune.pdl == 0 ? 0 : 1;
+  if (ctx->tune.defer_warps != 2) {
+    VMVO_CUDA(ctx, cudaLaunchKernelEx(&lc, vmvo_deferred_rescore_kernel<DUAL, IMU, 8>, p));
+  } else {
+    lc.blockDim = dim3(32 * 2);
+    VMVO_CUDA(ctx, cudaLaunchKernelEx(&lc, vmvo_deferred_rescore_kernel<DUAL, IMU, 2>, p));
+  }
   return check_launch(ctx, "vmvo_deferred_rescore_kernel");
 }
 
@@ -1700,7 +1808,8 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
                             double* d_out_poses, double* d_out_steer, double* d_out_vel,
                             int32_t out_stride, float* d_dbg_cost, float* d_dbg_err,
                             int64_t n_runs, const int64_t* d_run_offsets, const vmvo_exchange* ex,
-                            void* stream) {
+                            int32_t n_drives, const int64_t* d_drive_offsets,
+                            const int64_t* d_window_offsets, void* stream) {
   if (!ctx) return VMVO_ERR_BAD_ARG;
   int rc = validate_cfg(ctx, cfg);
   if (rc) return rc;
@@ -1708,8 +1817,17 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
   if (n_windows == 0) return VMVO_OK;
   rc = validate_exchange(ctx, ex);
   if (rc) return rc;
-  if (!d_win_start || !d_win_len || !d_win_drive || !d_dt_per_drive || !d_results)
-    return fail(ctx, VMVO_ERR_BAD_ARG, "NULL window plan / dt / result pointer");
+  if (!d_dt_per_drive || !d_results) return fail(ctx, VMVO_ERR_BAD_ARG, "NULL dt / result pointer");
+  const bool planned = d_win_start || d_win_len || d_win_drive;
+  if (planned && (!d_win_start || !d_win_len || !d_win_drive))
+    return fail(ctx, VMVO_ERR_BAD_ARG, "the window plan is three arrays: pass all or none");
+  if (!planned) {
+    if (cfg->window_mode != VMVO_WINDOW_FRAMES)
+      return fail(ctx, VMVO_ERR_UNSUPPORTED, "window extents are computed in the kernel in frames mode only: "
+                  "time mode needs the plan of vmvo_plan_windows");
+    if (n_drives < 1 || !d_drive_offsets || !d_window_offsets)
+      return fail(ctx, VMVO_ERR_BAD_ARG, "without a plan the search needs the drive and window offsets");
+  }
   if (cfg->seed_mode == VMVO_SEED_CHAINED && !d_run_offsets)
     return fail(ctx, VMVO_ERR_UNSUPPORTED,
                 "seed_mode chained walks the windows of a drive in order: call "
@@ -1806,6 +1924,10 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
   p.win_start = (const long long*)d_win_start;
   p.win_len = d_win_len;
   p.win_drive = d_win_drive;
+  p.drive_off = (const long long*)d_drive_offsets;
+  p.win_off = (const long long*)d_window_offsets;
+  p.n_drives = n_drives;
+  p.window_frames = cfg->window_frames;
   p.dt_drive = d_dt_per_drive;
   p.vo = d_vo;
   p.gps = d_gps;
@@ -1866,20 +1988,36 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
     if (slots > budget) slots = budget;
     need = (size_t)slots * slot_bytes;
   }
+  // the buffer of a launch with deferral: [ready words, one per slot][slots]
+  const size_t ready_bytes = ((size_t)slots * 4 + 127) & ~(size_t)127;
+  if (need > 0) need += ready_bytes;
   vmvo_launch_slot* ls = acquire_launch_slot(ctx, need, capturing);
   if (!ls)
     return fail(ctx, VMVO_ERR_UNSUPPORTED, "%d searches of this ctx are in flight or captured in graphs: "
                 "no launch slot left", kLaunchSlots);
-  VMVO_CUDA(ctx, cudaMemsetAsync(ls->d_counters, 0, 2 * sizeof(unsigned long long), st));   // head + slot count
+  // queue head, slot allocation count, finished windows
+  VMVO_CUDA(ctx, cudaMemsetAsync(ls->d_counters, 0, 4 * sizeof(unsigned long long), st));
   p.work_counter = ls->d_counters;
-  if (need > 0 && ls->d_defer) {
-    if (ls->defer_bytes < need) slots = (long long)(ls->defer_bytes / slot_bytes);
-    if (slots > 0) {
-      p.defer_buf = ls->d_defer;
-      p.defer_slots = (int)(slots > 0x7fffffff ? 0x7fffffff : slots);
-      p.defer_slot_bytes = (int)slot_bytes;
-      p.defer_count = reinterpret_cast<unsigned*>(ls->d_counters + 1);
+  p.windows_done = ls->d_counters + 2;
+  p.defer_ready = nullptr;
+  {   // windows this launch completes: this rank's share of the deal (exact, not the padded n_local)
+    long long todo = n_windows;
+    if (!p.run_offsets && dealt && p.sh_block_sh >= 0) {
+      const long long span = (long long)ex->block * p.sh_world;
+      const long long full = n_windows / span, rest = n_windows - full * span;
+      long long part = rest - (long long)p.sh_rank * ex->block;
+      part = part < 0 ? 0 : (part > ex->block ? ex->block : part);
+      todo = full * ex->block + part;
     }
+    p.n_todo = todo;
+  }
+  if (need > 0 && ls->d_defer && ls->defer_bytes >= need && slots > 0) {
+    p.defer_ready = reinterpret_cast<unsigned*>(ls->d_defer);
+    p.defer_buf = ls->d_defer + ready_bytes;
+    p.defer_slots = (int)(slots > 0x7fffffff ? 0x7fffffff : slots);
+    p.defer_slot_bytes = (int)slot_bytes;
+    p.defer_count = reinterpret_cast<unsigned*>(ls->d_counters + 1);
+    VMVO_CUDA(ctx, cudaMemsetAsync(p.defer_ready, 0, (size_t)p.defer_slots * 4, st));
   }
 
   const bool dual = use_vo && use_gps;
@@ -1907,7 +2045,7 @@ extern "C" int vmvo_grid_search_f32(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, i
                                     int32_t out_stride, void* stream) {
   return grid_search_impl(ctx, cfg, n_windows, d_win_start, d_win_len, d_win_drive, d_dt_per_drive,
                           d_vo, d_gps, d_imu, false, d_seeds, d_results, d_out_poses, d_out_steer,
-                          d_out_vel, out_stride, nullptr, nullptr, 0, nullptr, nullptr, stream);
+                          d_out_vel, out_stride, nullptr, nullptr, 0, nullptr, nullptr, 0, nullptr, nullptr, stream);
 }
 
 extern "C" int vmvo_grid_search_f64(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n_windows,
@@ -1919,7 +2057,7 @@ extern "C" int vmvo_grid_search_f64(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, i
                                     int32_t out_stride, void* stream) {
   return grid_search_impl(ctx, cfg, n_windows, d_win_start, d_win_len, d_win_drive, d_dt_per_drive,
                           d_vo, d_gps, d_imu, true, d_seeds, d_results, d_out_poses, d_out_steer,
-                          d_out_vel, out_stride, nullptr, nullptr, 0, nullptr, nullptr, stream);
+                          d_out_vel, out_stride, nullptr, nullptr, 0, nullptr, nullptr, 0, nullptr, nullptr, stream);
 }
 
 // stream_f64 != 0: the pose streams are double4 / double (as in vmvo_grid_search_f64)
@@ -1935,7 +2073,7 @@ extern "C" int vmvo_grid_search_chained(vmvo_ctx* ctx, const vmvo_search_cfg* cf
   return grid_search_impl(ctx, cfg, n_windows, d_win_start, d_win_len, d_win_drive, d_dt_per_drive,
                           d_vo, d_gps, d_imu, stream_f64 != 0, nullptr, d_results, d_out_poses,
                           d_out_steer, d_out_vel, out_stride, nullptr, nullptr, n_runs, d_run_offsets,
-                          nullptr, stream);
+                          nullptr, 0, nullptr, nullptr, stream);
 }
 
 extern "C" int vmvo_grid_search_debug_f32(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n_windows,
@@ -1947,17 +2085,25 @@ extern "C" int vmvo_grid_search_debug_f32(vmvo_ctx* ctx, const vmvo_search_cfg* 
   if (!d_scan_cost || !d_scan_err) return fail(ctx, VMVO_ERR_BAD_ARG, "debug outputs are NULL");
   return grid_search_impl(ctx, cfg, n_windows, d_win_start, d_win_len, d_win_drive, d_dt_per_drive,
                           d_vo, d_gps, d_imu, false, d_seeds, d_results, nullptr, nullptr, nullptr, 0,
-                          d_scan_cost, d_scan_err, 0, nullptr, nullptr, stream);
+                          d_scan_cost, d_scan_err, 0, nullptr, nullptr, 0, nullptr, nullptr, stream);
 }
 
-extern "C" int vmvo_grid_search_sharded(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n_windows,
-                                        const int64_t* d_win_start, const int32_t* d_win_len,
-                                        const int32_t* d_win_drive, const double* d_dt_per_drive,
-                                        const void* d_vo, const void* d_gps, const void* d_imu,
-                                        int32_t stream_f64, const double* d_seeds, int64_t n_runs,
-                                        const int64_t* d_run_offsets, vmvo_window_result* d_results,
-                                        const vmvo_exchange* ex, void* stream) {
+extern "C" int vmvo_grid_search_sharded(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int32_t n_drives,
+                                        const int64_t* d_drive_offsets, const int64_t* d_window_offsets,
+                                        int64_t n_windows, const int64_t* d_win_start,
+                                        const int32_t* d_win_len, const int32_t* d_win_drive,
+                                        const double* d_dt_per_drive, const void* d_vo, const void* d_gps,
+                                        const void* d_imu, int32_t stream_f64, const double* d_seeds,
+                                        vmvo_window_result* d_results, const vmvo_exchange* ex,
+                                        void* stream) {
+  if (!ctx) return VMVO_ERR_BAD_ARG;
+  const bool chained = cfg && cfg->seed_mode == VMVO_SEED_CHAINED;
+  if (chained && (n_drives < 1 || !d_window_offsets))
+    return fail(ctx, VMVO_ERR_BAD_ARG, "seed_mode chained walks the windows of each drive in order: "
+                "pass n_drives and d_window_offsets");
   return grid_search_impl(ctx, cfg, n_windows, d_win_start, d_win_len, d_win_drive, d_dt_per_drive,
                           d_vo, d_gps, d_imu, stream_f64 != 0, d_seeds, d_results, nullptr, nullptr,
-                          nullptr, 0, nullptr, nullptr, n_runs, d_run_offsets, ex, stream);
+                          nullptr, 0, nullptr, nullptr, chained ? n_drives : 0,
+                          chained ? d_window_offsets : nullptr, ex, n_drives, d_drive_offsets,
+                          d_window_offsets, stream);
 }

@@ -167,26 +167,41 @@ class DriveSet:
 class WindowPlan:
     window_offsets: List[int]              # host, len D+1
     d_window_offsets: torch.Tensor         # int64 [D+1]
-    win_start: torch.Tensor                # int64 [n_windows] absolute frame index
-    win_len: torch.Tensor                  # int32 [n_windows]
-    win_drive: torch.Tensor                # int32 [n_windows]
+    # the extents (None in a plan without them: frames mode, the search derives them itself)
+    win_start: Optional[torch.Tensor]      # int64 [n_windows] absolute frame index
+    win_len: Optional[torch.Tensor]        # int32 [n_windows]
+    win_drive: Optional[torch.Tensor]      # int32 [n_windows]
 
     @property
     def n_windows(self) -> int:
         return self.window_offsets[-1]
 
 
-def plan_windows(cfg: SearchConfig, drives: DriveSet, into: Optional[WindowPlan] = None) -> WindowPlan:
+def plan_windows(cfg: SearchConfig, drives: DriveSet, into: Optional[WindowPlan] = None,
+                 extents: bool = True) -> WindowPlan:
     """a8 for every window of every drive (vmvo/schema.py:117-127, …v2.py:48).
 
     ``into``: a plan allocated by an earlier call for the same drive lengths; only the kernel
     is launched (no allocation, no host-to-device copy), e.g. under CUDA-graph capture.
+
+    ``extents=False`` (frames mode only): just the window counts per drive -- no kernel, no
+    extent arrays; ``grid_search`` then lets the search kernel derive each window's extent itself
+    (window i of a drive = poses i .. i + window_frames), which saves the planning launch of a step.
     """
     ctx = _lib.context(drives.device.index)
     c = cfg.to_c()
+    if not extents:
+        if cfg.window_mode != "frames":
+            raise ValueError("a plan without extents is for window_mode 'frames'")
+        woffs = [0]
+        for d in range(drives.n_drives):
+            woffs.append(woffs[-1] + cfg.window_count(drives.drive_offsets[d + 1] - drives.drive_offsets[d]))
+        return WindowPlan(window_offsets=woffs,
+                          d_window_offsets=torch.tensor(woffs, dtype=torch.int64, device=drives.device),
+                          win_start=None, win_len=None, win_drive=None)
     if into is not None:
         plan, n = into, into.n_windows
-        if n:
+        if n and plan.win_start is not None:
             ctx.check(ctx.lib.vmvo_plan_windows(
                 ctx.handle, C.byref(c), drives.n_drives, _lib.ptr(drives.d_drive_offsets),
                 _lib.ptr(plan.d_window_offsets), n, _lib.ptr(drives.time), _lib.ptr(plan.win_start),
@@ -241,10 +256,13 @@ def grid_search(cfg: SearchConfig, drives: DriveSet, plan: WindowPlan,
     """
     ctx = _lib.context(drives.device.index)
     c = cfg.to_c()
-    if exchange is not None:
+    if exchange is not None or plan.win_start is None:
         if window_range is not None or want_rollouts:
-            raise ValueError("a sharded search covers the whole plan and returns records only")
+            raise ValueError("a sharded search / a search without planned extents covers the whole plan "
+                             "and returns records only")
         n, dev = plan.n_windows, drives.device
+        if out is None and exchange is None:
+            out = torch.empty((n, 64), dtype=torch.uint8, device=dev)
         if out is None or out.shape != (n, 64) or out.dtype != torch.uint8 or not out.is_contiguous():
             raise ValueError("a sharded search writes into the gather buffer: out = uint8 [n_windows, 64]")
         d_seeds = None
@@ -252,15 +270,14 @@ def grid_search(cfg: SearchConfig, drives: DriveSet, plan: WindowPlan,
             d_seeds = _as_dev(seeds, torch.float64, dev)
             if d_seeds.shape != (n, 2):
                 raise ValueError("seeds must be [n_windows, 2]")
-        chained = cfg.seed_mode == "chained"
         if n:
             ctx.check(ctx.lib.vmvo_grid_search_sharded(
-                ctx.handle, C.byref(c), n, _lib.ptr(plan.win_start), _lib.ptr(plan.win_len),
+                ctx.handle, C.byref(c), drives.n_drives, _lib.ptr(drives.d_drive_offsets),
+                _lib.ptr(plan.d_window_offsets), n, _lib.ptr(plan.win_start), _lib.ptr(plan.win_len),
                 _lib.ptr(plan.win_drive), _lib.ptr(drives.dt), _lib.ptr(drives.vo), _lib.ptr(drives.gps),
-                _lib.ptr(drives.imu), int(drives.f64), _lib.ptr(d_seeds),
-                len(plan.window_offsets) - 1 if chained else 0,
-                _lib.ptr(plan.d_window_offsets) if chained else None, _lib.ptr(out),
-                C.byref(exchange), _lib.stream_ptr(dev)), "vmvo_grid_search_sharded")
+                _lib.ptr(drives.imu), int(drives.f64), _lib.ptr(d_seeds), _lib.ptr(out),
+                None if exchange is None else C.byref(exchange), _lib.stream_ptr(dev)),
+                "vmvo_grid_search_sharded")
         return SearchOutput(results=out)
     lo, hi = (0, plan.n_windows) if window_range is None else window_range
     n = hi - lo
@@ -378,8 +395,9 @@ def optimize_drives(cfg: SearchConfig, drives: DriveSet, plan: Optional[WindowPl
 
 class DrivePipeline:
     """plan -> search -> write-back for one resident batch of drives, captured once as a CUDA
-    graph and replayed: four kernel launches (plan, search, deferred re-scores, write-back) and one
-    memset per pass, no per-pass host work.
+    graph and replayed: three kernel launches in frames mode (search, deferred re-scores, write-back:
+    the search derives the window extents itself), four in time mode (the plan first), one memset,
+    no per-pass host work.
 
     The pose streams and stamps are read from ``drives`` at replay time, so new data of the
     same shape can be copied into ``drives.vo`` / ``.gps`` / ``.imu`` / ``.time`` between passes.
@@ -393,7 +411,7 @@ class DrivePipeline:
     ``run`` are collective over the gather's group (each pass waits for the peers' records).
     """
 
-    KERNELS_PER_PASS = 4
+    KERNELS_PER_PASS = 4       # (time mode; see kernels_per_pass)
 
     def __init__(self, cfg: SearchConfig, drives: DriveSet, blend_gps: bool = True,
                  records: Optional[torch.Tensor] = None, use_graph: bool = True,
@@ -402,7 +420,8 @@ class DrivePipeline:
         if cfg.seed_mode == "given":
             raise ValueError("DrivePipeline derives seeds from the data (seed_mode data / chained)")
         self.cfg, self.drives, self.blend_gps = cfg, drives, blend_gps
-        self.plan = plan_windows(cfg, drives)
+        self.plan = plan_windows(cfg, drives, extents=cfg.window_mode != "frames")
+        self.kernels_per_pass = 3 if self.plan.win_start is None else 4
         dev = drives.device
         n = self.plan.n_windows
         self.gather, self.frame_range = gather, frame_range
