@@ -32,6 +32,7 @@ block = int(sys.argv[1]) if len(sys.argv) > 1 else bench.DEAL_BLOCK
 class Variant(DrivePipeline):
     mirrors = True
     arrival = True
+    search_only = False
 
     def _ex(self, on):
         ex = _lib.Exchange.from_buffer_copy(self.gather.exchange)
@@ -45,13 +46,15 @@ class Variant(DrivePipeline):
         grid_search(self.cfg, self.drives, self.plan, out=self.records, exchange=self._ex_s)
 
     def _write_back(self):
+        if self.search_only:
+            return
         self._ex_w = self._ex(self.arrival)
         write_back(self.cfg, self.drives, self.plan, self.records, blend_gps=False, out=self.trajectory,
                    frame_range=self.frame_range, exchange=self._ex_w)
 
 
-def run(name, mirrors, arrival, align=False, steps=40):
-    cls = type("V", (Variant,), {"mirrors": mirrors, "arrival": arrival})
+def run(name, mirrors, arrival, align=False, steps=40, search_only=False):
+    cls = type("V", (Variant,), {"mirrors": mirrors, "arrival": arrival, "search_only": search_only})
     sets = [PeerGather(n_win, dev, block=block) for _ in range(2)]
     pipes = [cls(cfg, drives, blend_gps=False, gather=g, frame_range=fr) for g in sets]
     st = {"n": 0}
@@ -90,8 +93,8 @@ def run(name, mirrors, arrival, align=False, steps=40):
 
 if rank == 0:
     print(f"world {world}, {n_win} windows pooled, block {block}", flush=True)
-run("deal only (no peer stores, no arrival words)", False, False)
-run("deal + peer stores", True, False)
+run("search of this rank's deal only (no peer stores, no write-back)", False, False, search_only=True)
+run("search of this rank's deal + peer stores (no write-back)", True, False, search_only=True)
 run("deal + peer stores + arrival words (the shipped step)", True, True)
 run("the shipped step, ranks aligned before each timed step", True, True, align=True)
 # one GPU's share alone, for scale: every rank searches its deal of the pool without any peer

@@ -28,7 +28,7 @@ namespace vmvo {
 
 constexpr int kCandPerWarp = 128;  // candidate list entries per team warp (flushed when full)
 constexpr int kMaxWarps = 16;      // most warps per CTA (and per team) of any kernel variant
-constexpr int kHeaderBytes = 1152;
+constexpr int kHeaderBytes = 1280;
 
 struct SearchParams {
   int gv, gs;
@@ -176,6 +176,7 @@ struct BandWin {       // window-level inputs, identical in every thread
 struct SmemHeader {
   uint64_t mbar[2];
   long long wid[2];
+  vmvo_window_result rec;   // the window's record, assembled by one thread, stored by a warp
   WinInfo wi;
   BandWin bw;
   float red[3 * kMaxWarps];
@@ -658,15 +659,25 @@ vmvo_window_search_kernel(const SearchParams p) {
     }
   };
 
-  // one record, to this GPU's buffer and to every mirror (peer GPUs' gather buffers: plain stores
-  // over NVLink, visible to the peers when the kernel has completed)
-  auto store_record = [&](long long w, const vmvo_window_result& r) {
-    p.results[w] = r;
-    for (int q = 0; q < p.n_mirrors; ++q) p.mirrors[q][w] = r;
+  // One record, to this GPU's buffer and to every mirror (peer GPUs' gather buffers: plain stores
+  // over NVLink, visible to the peers when the kernel has completed).  One thread assembles it in
+  // shared memory (store_record); warp 0 stores it (flush_record): four lanes per destination, so
+  // that each copy leaves as ONE 64-byte write -- with seven peers a single thread would issue 32
+  // separate 16-byte stores per window, 28 of them small NVLink packets.
+  auto store_record = [&](const vmvo_window_result& r) { hd->rec = r; };
+  auto flush_record = [&](long long w) {   // every lane of the team's warp 0
+    __syncwarp();
+    const uint4 part = reinterpret_cast<const uint4*>(&hd->rec)[lane & 3];
+    for (int t = lane >> 2; t <= p.n_mirrors; t += 8) {
+      vmvo_window_result* base = t == 0 ? p.results : p.mirrors[t - 1];
+      reinterpret_cast<uint4*>(base + w)[lane & 3] = part;
+    }
     if (p.defer_ready) {       // one finished window (the second kernel watches the count)
       __threadfence();
-      atomicAdd(p.windows_done, 1ULL);
+      __syncwarp();
+      if (lane == 0) atomicAdd(p.windows_done, 1ULL);
     }
+    __syncwarp();
   };
 
   const bool chained = p.run_offsets != nullptr;
@@ -741,14 +752,17 @@ vmvo_window_search_kernel(const SearchParams p) {
       r.v_seed = vs;
       r.s_seed = ss;
       r.x1 = r.y1 = r.theta1 = CUDART_NAN;
-      store_record(w, r);
+      store_record(r);
     };
 
     if (len > P || len < 1) {  // uniform branch
       // no pose at all (an empty time extent, NaN stamps): "No frames found", schema.py:122
-      if (tid == 0)
-        write_unsearched(len < 1 ? (VMVO_WIN_EMPTY | VMVO_WIN_NO_FRAMES) : VMVO_WIN_TOO_LONG, 0,
-                         CUDART_NAN, CUDART_NAN);
+      if (warp == 0) {
+        if (lane == 0)
+          write_unsearched(len < 1 ? (VMVO_WIN_EMPTY | VMVO_WIN_NO_FRAMES) : VMVO_WIN_TOO_LONG, 0,
+                           CUDART_NAN, CUDART_NAN);
+        flush_record(w);
+      }
       team.sync();
       continue;
     }
@@ -1046,7 +1060,10 @@ vmvo_window_search_kernel(const SearchParams p) {
     const WinInfo& wi = hd->wi;
 
     if (status & VMVO_WIN_EMPTY) {
-      if (tid == 0) write_unsearched(status, N, v_seed, s_seed);
+      if (warp == 0) {
+        if (lane == 0) write_unsearched(status, N, v_seed, s_seed);
+        flush_record(w);
+      }
       team.sync();
       continue;
     }
@@ -1404,8 +1421,9 @@ vmvo_window_search_kernel(const SearchParams p) {
       r.y1 = bwi >= 0 ? hd->bpose[bwi][1] : CUDART_NAN;
       r.theta1 = bwi >= 0 ? hd->bpose[bwi][2] : CUDART_NAN;
       hd->winner = r.best_idx;
-      store_record(w, r);
+      store_record(r);
     }
+    if (warp == 0 && !deferred) flush_record(w);
     if (chained) {  // last steering angle of the optimum (optimize_trajectory_v2.py:146)
       team.sync();
       const int h = hd->winner;
@@ -1488,6 +1506,7 @@ vmvo_deferred_rescore_kernel(const SearchParams p) {
   __shared__ double s_cost[kDeferWarps], s_pose[kDeferWarps][3];
   __shared__ int s_h[kDeferWarps], s_n[kDeferWarps];
   __shared__ int s_go;
+  __shared__ vmvo_window_result s_rec;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int P = p.maxp;
   const int n_arr = 2 + (DUAL ? 2 : 0) + (IMU ? 1 : 0);
@@ -1638,8 +1657,15 @@ vmvo_deferred_rescore_kernel(const SearchParams p) {
       r.x1 = bwi >= 0 ? s_pose[bwi][0] : CUDART_NAN;
       r.y1 = bwi >= 0 ? s_pose[bwi][1] : CUDART_NAN;
       r.theta1 = bwi >= 0 ? s_pose[bwi][2] : CUDART_NAN;
-      p.results[dh->w] = r;
-      for (int q = 0; q < p.n_mirrors; ++q) p.mirrors[q][dh->w] = r;
+      s_rec = r;
+    }
+    __syncthreads();
+    {   // four threads per destination: every copy of the record leaves as one 64-byte write
+      const uint4 part = reinterpret_cast<const uint4*>(&s_rec)[threadIdx.x & 3];
+      for (int t = threadIdx.x >> 2; t <= p.n_mirrors; t += (32 * kDeferWarps) >> 2) {
+        vmvo_window_result* base = t == 0 ? p.results : p.mirrors[t - 1];
+        reinterpret_cast<uint4*>(base + dh->w)[threadIdx.x & 3] = part;
+      }
     }
     __syncthreads();
   }
