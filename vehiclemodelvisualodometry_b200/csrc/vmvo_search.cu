@@ -1506,7 +1506,7 @@ vmvo_deferred_rescore_kernel(const SearchParams p) {
   __shared__ double s_cost[kDeferWarps], s_pose[kDeferWarps][3];
   __shared__ int s_h[kDeferWarps], s_n[kDeferWarps];
   __shared__ int s_go;
-  __shared__ vmvo_window_result s_rec;
+  __shared__ __align__(16) vmvo_window_result s_rec;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int P = p.maxp;
   const int n_arr = 2 + (DUAL ? 2 : 0) + (IMU ? 1 : 0);
