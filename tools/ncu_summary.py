@@ -27,9 +27,22 @@ KEYS = [
     "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
     "smsp__thread_inst_executed_per_inst_executed.ratio", "sm__cycles_active.avg",
 ]
+# pipe activity as the hardware counts it (cycles a pipe is busy, not instructions sent to it: a
+# packed FFMA2 keeps the FMA pipe busy longer than a scalar FFMA), and the issue rate
+EXTRA = ["sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+         "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed",
+         "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+         "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+         "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_elapsed",
+         "sm__inst_issued.avg.per_cycle_active", "smsp__average_warp_latency_per_inst_issued.ratio",
+         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
 for r in rows[2:]:
     print("== kernel:", r[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "?")
     for k in KEYS:
+        if k in hdr:
+            i = hdr.index(k)
+            print(f"{k:70s} {r[i]:>18s} {units[i]}")
+    for k in EXTRA:
         if k in hdr:
             i = hdr.index(k)
             print(f"{k:70s} {r[i]:>18s} {units[i]}")

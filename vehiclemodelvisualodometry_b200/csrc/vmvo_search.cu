@@ -672,11 +672,10 @@ vmvo_window_search_kernel(const SearchParams p) {
       vmvo_window_result* base = t == 0 ? p.results : p.mirrors[t - 1];
       reinterpret_cast<uint4*>(base + w)[lane & 3] = part;
     }
-    if (p.defer_ready) {       // one finished window (the second kernel watches the count)
-      __threadfence();
-      __syncwarp();
-      if (lane == 0) atomicAdd(p.windows_done, 1ULL);
-    }
+    // One window whose list is NOT parked (the second kernel watches the count to learn when the
+    // set of parked windows is final; it never reads this record).  No fence: a fence behind stores
+    // to peer memory would wait for their acknowledgement over NVLink, window after window.
+    if (p.defer_ready && lane == 0) atomicAdd(p.windows_done, 1ULL);
     __syncwarp();
   };
 
