@@ -100,44 +100,73 @@ __global__ void gps_delta_kernel(int n_drives, const long long* off, long long t
 
 // per drive: the cumulative path (n+1 points, a leading duplicate of the origin) -- a dependent
 // chain of additions, sequential by definition -- and the de-duplication state machine
-// (vmvo/utils/trajectory.py:206-216, 243-300).  One warp per drive: 32 deltas are loaded
-// coalesced, every lane walks the same chain (values broadcast by shuffle) and keeps point l of
-// the batch.  The state machine needs no chain: every point between `last` and i equals point
-// `last` bit for bit, so "x[last] != x[i]" is the local test "point i differs from point i-1";
-// segment ends are then found with ballot / ffs / clz, and only runs of repeated fixes longer
-// than a batch need the strided fill.
-__global__ void gps_scan_kernel(int n_drives, const long long* off, long long total, const double* dxy,
-                                double* X, double* Y, int* seg_lo, int* seg_hi, int* status) {
-  const int lane = threadIdx.x & 31;
+// (vmvo/utils/trajectory.py:206-216, 243-300).  One warp per drive: 32 deltas per axis are loaded
+// coalesced and staged in shared memory; lane 0 (x) and lane 1 (y) pull their 32 deltas into
+// registers and run the chain -- 32 dependent DADDs, nothing else on the critical path -- leaving
+// the 32 points in shared memory for the warp (a chain step costs one DADD latency; walking the
+// chain redundantly in every lane with a shuffle per step measured 88 clk per step).  The state
+// machine needs no chain: every point between `last` and i equals point `last` bit for bit, so
+// "x[last] != x[i]" is the local test "point i differs from point i-1"; segment ends are then found
+// with ballot / ffs / clz, and only runs of repeated fixes longer than a batch need the strided fill.
+constexpr int kGpsScanWarps = 4;
+__global__ void __launch_bounds__(32 * kGpsScanWarps)
+gps_scan_kernel(int n_drives, const long long* off, long long total, const double* dxy,
+                double* X, double* Y, int* seg_lo, int* seg_hi, int* status) {
+  __shared__ __align__(16) double s_delta[kGpsScanWarps][2][32];
+  __shared__ __align__(16) double s_point[kGpsScanWarps][2][32];
+  const int lane = threadIdx.x & 31, wb = threadIdx.x >> 5;
   const int d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (d >= n_drives) return;
   const long long f0 = off[d], n = off[d + 1] - f0;
   const long long o0 = f0 + d;          // outputs hold n + 1 points per drive
-  const long long m = n + 1;
   if (lane == 0) {
     X[o0] = 0.0;
     Y[o0] = 0.0;
     seg_lo[o0] = 0;
     seg_hi[o0] = 0;
   }
-  double xc = 0.0, yc = 0.0;            // last point produced (replicated in every lane)
+  double carry = 0.0;                   // lanes 0 / 1: last x / y produced
+  double x_last = 0.0, y_last = 0.0;    // every lane: point `base`
   long long last = 0;                   // latest segment end
   int st = 0;
+  // the deltas of the next batch are fetched while this batch's chain runs (a global load costs
+  // more than the 32 additions it feeds)
+  double nx = lane < n ? dxy[f0 + lane] : 0.0, ny = lane < n ? dxy[total + f0 + lane] : 0.0;
   for (long long base = 0; base < n; base += 32) {
     const long long i0 = base + lane;
     const bool valid = i0 < n;
-    const double ddx = valid ? dxy[f0 + i0] : 0.0, ddy = valid ? dxy[total + f0 + i0] : 0.0;
-    const double x_in = xc, y_in = yc;  // point `base`
-    double mx = 0.0, my = 0.0;
-#pragma unroll
-    for (int l = 0; l < 32; ++l) {      // x[i+1] = dx_i + x[i]; padding deltas are zero
-      xc = dadd(__shfl_sync(FULL, ddx, l), xc);
-      yc = dadd(__shfl_sync(FULL, ddy, l), yc);
-      if (l == lane) { mx = xc; my = yc; }
+    s_delta[wb][0][lane] = nx;          // padding deltas are zero
+    s_delta[wb][1][lane] = ny;
+    {
+      const long long i1 = i0 + 32;
+      nx = i1 < n ? dxy[f0 + i1] : 0.0;
+      ny = i1 < n ? dxy[total + f0 + i1] : 0.0;
     }
+    __syncwarp();
+    if (lane < 2) {                     // x[i+1] = dx_i + x[i], one axis per lane
+      double v[32];
+      const double2* src = reinterpret_cast<const double2*>(s_delta[wb][lane]);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const double2 t = src[q];
+        v[2 * q] = t.x;
+        v[2 * q + 1] = t.y;
+      }
+      double2* dst = reinterpret_cast<double2*>(s_point[wb][lane]);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const double a = dadd(v[2 * q], carry);
+        carry = dadd(v[2 * q + 1], a);
+        dst[q] = make_double2(a, carry);
+      }
+    }
+    __syncwarp();
+    const double mx = s_point[wb][0][lane], my = s_point[wb][1][lane];
     // lane l holds point i = base + l + 1; its predecessor is lane l-1's point (or point `base`)
     double px = __shfl_up_sync(FULL, mx, 1), py = __shfl_up_sync(FULL, my, 1);
-    if (lane == 0) { px = x_in; py = y_in; }
+    if (lane == 0) { px = x_last; py = y_last; }
+    x_last = __shfl_sync(FULL, mx, 31);   // (padding deltas are zero: lane 31 holds the last valid point)
+    y_last = __shfl_sync(FULL, my, 31);
     const long long i = base + lane + 1;
     const unsigned bits = __ballot_sync(FULL, valid && (mx != px || my != py));
     if (valid) {
@@ -153,9 +182,7 @@ __global__ void gps_scan_kernel(int n_drives, const long long* off, long long to
       last = base + (31 - __clz(bits)) + 1;
       if (last == n) st = 1;   // the reference indexes velocity[n] here: IndexError
     }
-    // carry: the last VALID point of the batch (padding deltas are zero, so xc already is it)
   }
-  (void)m;
   if (lane == 0) status[d] = st;
 }
 
