@@ -232,9 +232,19 @@ struct Team {
 // ---- FP32 error band ----------------------------------------------
 // |J_fp32 - J_fp64| <= c0 + c1*sqrt(J) + c2*J for every hypothesis of an item, from the item's
 // own step length, heading excursion and tan magnitude.
+// Square root for the band: one MUFU (sqrt.approx, relative error <= 2^-22) scaled up by 2^-20 so
+// that the result is never below the true root -- every use in the band wants an upper bound (a wider
+// band, a larger threshold), and the IEEE sqrtf costs ten instructions and a dependent chain per use,
+// three uses per thread and pass.  NaN and +inf pass through.
+__device__ __forceinline__ float sqrt_up(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r * 1.000001f;
+}
+
 struct Band {
   float c0, c1, c2;
-  __device__ __forceinline__ float err(float J) const { return fmaf(c1, sqrtf(J), fmaf(c2, J, c0)); }
+  __device__ __forceinline__ float err(float J) const { return fmaf(c1, sqrt_up(J), fmaf(c2, J, c0)); }
   // Largest cost that can still be a candidate under the bound U on the minimum: g(J) = J - err(J)
   // is convex with g(0) <= 0 <= U, so {J >= 0 : g(J) <= U} = [0, T] with sqrt(T) the larger root of
   // (1 - c2) s^2 - c1 s - (c0 + U) = 0.  One sqrt per thread instead of one per hypothesis; T is
@@ -243,7 +253,7 @@ struct Band {
     if (!(c2 < 0.5f)) return CUDART_INF_F;
     const float a = 1.f - c2;
     // (2a is in (1, 2]: the approximate division is good to 2 ulp, far inside the rounding-up)
-    const float s = __fdividef(c1 + sqrtf(fmaf(c1, c1, 4.f * a * (c0 + U))), 2.f * a);
+    const float s = __fdividef(c1 + sqrt_up(fmaf(c1, c1, 4.f * a * (c0 + U))), 2.f * a);
     return s * s * 1.0000153f;
   }
 };
@@ -251,6 +261,7 @@ struct Band {
 // fast = the packed / rotation scan (scan_item_fast): headings are the affine form A_k + a_i*B_k
 // (error <= (eps_TL + 5u + k*u) * Theta', Theta' = sum (V_w*dt + |a|max*t*dt)*|TL|), half of the
 // sin/cos pairs come from one rotation of a MUFU pair by a MUFU angle.
+template <bool IMU>
 __device__ __forceinline__ Band make_band(const BandWin& w, float vmax, float theta_tv, float tlmax,
                                           bool fast) {
   const float u = 5.9604644775390625e-8f;           // 2^-24
@@ -264,12 +275,14 @@ __device__ __forceinline__ Band make_band(const BandWin& w, float vmax, float th
   const float q1 = vmax * (eps_trig + u) + 2.f * u * w.dmax + 2.f * u * w.dabmax + head;
   const float q2 = vmax * g;
   const float e2pos = 3.f * (q1 * q1 * w.s2 + q2 * q2 * w.s4);
-  const float ei = u * (w.imax + 3.1415927f) + (theta_tv * 0.15915494f + 1.f) * 1.75e-7f;
-  const float e2imu = 2.f * (g * g * w.s2 + w.n * ei * ei);
-  const float e2 = w.wpos * e2pos + w.wimu * e2imu;
+  float e2 = w.wpos * e2pos;
+  if (IMU) {     // (compile-time: a search without the yaw term does not pay for its band)
+    const float ei = u * (w.imax + 3.1415927f) + (theta_tv * 0.15915494f + 1.f) * 1.75e-7f;
+    e2 += w.wimu * (2.f * (g * g * w.s2 + w.n * ei * ei));
+  }
   Band b;
   b.c0 = SF * 2.f * e2;
-  b.c1 = SF * 2.f * sqrtf(2.f * e2);
+  b.c1 = SF * 2.f * sqrt_up(2.f * e2);
   b.c2 = w.c2;
   return b;
 }
@@ -1216,7 +1229,7 @@ vmvo_window_search_kernel(const SearchParams p) {
           const float dtf = (float)dt, vpos = fmaxf((float)v_seed, 0.f), amax = (float)p.max_accel;
           const float vmax_all = 1.000002f * (vpos + amax * (float)N * dtf) * dtf;
           const float tv_all = 1.000002f * fmaf(vpos * dtf, s0_all, 1.000002f * amax * dtf * dtf * s1_all);
-          loose = make_band(hd->bw, vmax_all, tv_all, tl_all, fast_w);
+          loose = make_band<IMU>(hd->bw, vmax_all, tv_all, tl_all, fast_w);
         }
         const int q = pass * T + tid;
         ScanOut<C> so;
@@ -1280,7 +1293,7 @@ vmvo_window_search_kernel(const SearchParams p) {
             const float vmax = fmaxf(vdc[0], vdc[(N - 1) * p.vd_cols]);
             const float tv = 1.000002f * fmaf(fmaxf((float)v_seed, 0.f) * dtf, TS[gs4 + j],
                                               1.000002f * acoef * dtf * dtf * TS[2 * gs4 + j]);
-            band = make_band(hd->bw, vmax, tv, TS[j], fast);
+            band = make_band<IMU>(hd->bw, vmax, tv, TS[j], fast);
           }
           if (p.dbg_cost) {
 #pragma unroll
