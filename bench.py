@@ -393,9 +393,9 @@ def roofline(ctx, dev, res, clocks, extras=True):
     """What binds the search kernel: FP32 issue (the FMA pipe).  ``frac`` = FP32-pipe lane-operations
     the kernel EXECUTES per launch (from the committed ncu instruction counts of this workload,
     profiles/kernel_counts_r02.json; a packed FFMA2 / FADD2 / FMUL2 counts as two) divided by the
-    kernel's launch time and by the FFMA lane-operation rate measured live.  Beside it: the same
-    with each opcode weighted by its measured issue cost on the FMA pipe (``frac_pipe_time``), the
-    algorithmic FP32 figure (25 flops per hypothesis-step), and both SFU figures."""
+    kernel's launch time and by the FFMA lane-operation rate measured live.  Beside it: the hardware
+    counters of the same launch under ncu (FMA-pipe active cycles, XU issue share), the algorithmic
+    FP32 figure (25 flops per hypothesis-step), and both SFU figures."""
     import torch
 
     from vehiclemodelvisualodometry_b200.search import executed_mufu_per_hypothesis_step
@@ -433,7 +433,11 @@ def roofline(ctx, dev, res, clocks, extras=True):
         out["executed_fp32_lane_ops_per_hypothesis_step"] = counts["fp32_lane_ops_per_hypothesis_step"]
         out["achieved"] = lane_ops / sec / 1e9
         out["frac"] = lane_ops / sec / ffma
-        out["frac_pipe_time"] = counts["fma_pipe_clk_per_hypothesis_step"] * hsteps / 32 / sec / (sms * 4 * sm_max * 1e6)
+        # the hardware's own view of the same launch (captured under ncu, profiles/): share of cycles the
+        # FMA pipe is busy, share of issue slots the XU (MUFU) pipe takes, share of cycles an instruction issues
+        out["ncu_pipe_fma_cycles_active_pct"] = counts.get("hw_pipe_fma_cycles_active_pct")
+        out["ncu_pipe_xu_inst_pct"] = counts.get("hw_pipe_xu_inst_pct")
+        out["ncu_issue_active_pct"] = counts.get("hw_issue_active_pct")
         out["counts_source"] = counts.get("source")
     else:
         out["achieved"] = hsteps * FLOP_PER_HSTEP / 2 / sec / 1e9
