@@ -91,11 +91,12 @@ struct SearchParams {
   unsigned* defer_count;
   int defer_slots, defer_slot_bytes, defer_min;
   // the second kernel runs BESIDE the end of the search (programmatic dependent launch): a parked
-  // window is published through defer_ready[slot] and every finished window counts in windows_done,
-  // so the second kernel knows when slot lists are final without waiting for the grid to drain
+  // window is published through defer_ready[slot] and every team that runs out of windows counts in
+  // windows_done, so the second kernel knows when the set of slots is final without waiting for the
+  // grid to drain
   unsigned* defer_ready;               // [defer_slots], cleared with the counters before the launch
-  unsigned long long* windows_done;
-  long long n_todo;                    // windows this launch completes (this rank's share)
+  unsigned long long* windows_done;    // (counts finished TEAMS)
+  long long n_todo;                    // teams of the launch
   float* dbg_cost;       // optional [n_windows][gv*gs] FP32 scan costs   (tests only)
   float* dbg_err;        // optional [n_windows][gv*gs] error-band widths (tests only)
 };
@@ -677,18 +678,21 @@ vmvo_window_search_kernel(const SearchParams p) {
   // shared memory (store_record); warp 0 stores it (flush_record): four lanes per destination, so
   // that each copy leaves as ONE 64-byte write -- with seven peers a single thread would issue 32
   // separate 16-byte stores per window, 28 of them small NVLink packets.
-  auto store_record = [&](const vmvo_window_result& r) { hd->rec = r; };
+  // Without mirrors (one GPU) the assembling thread stores the record itself.
+  auto store_record = [&](long long w, const vmvo_window_result& r) {
+    if (p.n_mirrors == 0) p.results[w] = r;
+    else hd->rec = r;
+  };
   auto flush_record = [&](long long w) {   // every lane of the team's warp 0
+    if (p.n_mirrors == 0) return;
     __syncwarp();
     const uint4 part = reinterpret_cast<const uint4*>(&hd->rec)[lane & 3];
     for (int t = lane >> 2; t <= p.n_mirrors; t += 8) {
       vmvo_window_result* base = t == 0 ? p.results : p.mirrors[t - 1];
       reinterpret_cast<uint4*>(base + w)[lane & 3] = part;
     }
-    // One window whose list is NOT parked (the second kernel watches the count to learn when the
-    // set of parked windows is final; it never reads this record).  No fence: a fence behind stores
-    // to peer memory would wait for their acknowledgement over NVLink, window after window.
-    if (p.defer_ready && lane == 0) atomicAdd(p.windows_done, 1ULL);
+    // (no fence here: a fence behind stores to peer memory would wait for their acknowledgement
+    // over NVLink, window after window)
     __syncwarp();
   };
 
@@ -740,7 +744,15 @@ vmvo_window_search_kernel(const SearchParams p) {
   for (int it = 0;; ++it) {
     const int cur = it & 1;
     const long long w = hd->wid[cur];
-    if (w >= p.n_windows) break;
+    if (w >= p.n_windows) {
+      // this team parks no more windows: the second kernel watches the count of finished teams to
+      // learn when the set of parked windows is final (its ready words are behind fences already)
+      if (tid == 0 && p.defer_ready) {
+        __threadfence();
+        atomicAdd(p.windows_done, 1ULL);
+      }
+      break;
+    }
     if (fetcher) {  // prefetch the next window's poses while this one is searched
       const long long wn = next_window(w, cur ^ 1);
       hd->wid[cur ^ 1] = wn;
@@ -764,7 +776,7 @@ vmvo_window_search_kernel(const SearchParams p) {
       r.v_seed = vs;
       r.s_seed = ss;
       r.x1 = r.y1 = r.theta1 = CUDART_NAN;
-      store_record(r);
+      store_record(w, r);
     };
 
     if (len > P || len < 1) {  // uniform branch
@@ -1407,8 +1419,6 @@ vmvo_window_search_kernel(const SearchParams p) {
     if (tid == 0 && deferred) {     // the slot is complete (every thread's stores precede the barrier)
       __threadfence();
       *reinterpret_cast<volatile unsigned*>(p.defer_ready + hd->slot) = 1u;
-      __threadfence();
-      atomicAdd(p.windows_done, 1ULL);
     }
     if (tid == 0 && !deferred) {
       int bwi = -1;
@@ -1433,7 +1443,7 @@ vmvo_window_search_kernel(const SearchParams p) {
       r.y1 = bwi >= 0 ? hd->bpose[bwi][1] : CUDART_NAN;
       r.theta1 = bwi >= 0 ? hd->bpose[bwi][2] : CUDART_NAN;
       hd->winner = r.best_idx;
-      store_record(r);
+      store_record(w, r);
     }
     if (warp == 0 && !deferred) flush_record(w);
     if (chained) {  // last steering angle of the optimum (optimize_trajectory_v2.py:146)
@@ -1496,8 +1506,8 @@ vmvo_window_search_kernel(const SearchParams p) {
 // the END of the search, when a growing share of the SMs would otherwise idle (the last window of a
 // team ends up to one window time after the queue runs dry).  No CTA relies on the search having
 // completed: CTA b handles slots b, b + grid, ... and waits for each slot's ready word; a slot index
-// is known to stay empty once every window of the launch has finished (windows_done == n_todo) and
-// the allocation count is below it.
+// is known to stay empty once every team of the search has run out of windows (a counter the teams
+// bump on their way out) and the allocation count is below it.
 
 
 __device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
@@ -1718,6 +1728,7 @@ static int launch_search_v(vmvo_ctx* ctx, const SearchParams& p_in, cudaStream_t
   long long need = (p.n_local + teams - 1) / teams;
   if (need < 1) need = 1;      // (an empty share still advances the exchange's step counter)
   if (grid > need) grid = need;
+  p.n_todo = grid * teams;
   kern<<<(unsigned)grid, cta_threads, smem, st>>>(p);
   int rc = check_launch(ctx, "vmvo_window_search_kernel");
   if (rc || !p.defer_buf) return rc;
@@ -2038,17 +2049,7 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
   p.work_counter = ls->d_counters;
   p.windows_done = ls->d_counters + 2;
   p.defer_ready = nullptr;
-  {   // windows this launch completes: this rank's share of the deal (exact, not the padded n_local)
-    long long todo = n_windows;
-    if (!p.run_offsets && dealt && p.sh_block_sh >= 0) {
-      const long long span = (long long)ex->block * p.sh_world;
-      const long long full = n_windows / span, rest = n_windows - full * span;
-      long long part = rest - (long long)p.sh_rank * ex->block;
-      part = part < 0 ? 0 : (part > ex->block ? ex->block : part);
-      todo = full * ex->block + part;
-    }
-    p.n_todo = todo;
-  }
+  p.n_todo = 0;
   if (need > 0 && ls->d_defer && ls->defer_bytes >= need && slots > 0) {
     p.defer_ready = reinterpret_cast<unsigned*>(ls->d_defer);
     p.defer_buf = ls->d_defer + ready_bytes;
