@@ -628,8 +628,9 @@ def formats_rows(ctx, dev, timer):
 
 
 def facade_latency(dev):
-    """BicycleModel.run through the reference-shaped facade (one H2D + launch + D2H per call) beside
-    the reference's own 15 us per call (vmvo/bicycle_model.py:40-78)."""
+    """BicycleModel.run / run_sequence through the reference-shaped facade (host buffers, one launch
+    and one synchronisation per call) beside the reference's own 15 us per step (BASELINE.md 2;
+    vmvo/bicycle_model.py:40-78)."""
     from vehiclemodelvisualodometry_b200 import BicycleModel, State
 
     m = BicycleModel(state=State(x=0.0, y=0.0, theta=0.0, velocity=5.0, steering_angle=0.0))

@@ -280,6 +280,15 @@ int vmvo_rollout_f32(vmvo_ctx* ctx, int64_t n_seq, int32_t n_steps, const float*
                      const float* d_vel, float dt, const float* d_state0, float max_steer,
                      float max_accel, float* d_out, int32_t* d_fail, void* stream);
 
+/* The scalar caller's form of the same operator (BicycleModel.run / run_sequence are called one step
+ * or one short sequence at a time, vmvo/bicycle_model.py:40-92): HOST pointers in and out, one
+ * sequence, synchronous.  The controls go through a pinned buffer of the ctx that the GPU reads in
+ * place; one launch and one stream synchronisation per call, no allocation, no torch.
+ * h_state0 [4], h_out [n_steps][3], h_fail [2] as above.                                          */
+int vmvo_rollout_host_f64(vmvo_ctx* ctx, int32_t n_steps, const double* h_steer, const double* h_vel,
+                          double dt, const double* h_state0, double max_steer, double max_accel,
+                          double* h_out, int32_t* h_fail);
+
 /* ---- a10: cost of given control sequences -------------------------------------------
  * The closure `cost` inside mpc_run (vmvo/utils/mpc.py:56-85): n_seq steering sequences
  * [n_seq][n_steps] at constant speed `velocity`, against one target polyline

@@ -322,7 +322,8 @@ def grid_costs(spec: SearchSpec, wt: WindowTargets, dt: float) -> np.ndarray:
     """Cost of every hypothesis, float64 [G_v, G_s], by rolling the model forward.
 
     Per step the term is  w_vo*|p - T_vo|^2 + w_gps*|p - T_gps|^2 + w_imu*wrap(th - th_imu)^2
-    + K*S^2 (zero-weight terms skipped), accumulated in step order like mpc.py:70-78.
+    + K*S^2 (zero-weight terms skipped), accumulated in step order like mpc.py:70-78 (the CUDA
+    kernels associate the same sums differently -- warp scans, butterflies -- and agree to ~1e-15).
     """
     N = wt.n_steps
     V, S = hypothesis_controls(spec, wt.v_seed, wt.s_seed, N, dt)

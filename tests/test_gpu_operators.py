@@ -84,6 +84,31 @@ def test_rollout_batch_random(cuda_device):
         np.testing.assert_allclose(poses[b], ref, rtol=0, atol=1e-10)
 
 
+def test_host_rollout_is_the_tensor_rollout(cuda_device):
+    """vmvo_rollout_host_f64 (what BicycleModel.run / run_sequence call: host buffers, pinned staging,
+    one launch) against vmvo_rollout_f64 through tensors: the same kernel, the same bits; sequences
+    that outgrow the staging buffer; the (kind, step) of a violated bound."""
+    rng = np.random.default_rng(81)
+    for n in (1, 2, 31, 32, 33, 100, 9000, 5):
+        steer = rng.uniform(-460, 460, n)
+        vel = np.abs(np.cumsum(rng.uniform(-0.4, 0.4, n)) + 8)
+        st0 = np.array([1.5, -2.0, 0.3, vel[0]])
+        got, kind, step = _lib.rollout_host_f64(steer, vel, 0.05, st0, 460.0, 10.0)
+        want, fail = rollout_batch(torch.tensor(steer[None], device=cuda_device),
+                                   torch.tensor(vel[None], device=cuda_device), 0.05,
+                                   torch.tensor(st0[None], device=cuda_device))
+        assert np.array_equal(got, want[0].cpu().numpy())
+        assert (kind, step) == (0, -1) and fail[0].tolist() == [0, -1]
+        if n >= 31:
+            np.testing.assert_allclose(got, O.rollout(steer, vel, 0.05, st0), rtol=0, atol=1e-9)
+    steer = np.array([1.0, 2.0, 500.0, 3.0])
+    got, kind, step = _lib.rollout_host_f64(steer, np.ones(4), 0.1, [0, 0, 0, 1.0], 460.0, 10.0)
+    assert (kind, step) == (_lib.FAIL_STEER, 2)
+    got, kind, step = _lib.rollout_host_f64(np.zeros(3), [1.0, 1.2, 9.0], 0.1, [0, 0, 0, 1.0], 460.0, 10.0)
+    assert (kind, step) == (_lib.FAIL_ACCEL, 2)
+    assert _lib.rollout_host_f64(np.zeros(0), np.zeros(0), 0.1, [0, 0, 0, 1.0], 460.0, 10.0)[1:] == (0, -1)
+
+
 # ---- a7 / a8 / a9 / a13 ----------------------------------------------------------------------
 def test_sub_trajectory_from_time_kat(cuda_device):
     tr = Trajectory(x=[0, 1, 2, 3, 4], y=[0, 0, 1, 1, 2], theta=[.5, .5, .6, .7, .8], velocity=[1] * 5,

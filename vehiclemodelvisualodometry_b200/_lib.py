@@ -91,6 +91,7 @@ _SIGNATURES = {
                                    _c_vp, _c_vp, _c_vp]),
     "vmvo_rollout_f32": (C.c_int, [_c_vp, _c_i64, _c_i32, _c_vp, _c_vp, _c_f32, _c_vp, _c_f32, _c_f32,
                                    _c_vp, _c_vp, _c_vp]),
+    "vmvo_rollout_host_f64": (C.c_int, [_c_vp, _c_i32, _c_vp, _c_vp, _c_f64, _c_vp, _c_f64, _c_f64, _c_vp, _c_vp]),
     "vmvo_sequence_cost_f64": (C.c_int, [_c_vp, _c_i64, _c_i32, _c_vp, _c_f64, _c_f64, _c_vp, _c_f64,
                                          _c_vp, _c_vp]),
     "vmvo_extract_window_f64": (C.c_int, [_c_vp, _c_i32, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),
@@ -250,6 +251,22 @@ def stream_ptr(device=None) -> int:
 
 
 # ---- small NumPy-in / NumPy-out operators used by the Trajectory / BicycleModel facades --------
+
+def rollout_host_f64(steer, vel, dt: float, state0, max_steer: float, max_accel: float):
+    """One control sequence through ``vmvo_rollout_host_f64``: NumPy in, (poses [n, 3], fail kind,
+    fail step) out; one launch and one stream synchronisation, no tensors."""
+    ctx = context()
+    steer = np.ascontiguousarray(steer, dtype=np.float64)
+    vel = np.ascontiguousarray(vel, dtype=np.float64)
+    s0 = np.ascontiguousarray(state0, dtype=np.float64)
+    n = steer.shape[0]
+    out = np.empty((n, 3), dtype=np.float64)
+    fail = np.zeros(2, dtype=np.int32)
+    ctx.check(ctx.lib.vmvo_rollout_host_f64(ctx.handle, n, steer.ctypes.data, vel.ctypes.data, float(dt),
+                                            s0.ctypes.data, float(max_steer), float(max_accel),
+                                            out.ctypes.data, fail.ctypes.data), "vmvo_rollout_host_f64")
+    return out, int(fail[0]), int(fail[1])
+
 
 def _dev(a, dtype):
     import torch

@@ -84,16 +84,12 @@ class BicycleModel:
         n = len(steering_angles)
         if n == 0:
             return []
-        dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
-        if dev is None:
-            _lib.context()  # raises: no CUDA device, no CPU fallback
-        s = torch.as_tensor(np.asarray(steering_angles, dtype=np.float64)).reshape(1, n).to(dev)
-        v = torch.as_tensor(np.asarray(velocities, dtype=np.float64)).reshape(1, n).to(dev)
+        # the scalar caller's path (vmvo_rollout_host_f64): host buffers in and out, one launch and one
+        # stream synchronisation per call; raises when there is no GPU (no CPU fallback)
         st = self.state
-        s0 = torch.tensor([[st.x, st.y, st.theta, st.velocity]], dtype=torch.float64, device=dev)
-        poses, fail = rollout_batch(s, v, float(dt), s0, self.max_steer, self.max_accel)
-        poses = poses[0].cpu().numpy()
-        kind, step = (int(z) for z in fail[0].cpu().tolist())
+        poses, kind, step = _lib.rollout_host_f64(steering_angles, velocities, float(dt),
+                                                  (st.x, st.y, st.theta, st.velocity),
+                                                  self.max_steer, self.max_accel)
         good = n if kind == 0 else step
         states: List[State] = []
         sa = np.asarray(steering_angles, dtype=np.float64)

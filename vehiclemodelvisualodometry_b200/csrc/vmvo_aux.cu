@@ -397,6 +397,9 @@ extern "C" int vmvo_ctx_create(int device, vmvo_ctx** out) {
   ctx->err[0] = 0;
   ctx->d_counters = nullptr;
   ctx->slot_mutex = new std::mutex();
+  ctx->h_stage = nullptr;
+  ctx->h_stage_bytes = 0;
+  ctx->host_stream = nullptr;
   ctx->tune = vmvo_tuning{-1, -1, -1, -1, -1, -1, -1, -1};
   for (int q = 0; q < kLaunchSlots; ++q) ctx->slots[q] = vmvo_launch_slot{nullptr, nullptr, 0, nullptr, false, false};
   DeviceGuard guard(device);
@@ -425,6 +428,8 @@ extern "C" int vmvo_ctx_destroy(vmvo_ctx* ctx) {
   {
     DeviceGuard guard(ctx->device);
     cudaFree(ctx->d_counters);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->host_stream) cudaStreamDestroy(ctx->host_stream);
     for (int q = 0; q < kLaunchSlots; ++q) {
       if (ctx->slots[q].d_defer) cudaFree(ctx->slots[q].d_defer);
       if (ctx->slots[q].done) cudaEventDestroy(ctx->slots[q].done);
@@ -706,6 +711,55 @@ extern "C" int vmvo_rollout_f32(vmvo_ctx* ctx, int64_t n_seq, int32_t n_steps, c
                                 float max_accel, float* d_out, int32_t* d_fail, void* stream) {
   return rollout_impl<float>(ctx, n_seq, n_steps, d_steer, d_vel, dt, d_state0, max_steer, max_accel,
                              d_out, d_fail, stream);
+}
+
+// ---- a1 / a2 for a scalar caller: host buffers in, host buffers out, synchronous ---------------------
+// BicycleModel.run / run_sequence of the reference are called one step or one short sequence at a
+// time from Python (vmvo/bicycle_model.py:40-92).  Through tensors that is an allocation, three
+// copies and a launch per call; here the controls are written into a pinned buffer the GPU reads in
+// place (mapped host memory), the same rollout_kernel runs on a stream of the ctx's own, and the poses
+// come back through the same buffer: one launch and one stream synchronisation per call.
+extern "C" int vmvo_rollout_host_f64(vmvo_ctx* ctx, int32_t n_steps, const double* h_steer,
+                                     const double* h_vel, double dt, const double* h_state0,
+                                     double max_steer, double max_accel, double* h_out,
+                                     int32_t* h_fail) {
+  if (!ctx) return VMVO_ERR_BAD_ARG;
+  if (n_steps < 0 || !h_state0 || !h_fail || (n_steps > 0 && (!h_steer || !h_vel || !h_out)))
+    return fail(ctx, VMVO_ERR_BAD_ARG, "bad argument");
+  if (n_steps == 0) {
+    h_fail[0] = VMVO_FAIL_NONE;
+    h_fail[1] = -1;
+    return VMVO_OK;
+  }
+  VMVO_ON_DEVICE(ctx);
+  std::lock_guard<std::mutex> lock(*ctx->slot_mutex);
+  const size_t n = (size_t)n_steps;
+  const size_t need = (n * 5 + 4) * sizeof(double) + 16;
+  if (ctx->h_stage_bytes < need) {
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    ctx->h_stage = nullptr;
+    ctx->h_stage_bytes = 0;
+    const size_t bytes = need < 65536 ? 65536 : need * 2;
+    VMVO_CUDA(ctx, cudaHostAlloc(&ctx->h_stage, bytes, cudaHostAllocMapped | cudaHostAllocPortable));
+    ctx->h_stage_bytes = bytes;
+  }
+  if (!ctx->host_stream) VMVO_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->host_stream, cudaStreamNonBlocking));
+  double* hs = reinterpret_cast<double*>(ctx->h_stage);      // [steer n][vel n][state0 4][out 3n][fail 2 x int]
+  memcpy(hs, h_steer, n * sizeof(double));
+  memcpy(hs + n, h_vel, n * sizeof(double));
+  memcpy(hs + 2 * n, h_state0, 4 * sizeof(double));
+  void* dv = nullptr;
+  VMVO_CUDA(ctx, cudaHostGetDevicePointer(&dv, ctx->h_stage, 0));
+  double* ds = reinterpret_cast<double*>(dv);
+  int* d_fail = reinterpret_cast<int*>(ds + 5 * n + 4);
+  rollout_kernel<double><<<1, 32, 0, ctx->host_stream>>>(1, n_steps, ds, ds + n, dt, ds + 2 * n, 2.83972, 13.27,
+                                                         max_steer, max_accel, ds + 2 * n + 4, d_fail);
+  int rc = check_launch(ctx, "rollout_kernel");
+  if (rc) return rc;
+  VMVO_CUDA(ctx, cudaStreamSynchronize(ctx->host_stream));
+  memcpy(h_out, hs + 2 * n + 4, 3 * n * sizeof(double));
+  memcpy(h_fail, reinterpret_cast<int*>(hs + 5 * n + 4), 2 * sizeof(int));
+  return VMVO_OK;
 }
 
 extern "C" int vmvo_sequence_cost_f64(vmvo_ctx* ctx, int64_t n_seq, int32_t n_steps,

@@ -37,6 +37,10 @@ struct vmvo_ctx {
   std::mutex* slot_mutex;
   long long launches;
   vmvo_tuning tune;
+  // vmvo_rollout_host_f64: a pinned, device-mapped staging buffer and a stream of the ctx's own
+  void* h_stage;
+  size_t h_stage_bytes;
+  cudaStream_t host_stream;
   char err[512];
 };
 
