@@ -547,6 +547,8 @@ __device__ __forceinline__ void scan_item_fast(int N, int gs, int vd_cols, int j
     for (int q = 0; q < 4; ++q) {
       ex[q] = __ffma2_rn(v2[q], c2[q], __fadd2_rn(ex[q], ndx));
       ey[q] = __ffma2_rn(v2[q], s2[q], __fadd2_rn(ey[q], ndy));
+      // (scalar FFMAs for these eight accumulations -- 16 FFMA instead of 8 FFMA2, less FMA-pipe time,
+      // eight more issue slots -- measured the same on the dense grid and 1.5 % slower on 32x32)
       JA[q] = __ffma2_rn(ex[q], ex[q], JA[q]);
       JA2[q] = __ffma2_rn(ey[q], ey[q], JA2[q]);
       if (DUAL) {
