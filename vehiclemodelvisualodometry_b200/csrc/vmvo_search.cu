@@ -24,6 +24,10 @@
 #include <math_constants.h>
 #include <stdlib.h>
 
+#ifndef VMVO_MINB
+#define VMVO_MINB 2     // CTAs of eight warps per SM the search kernel is built for (128 registers)
+#endif
+
 namespace vmvo {
 
 constexpr int kCandPerWarp = 128;  // candidate list entries per team warp (flushed when full)
@@ -97,6 +101,11 @@ struct SearchParams {
   unsigned* defer_ready;               // [defer_slots], cleared with the counters before the launch
   unsigned long long* windows_done;    // (counts finished TEAMS)
   long long n_todo;                    // teams of the launch
+  // window preparation as a pass of its own (vmvo_window_prep_kernel): one record per queue item,
+  // staged into shared memory by the fetcher instead of the raw poses; NULL: phases A1-A3 run in
+  // the search kernel
+  unsigned char* prep;
+  int prep_stride;
   float* dbg_cost;       // optional [n_windows][gv*gs] FP32 scan costs   (tests only)
   float* dbg_err;        // optional [n_windows][gv*gs] error-band widths (tests only)
 };
@@ -119,10 +128,14 @@ struct SmemLayout {
   int off_raw, off_loc, off_loci, off_tgt, off_df, off_dab, off_fi, off_keep, off_tl, off_js,
       off_ts, off_tsp, off_vd, off_cand, total;
   // P poses per window, n_streams pose streams staged, optional terms only when configured
+  int raw_buf;   // bytes of one staging buffer
   __host__ __device__ SmemLayout(int P, int gs, int vd_cols, int team_warps, int n_streams,
-                                 bool dual, bool imu, bool traverse, int pose_bytes) {
+                                 bool dual, bool imu, bool traverse, int pose_bytes, int prep_bytes = 0) {
     int o = kHeaderBytes;                       // barriers, window ids, reductions
-    off_raw = o;  o += 2 * n_streams * P * pose_bytes;  // raw[2 buffers][streams][P] float4/double4
+    // raw[2 buffers][streams][P] float4/double4 -- or, with a preparation pass, two window records
+    raw_buf = n_streams * P * pose_bytes;
+    if (prep_bytes > raw_buf) raw_buf = prep_bytes;
+    off_raw = o;  o += 2 * raw_buf;
     off_loc = o;  o += n_streams * 3 * P * 8;   // double loc[streams][3][P]  (lx, ly, lth)
     off_loci = o; o += imu ? P * 8 : 0;         // double imu yaw relative to the window start
     off_tgt = o;  o += (2 + (dual ? 2 : 0) + (imu ? 1 : 0)) * P * 8;  // tAx, tAy, [tBx, tBy], [tI]
@@ -164,6 +177,31 @@ struct DeferHdr {
 constexpr int kDeferHdrBytes = 128;
 static_assert(sizeof(DeferHdr) <= kDeferHdrBytes, "deferred-window header too large");
 
+// ---- window preparation records (vmvo_window_prep_kernel -> the search kernel) -------------------
+// What phases A1-A3 produce for one window: seeds, step count, status, duplicate classes, the band's
+// maxima, then the FP32 target increments of the scan and the float64 targets of the re-score, laid
+// out like the search kernel's own arrays so that it can work on the staged record in place.
+struct PrepHdr {
+  double v_seed, s_seed, dt;
+  int n_targets, n_steps, status;     // status: EMPTY | NO_FRAMES / TOO_LONG for a window without a search
+  int n_dead, sat_lo, sat_hi, len;
+  float dmax, dabmax, imax;           // dmax = +inf: a non-finite input somewhere in the window
+};
+constexpr int kPrepHdrBytes = 128;
+static_assert(sizeof(PrepHdr) <= kPrepHdrBytes, "preparation header too large");
+struct PrepLayout {
+  int off_df, off_dab, off_fi, off_tgt, total;
+  __host__ __device__ PrepLayout(int P, bool dual, bool imu) {
+    int o = kPrepHdrBytes;
+    off_df = o;  o += P * 8;                    // float2 D[k]
+    off_dab = o; o += dual ? P * 8 : 0;         // float2 DAB[k]
+    off_fi = o;  o += imu ? P * 4 : 0;          // float imu target per step
+    o = (o + 15) & ~15;
+    off_tgt = o; o += (2 + (dual ? 2 : 0) + (imu ? 1 : 0)) * P * 8;
+    total = (o + 127) & ~127;
+  }
+};
+
 // window-level inputs of the FP32 error band
 struct BandWin {       // window-level inputs, identical in every thread
   float n, s2, s4;     // N, sum k^2, bound on sum ((k^2+k)/2)^2
@@ -195,6 +233,7 @@ struct SmemHeader {
   int wlen[2];
   long long wstart[2];
   double wdt[2];
+  long long witem[2];   // queue item of the window in each staging buffer (its preparation record)
 };
 static_assert(sizeof(SmemHeader) <= kHeaderBytes, "header too large");
 
@@ -598,8 +637,10 @@ vmvo_window_search_kernel(const SearchParams p) {
   extern __shared__ __align__(1024) unsigned char smem_cta[];
   const int P = p.maxp;
   const int n_streams = p.load_vo + p.load_gps;
+  const bool use_prep = p.prep != nullptr;     // phases A1-A3 were run by vmvo_window_prep_kernel
+  const PrepLayout prl(P, DUAL, IMU);
   const SmemLayout lay(P, p.gs, p.vd_cols, p.team_warps, n_streams, DUAL, IMU,
-                       p.target_mode == VMVO_TARGET_TRAVERSE, (int)sizeof(Pose4));
+                       p.target_mode == VMVO_TARGET_TRAVERSE, (int)sizeof(Pose4), use_prep ? prl.total : 0);
   // stream s (0 = VO, 1 = GPS) lives in slot s when both are staged, else in slot 0
   const int slot_vo = 0, slot_gps = p.load_vo ? 1 : 0;
   const Team team{p.team_warps, p.team_warps * 32, (int)threadIdx.x >> p.t_sh};
@@ -637,7 +678,14 @@ vmvo_window_search_kernel(const SearchParams p) {
   const bool ksteer = p.k_steer != 0.0;
   const double kd = kDegToRad / p.ratio;   // steering-wheel degrees -> road-wheel radians
 
+  long long q_item = 0;      // fetcher thread: the queue item behind the window just popped
   auto issue_load = [&](long long w, int buf) {  // the fetcher thread only
+    if (use_prep) {          // the window's preparation record instead of its poses
+      mbar_arrive_expect_tx(&hd->mbar[buf], (unsigned)prl.total);
+      bulk_g2s(smem + lay.off_raw + buf * lay.raw_buf, p.prep + (size_t)q_item * p.prep_stride,
+               (unsigned)prl.total, &hd->mbar[buf]);
+      return;
+    }
     long long start;
     int len, drv;
     if (p.win_start) {
@@ -711,6 +759,7 @@ vmvo_window_search_kernel(const SearchParams p) {
     const bool dealt = p.sh_world > 1;
     for (;;) {
       long long r = (long long)atomicAdd(p.work_counter, 1ULL);
+      q_item = r;
       if (!chained) {
         if (!dealt || p.sh_block_sh < 0) return r < p.n_local ? r : p.n_windows;
         if (r >= p.n_local) return p.n_windows;
@@ -737,6 +786,9 @@ vmvo_window_search_kernel(const SearchParams p) {
     mbar_init(&hd->mbar[1], 1);
     mbar_fence_init();
     hd->count = 0;
+    // with a preparation pass this kernel is its programmatic dependent: everything above ran beside
+    // the pass's last wave; the records are complete from here on
+    if (use_prep) asm volatile("griddepcontrol.wait;" ::: "memory");
     const long long w = next_window(-1, 0);
     hd->wid[0] = w;
     if (w < p.n_windows) issue_load(w, 0);
@@ -762,9 +814,19 @@ vmvo_window_search_kernel(const SearchParams p) {
     }
     if (chained && hd->first[cur]) s_chain = 0.0;   // optimize_trajectory_v2.py:46
     const long long start = hd->wstart[cur];
-    const int len = hd->wlen[cur];
-    const double dt = hd->wdt[cur];
     mbar_wait(&hd->mbar[cur], (unsigned)((it >> 1) & 1));
+    // with a preparation pass the staged bytes are the window's record: header, FP32 increments,
+    // float64 targets -- used in place
+    const PrepHdr* ph = reinterpret_cast<const PrepHdr*>(smem + lay.off_raw + cur * lay.raw_buf);
+    const int len = use_prep ? ph->len : hd->wlen[cur];
+    const double dt = use_prep ? ph->dt : hd->wdt[cur];
+    if (use_prep) {
+      unsigned char* rec = smem + lay.off_raw + cur * lay.raw_buf;
+      Df = reinterpret_cast<float2*>(rec + prl.off_df);
+      Dab = reinterpret_cast<float2*>(rec + prl.off_dab);
+      fI = reinterpret_cast<float*>(rec + prl.off_fi);
+      tgt = reinterpret_cast<double*>(rec + prl.off_tgt);
+    }
 
     // the record of a window that is not searched (too long / empty): everything but the status,
     // the step count and the seeds stays "none"
@@ -795,6 +857,18 @@ vmvo_window_search_kernel(const SearchParams p) {
 
     const int slot_prim = p.primary == VMVO_PRIMARY_VO ? slot_vo : slot_gps;
     const Pose4* rp = raw + (cur * n_streams + slot_prim) * P;
+    if (use_prep) {
+      if (tid == 0) {
+        hd->wi.v_seed = ph->v_seed;
+        hd->wi.s_seed = ph->s_seed;
+        hd->wi.dt = ph->dt;
+        hd->wi.n_targets = ph->n_targets;
+        hd->wi.n_steps = ph->n_steps;
+        hd->wi.n_dead = ph->n_dead;
+        hd->wi.sat_lo = ph->sat_lo;
+        hd->wi.sat_hi = ph->sat_hi;
+      }
+    } else {
     if (warp == (NW > 1 ? 1 : 0)) {
       // rows that never move: a_i <= 0 and V_w + a_i*t_1 <= 0 (a_i grows with i: a prefix).  On a
       // second warp when the team has one: warp 0 has the seed's division and atan to wait for.
@@ -920,6 +994,7 @@ vmvo_window_search_kernel(const SearchParams p) {
         hd->wi.sat_hi = sat_hi;
       }
     }
+    }
     team.sync();
 
     const int n_targets = hd->wi.n_targets;
@@ -931,7 +1006,12 @@ vmvo_window_search_kernel(const SearchParams p) {
     // ---- phase A3: targets in float64, FP32 increments for the scan, finiteness -------------
     bool finite = isfinite(v_seed) && isfinite(s_seed) && isfinite(dt);
     float dmax = 0.f, dabmax = 0.f, imax = 0.f;
-    {
+    if (use_prep) {      // (the record's maxima already carry a non-finite input as dmax = +inf)
+      finite = true;
+      dmax = ph->dmax;
+      dabmax = ph->dabmax;
+      imax = ph->imax;
+    } else {
       const int slot_a = sA == 0 ? slot_vo : slot_gps;
       const double* aX = loc + (slot_a * 3 + 0) * P;
       const double* aY = loc + (slot_a * 3 + 1) * P;
@@ -1494,6 +1574,273 @@ vmvo_window_search_kernel(const SearchParams p) {
   }
 }
 
+// ---- window preparation as a pass of its own ----------------------------------------------------------
+// Phases A1-A3 of the search -- local frames (a7), seeds, decimation (a9), float64 targets, FP32 target
+// increments, the band's maxima, the duplicate classes -- are a few hundred instructions of serial
+// float64 work per window (a sincos, a division, an atan), which a two-warp team of the search kernel
+// executes at 16 warps per SM with its partner warp waiting.  Here ONE WARP prepares one window, all
+// windows of the launch side by side at full occupancy; the search kernel then stages the finished
+// record (PrepLayout) instead of the raw poses and starts at the tables.  The operations are the search
+// kernel's own, in the same order: the records hold the same bits either way (every parity test runs
+// through both paths).  Item r of the queue is window deal(r), exactly as in the search kernel.
+constexpr int kPrepWarps = 8;
+
+// GS lanes per window: a whole warp, or -- for windows of at most 32 poses, the small-grid case the
+// pass exists for -- half a warp, two windows per warp side by side (the pass is a latency chain per
+// window, so what it costs is waves of resident windows: 11.3 us -> measured below with 16 lanes).
+// The two halves run as independent groups: every vote, shuffle and reduction carries the group's
+// lane mask.
+template <bool DUAL, bool IMU, typename SF, int GS>
+__global__ void __launch_bounds__(32 * kPrepWarps)
+vmvo_window_prep_kernel(const SearchParams p) {
+  using Pose4 = typename PoseOf<SF>::type;
+  extern __shared__ __align__(16) unsigned char smem_prep[];
+  const int P = p.maxp;
+  constexpr int kGroups = 32 / GS;                                  // windows per warp
+  const int lane = threadIdx.x & (GS - 1);                          // lane within the group
+  const int gshift = (threadIdx.x & 31) & ~(GS - 1);                // first lane of the group in its warp
+  const unsigned gmask = GS == 32 ? FULL : (((1u << GS) - 1u) << gshift);
+  const int warp = (threadIdx.x >> 5) * kGroups + (gshift / GS);    // group index within the CTA
+  const int n_streams = p.load_vo + p.load_gps;
+  const int slot_vo = 0, slot_gps = p.load_vo ? 1 : 0;
+  const bool traverse = p.target_mode == VMVO_TARGET_TRAVERSE;
+  const int warp_bytes = (n_streams * 3 * P + (IMU ? P : 0)) * 8 + (traverse ? ((P * 4 + 15) & ~15) : 0);
+  unsigned char* ws = smem_prep + (size_t)warp * warp_bytes;
+  double* loc = reinterpret_cast<double*>(ws);
+  double* loci = loc + n_streams * 3 * P;
+  int* keep = reinterpret_cast<int*>(ws + (n_streams * 3 * P + (IMU ? P : 0)) * 8);
+  const Pose4* g_vo = reinterpret_cast<const Pose4*>(p.vo);
+  const Pose4* g_gps = reinterpret_cast<const Pose4*>(p.gps);
+  const SF* g_imu = reinterpret_cast<const SF*>(p.imu);
+  const PrepLayout prl(P, DUAL, IMU);
+  const int sA = p.use_vo ? 0 : 1;
+  const int off = p.target_offset;
+  const unsigned long long kNaN = 0x7ff8000000000000ULL;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // (the search waits before its first record)
+
+  for (long long r = (long long)blockIdx.x * (kPrepWarps * kGroups) + warp; r < p.n_local;
+       r += (long long)gridDim.x * (kPrepWarps * kGroups)) {
+    long long w = r;
+    if (p.sh_world > 1 && p.sh_block_sh >= 0) {
+      const long long b = r >> p.sh_block_sh;
+      w = (((b * p.sh_world + p.sh_rank) << p.sh_block_sh)) + (r - (b << p.sh_block_sh));
+    }
+    if (w >= p.n_windows) continue;        // (the deal's padding: the search never asks for it)
+    unsigned char* rec = p.prep + (size_t)r * p.prep_stride;
+    PrepHdr* hdr = reinterpret_cast<PrepHdr*>(rec);
+    float2* Df = reinterpret_cast<float2*>(rec + prl.off_df);
+    float2* Dab = reinterpret_cast<float2*>(rec + prl.off_dab);
+    float* fI = reinterpret_cast<float*>(rec + prl.off_fi);
+    double* tgt = reinterpret_cast<double*>(rec + prl.off_tgt);
+    // the plan entry (as the search kernel's fetcher derives it)
+    long long start;
+    int len, drv;
+    if (p.win_start) {
+      start = p.win_start[w];
+      len = p.win_len[w];
+      drv = p.win_drive[w];
+    } else {
+      int lo = 0, hi = p.n_drives;
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (p.win_off[mid] <= w) lo = mid; else hi = mid;
+      }
+      drv = lo;
+      const long long i = w - p.win_off[drv], f0 = p.drive_off[drv], n = p.drive_off[drv + 1] - f0;
+      long long e = i + p.window_frames + 1;
+      e = e < n ? e : n;
+      start = f0 + i;
+      len = (int)(e - i);
+    }
+    const double dt = p.dt_drive[drv];
+    if (len > P || len < 1) {              // not searched: the search kernel only looks at len
+      if (lane == 0) {
+        PrepHdr h;
+        h.v_seed = h.s_seed = __longlong_as_double((long long)kNaN);
+        h.dt = dt;
+        h.n_targets = h.n_steps = 0;
+        h.status = len < 1 ? (VMVO_WIN_EMPTY | VMVO_WIN_NO_FRAMES) : VMVO_WIN_TOO_LONG;
+        h.n_dead = 0; h.sat_lo = 0; h.sat_hi = -1; h.len = len;
+        h.dmax = h.dabmax = h.imax = 0.f;
+        *hdr = h;
+      }
+      continue;
+    }
+    const int slot_prim = p.primary == VMVO_PRIMARY_VO ? slot_vo : slot_gps;
+    const Pose4* rp = (p.primary == VMVO_PRIMARY_VO ? g_vo : g_gps) + start;
+
+    // rows that never move
+    int n_dead = 0;
+    {
+      const double v_seed = p.seed_mode == VMVO_SEED_GIVEN
+                                ? p.seeds[2 * w]
+                                : dmul(dadd((double)rp[0].w, (double)rp[len - 1].w), 0.5);
+      for (int i0 = 0; i0 < p.gv; i0 += GS) {
+        const int i = i0 + lane;
+        bool dead = false;
+        if (i < p.gv) {
+          const double a = grid_rate(p.max_accel, i, p.gv);
+          dead = a <= 0.0 && !(dadd(v_seed, dmul(a, dmul(1.0, dt))) > 0.0) && v_seed == v_seed;
+        }
+        const unsigned b = __ballot_sync(gmask, dead);
+        n_dead += __popc(b);
+        if (b != gmask) break;
+      }
+    }
+
+    // ---- phase A1: local frames (a7) -----------------------------------------------------
+    for (int s = 0; s < 2; ++s) {
+      if (!(s == 0 ? p.load_vo : p.load_gps)) continue;
+      const int slot = s == 0 ? slot_vo : slot_gps;
+      const Pose4* rs = (s == 0 ? g_vo : g_gps) + start;
+      const Pose4 p0 = rs[0];
+      const double th0 = (double)p0.z;
+      double sn, cs;
+      sincos(th0, &sn, &cs);
+      double* lx = loc + (slot * 3 + 0) * P;
+      double* ly = loc + (slot * 3 + 1) * P;
+      double* lt = loc + (slot * 3 + 2) * P;
+      for (int m = lane; m < len; m += GS) {
+        const Pose4 q = rs[m];
+        const double dx = dsub((double)q.x, (double)p0.x);
+        const double dy = dsub((double)q.y, (double)p0.y);
+        lx[m] = dadd(dmul(dx, cs), dmul(dy, sn));
+        ly[m] = dadd(dmul(-dx, sn), dmul(dy, cs));
+        lt[m] = dsub((double)q.z, th0);
+      }
+    }
+    if (IMU) {
+      const double y0 = (double)g_imu[start];
+      for (int m = lane; m < len; m += GS) loci[m] = dsub((double)g_imu[start + m], y0);
+    }
+    __syncwarp(gmask);
+
+    // ---- phase A2: seeds, decimation (a9) -----------------------------------------------
+    const double* plx = loc + (slot_prim * 3 + 0) * P;
+    const double* ply = loc + (slot_prim * 3 + 1) * P;
+    const double* plt = loc + (slot_prim * 3 + 2) * P;
+    double v_seed, s_seed;
+    if (p.seed_mode == VMVO_SEED_GIVEN) {
+      v_seed = p.seeds[2 * w];
+      s_seed = p.seeds[2 * w + 1];
+    } else {
+      v_seed = dmul(dadd((double)rp[0].w, (double)rp[len - 1].w), 0.5);   // (/ 2, exactly)
+      s_seed = 0.0;
+      if (len >= 2 && dmul(v_seed, dt) > 1e-6) {
+        const double dth0 = dsub(plt[1], plt[0]);
+        const double dth = fabs(dth0) < kPi ? dth0 : remainder(dth0, kTwoPi);
+        const double ang = atan(ddiv(dmul(p.L, dth), dmul(v_seed, dt)));
+        s_seed = dmul(dmul(ang, kRadToDeg), p.ratio);
+        s_seed = s_seed < -p.max_steer ? -p.max_steer : s_seed;
+        s_seed = s_seed > p.max_steer ? p.max_steer : s_seed;
+      }
+    }
+    int n_targets = len;
+    if (traverse) {
+      if (lane == 0) {  // sequential by definition (distance accumulator with reset)
+        const double D = dmul(v_seed, dt);
+        int cnt = 1;
+        keep[0] = 0;
+        double dist = 0.0;
+        for (int i = 1; i < len; ++i) {
+          const double ddx = dsub(plx[i], plx[i - 1]), ddy = dsub(ply[i], ply[i - 1]);
+          const double seg = sqrt(dadd(dmul(ddx, ddx), dmul(ddy, ddy)));
+          if (dadd(dist, seg) > D) {
+            keep[cnt++] = i - 1;
+            dist = seg;
+          } else {
+            dist = dadd(dist, seg);
+          }
+        }
+        n_targets = cnt;
+      }
+      n_targets = __shfl_sync(gmask, n_targets, gshift);
+      __syncwarp(gmask);
+    }
+    int sat_lo = 0, sat_hi = -1;
+    if (s_seed == p.max_steer || s_seed == -p.max_steer) {
+      const bool hi = s_seed > 0;
+      int first = p.gs, last = -1;
+      for (int j0 = 0; j0 < p.gs; j0 += GS) {
+        const int j = j0 + lane;
+        bool in = false;
+        if (j < p.gs) {
+          const double rr = grid_rate(p.max_rate, j, p.gs);
+          in = hi ? (rr >= 0.0) : (rr <= 0.0);
+        }
+        const unsigned b = __ballot_sync(gmask, in) >> gshift;      // (bit l = lane l of the group)
+        if (b) {
+          first = min(first, j0 + __ffs(b) - 1);
+          last = max(last, j0 + 31 - __clz(b));
+        }
+      }
+      sat_lo = first;
+      sat_hi = last;
+    }
+    const int N = n_targets > 1 ? n_targets - 1 : 0;
+
+    // ---- phase A3: targets in float64, FP32 increments for the scan, finiteness -------------
+    bool finite = isfinite(v_seed) && isfinite(s_seed) && isfinite(dt);
+    float dmax = 0.f, dabmax = 0.f, imax = 0.f;
+    {
+      const int slot_a = sA == 0 ? slot_vo : slot_gps;
+      const double* aX = loc + (slot_a * 3 + 0) * P;
+      const double* aY = loc + (slot_a * 3 + 1) * P;
+      const double* bX = loc + (slot_gps * 3 + 0) * P;   // B is GPS (DUAL only)
+      const double* bY = loc + (slot_gps * 3 + 1) * P;
+      for (int q = lane; q < n_targets; q += GS) {
+        const int m = traverse ? keep[q] : q;
+        const double ax = aX[m], ay = aY[m];
+        tgt[q] = ax;
+        tgt[P + q] = ay;
+        finite = finite && isfinite(ax) && isfinite(ay);
+        if (DUAL) {
+          const double bx = bX[m], by = bY[m];
+          tgt[2 * P + q] = bx;
+          tgt[3 * P + q] = by;
+          finite = finite && isfinite(bx) && isfinite(by);
+        }
+        if (IMU) {
+          const double yi = loci[m];
+          tgt[(DUAL ? 4 : 2) * P + q] = yi;
+          finite = finite && isfinite(yi);
+        }
+        const int k = q + off;
+        if (k >= 1 && k <= N) {
+          const int mp = (q >= 1) ? (traverse ? keep[q - 1] : q - 1) : -1;
+          const double px = (k >= 2) ? aX[mp] : 0.0, py = (k >= 2) ? aY[mp] : 0.0;
+          const float dx = (float)dsub(ax, px), dy = (float)dsub(ay, py);
+          Df[k] = make_float2(dx, dy);
+          dmax = fmaxf(dmax, fmaxf(fabsf(dx), fabsf(dy)));
+          if (DUAL) {
+            const float ex = (float)dsub(ax, bX[m]), ey = (float)dsub(ay, bY[m]);
+            Dab[k] = make_float2(ex, ey);
+            dabmax = fmaxf(dabmax, fmaxf(fabsf(ex), fabsf(ey)));
+          }
+          if (IMU) {
+            const float yi = (float)loci[m];
+            fI[k] = yi;
+            imax = fmaxf(imax, fabsf(yi));
+          }
+        }
+      }
+    }
+    if (!__all_sync(gmask, finite)) dmax = CUDART_INF_F;
+    dmax = __uint_as_float(__reduce_max_sync(gmask, __float_as_uint(dmax)));
+    if (DUAL) dabmax = __uint_as_float(__reduce_max_sync(gmask, __float_as_uint(dabmax)));
+    if (IMU) imax = __uint_as_float(__reduce_max_sync(gmask, __float_as_uint(imax)));
+    if (lane == 0) {
+      PrepHdr h;
+      h.v_seed = v_seed; h.s_seed = s_seed; h.dt = dt;
+      h.n_targets = n_targets; h.n_steps = N; h.status = 0;
+      h.n_dead = n_dead; h.sat_lo = sat_lo; h.sat_hi = sat_hi; h.len = len;
+      h.dmax = dmax; h.dabmax = dabmax; h.imax = imax;
+      *hdr = h;
+    }
+    __syncwarp(gmask);
+  }
+}
+
 // ---- second kernel: the float64 re-scores of the deferred windows -------------------------------
 // One CTA of eight warps per slot.  The slot (header, float64 targets, list: a few KB) is copied to
 // shared memory first, and the warps share the list four entries at a time, each through the same
@@ -1708,8 +2055,9 @@ static int launch_search_v(vmvo_ctx* ctx, const SearchParams& p_in, cudaStream_t
   // warps are dealt to the four SM sub-partitions by warp index, so two-warp CTAs leave two of them idle)
   const int teams = ctx->tune.cta_teams > 0 ? ctx->tune.cta_teams : WARPS / p.team_warps;
   const int cta_threads = 32 * p.team_warps * teams;
+  const PrepLayout prl(p.maxp, DUAL, IMU);
   const SmemLayout lay(p.maxp, p.gs, p.vd_cols, p.team_warps, p.load_vo + p.load_gps, DUAL, IMU,
-                       p.target_mode == VMVO_TARGET_TRAVERSE, (int)(4 * sizeof(SF)));
+                       p.target_mode == VMVO_TARGET_TRAVERSE, (int)(4 * sizeof(SF)), p.prep ? prl.total : 0);
   const int smem = lay.total * teams;
   if (smem > 200 * 1024)
     return fail(ctx, VMVO_ERR_UNSUPPORTED,
@@ -1731,7 +2079,38 @@ static int launch_search_v(vmvo_ctx* ctx, const SearchParams& p_in, cudaStream_t
   if (need < 1) need = 1;      // (an empty share still advances the exchange's step counter)
   if (grid > need) grid = need;
   p.n_todo = grid * teams;
-  kern<<<(unsigned)grid, cta_threads, smem, st>>>(p);
+  if (p.prep) {     // phases A1-A3 of every window of the launch, one warp per window
+    const bool half = p.maxp <= 32 && ctx->tune.prep != 32;       // two windows per warp
+    auto pk = half ? vmvo_window_prep_kernel<DUAL, IMU, SF, 16> : vmvo_window_prep_kernel<DUAL, IMU, SF, 32>;
+    const int per_cta = kPrepWarps * (half ? 2 : 1);
+    const int n_streams = p.load_vo + p.load_gps;
+    const bool trav = p.target_mode == VMVO_TARGET_TRAVERSE;
+    const int warp_bytes = (n_streams * 3 * p.maxp + (IMU ? p.maxp : 0)) * 8 + (trav ? ((p.maxp * 4 + 15) & ~15) : 0);
+    const int psmem = warp_bytes * per_cta;
+    VMVO_CUDA(ctx, cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem));
+    long long pg = (p.n_local + per_cta - 1) / per_cta;
+    const long long pcap = (long long)ctx->sm_count * 16;
+    if (pg > pcap) pg = pcap;
+    if (pg < 1) pg = 1;
+    pk<<<(unsigned)pg, 32 * kPrepWarps, psmem, st>>>(p);
+    int prc = check_launch(ctx, "vmvo_window_prep_kernel");
+    if (prc) return prc;
+  }
+  if (p.prep && ctx->tune.pdl != 0) {
+    cudaLaunchConfig_t sc = {};
+    sc.gridDim = dim3((unsigned)grid);
+    sc.blockDim = dim3(cta_threads);
+    sc.dynamicSmemBytes = (size_t)smem;
+    sc.stream = st;
+    cudaLaunchAttribute sa[1];
+    sa[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    sa[0].val.programmaticStreamSerializationAllowed = 1;
+    sc.attrs = sa;
+    sc.numAttrs = 1;
+    VMVO_CUDA(ctx, cudaLaunchKernelEx(&sc, kern, p));
+  } else {
+    kern<<<(unsigned)grid, cta_threads, smem, st>>>(p);
+  }
   int rc = check_launch(ctx, "vmvo_window_search_kernel");
   if (rc || !p.defer_buf) return rc;
   long long g2 = p.defer_slots < (long long)ctx->sm_count * 16 ? p.defer_slots : (long long)ctx->sm_count * 16;
@@ -1913,6 +2292,10 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
   // team size: about two passes of 32 items per warp (measured best on 32x32: two warps)
   int tw = 1;
   while (tw < cta_warps && p.n_items > tw * 32 * 2) tw *= 2;
+  // window preparation as a pass of its own (vmvo_window_prep_kernel): for the small teams of small
+  // grids, where the serial float64 work of phases A1-A3 is a tenth of a window's time
+  const bool want_prep = !d_run_offsets && !d_dbg_cost && ctx->tune.prep != 0;
+  const int prep_rec_bytes = PrepLayout(cfg->max_window_poses, use_vo && use_gps, use_imu).total;
   // a small grid's whole VD table (every acceleration) fits beside the rest: one fill and one
   // barrier per window instead of one per pass
   const bool vd_whole = (size_t)p.n_ic * kC * cfg->max_window_poses * 4 <= 8192;
@@ -1923,7 +2306,7 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
     if (ch > p.n_ic || vd_whole) ch = p.n_ic;
     const SmemLayout probe(cfg->max_window_poses, p.gs, ch * kC, tw, (int)load_vo + (int)load_gps,
                            use_vo && use_gps, use_imu, cfg->target_mode == VMVO_TARGET_TRAVERSE,
-                           f64 ? 32 : 16);
+                           f64 ? 32 : 16, (want_prep && tw <= 2) ? prep_rec_bytes : 0);
     if (tw == cta_warps || probe.total * (cta_warps / tw) <= 110 * 1024) break;
     tw *= 2;
   }
@@ -2039,34 +2422,49 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
     if (slots > budget) slots = budget;
     need = (size_t)slots * slot_bytes;
   }
-  // the buffer of a launch with deferral: [ready words, one per slot][slots]
+  // the scratch buffer of a launch: [window preparation records][ready words, one per slot][slots]
   const size_t ready_bytes = ((size_t)slots * 4 + 127) & ~(size_t)127;
   if (need > 0) need += ready_bytes;
-  vmvo_launch_slot* ls = acquire_launch_slot(ctx, need, capturing);
+  size_t prep_total = 0;
+  if (want_prep && tw <= 2) {
+    prep_total = (size_t)p.n_local * (size_t)prep_rec_bytes;
+    if (prep_total > (256ull << 20)) prep_total = 0;       // (a batch this large keeps the fused phases)
+  }
+  const size_t need_all = need + prep_total;
+  vmvo_launch_slot* ls = acquire_launch_slot(ctx, need_all, capturing);
   if (!ls)
     return fail(ctx, VMVO_ERR_UNSUPPORTED, "%d searches of this ctx are in flight or captured in graphs: "
                 "no launch slot left", kLaunchSlots);
-  // queue head, slot allocation count, finished windows
+  // queue head, slot allocation count, finished teams
   VMVO_CUDA(ctx, cudaMemsetAsync(ls->d_counters, 0, 4 * sizeof(unsigned long long), st));
   p.work_counter = ls->d_counters;
   p.windows_done = ls->d_counters + 2;
   p.defer_ready = nullptr;
   p.n_todo = 0;
-  if (need > 0 && ls->d_defer && ls->defer_bytes >= need && slots > 0) {
-    p.defer_ready = reinterpret_cast<unsigned*>(ls->d_defer);
-    p.defer_buf = ls->d_defer + ready_bytes;
-    p.defer_slots = (int)(slots > 0x7fffffff ? 0x7fffffff : slots);
-    p.defer_slot_bytes = (int)slot_bytes;
-    p.defer_count = reinterpret_cast<unsigned*>(ls->d_counters + 1);
-    VMVO_CUDA(ctx, cudaMemsetAsync(p.defer_ready, 0, (size_t)p.defer_slots * 4, st));
+  p.prep = nullptr;
+  p.prep_stride = prep_rec_bytes;
+  if (need_all > 0 && ls->d_defer && ls->defer_bytes >= need_all) {
+    unsigned char* base = ls->d_defer;
+    if (prep_total > 0) {
+      p.prep = base;
+      base += prep_total;
+    }
+    if (need > 0 && slots > 0) {
+      p.defer_ready = reinterpret_cast<unsigned*>(base);
+      p.defer_buf = base + ready_bytes;
+      p.defer_slots = (int)(slots > 0x7fffffff ? 0x7fffffff : slots);
+      p.defer_slot_bytes = (int)slot_bytes;
+      p.defer_count = reinterpret_cast<unsigned*>(ls->d_counters + 1);
+      VMVO_CUDA(ctx, cudaMemsetAsync(p.defer_ready, 0, (size_t)p.defer_slots * 4, st));
+    }
   }
 
   const bool dual = use_vo && use_gps;
 #define VMVO_LAUNCH(SF)                                                                  \
-  (dual ? (use_imu ? launch_search<8, 8, 2, true, true, SF>(ctx, p, st)                  \
-                   : launch_search<8, 8, 2, true, false, SF>(ctx, p, st))                \
-        : (use_imu ? launch_search<8, 8, 2, false, true, SF>(ctx, p, st)                 \
-                   : launch_search<8, 8, 2, false, false, SF>(ctx, p, st)))
+  (dual ? (use_imu ? launch_search<8, 8, VMVO_MINB, true, true, SF>(ctx, p, st)                  \
+                   : launch_search<8, 8, VMVO_MINB, true, false, SF>(ctx, p, st))                \
+        : (use_imu ? launch_search<8, 8, VMVO_MINB, false, true, SF>(ctx, p, st)                 \
+                   : launch_search<8, 8, VMVO_MINB, false, false, SF>(ctx, p, st)))
   rc = f64 ? VMVO_LAUNCH(double) : VMVO_LAUNCH(float);
 #undef VMVO_LAUNCH
   release_launch_slot(ctx, ls, st, capturing);
