@@ -395,9 +395,9 @@ def optimize_drives(cfg: SearchConfig, drives: DriveSet, plan: Optional[WindowPl
 
 class DrivePipeline:
     """plan -> search -> write-back for one resident batch of drives, captured once as a CUDA
-    graph and replayed: three kernel launches in frames mode (search, deferred re-scores, write-back:
-    the search derives the window extents itself), four in time mode (the plan first), one memset,
-    no per-pass host work.
+    graph and replayed: on a small grid in frames mode four kernel launches (window preparation,
+    search, second kernel, write-back: the extents are derived in the kernels), one more in time mode
+    (the plan first), two small memsets, no per-pass host work (``kernels_per_pass``).
 
     The pose streams and stamps are read from ``drives`` at replay time, so new data of the
     same shape can be copied into ``drives.vo`` / ``.gps`` / ``.imu`` / ``.time`` between passes.
@@ -421,7 +421,6 @@ class DrivePipeline:
             raise ValueError("DrivePipeline derives seeds from the data (seed_mode data / chained)")
         self.cfg, self.drives, self.blend_gps = cfg, drives, blend_gps
         self.plan = plan_windows(cfg, drives, extents=cfg.window_mode != "frames")
-        self.kernels_per_pass = 3 if self.plan.win_start is None else 4
         dev = drives.device
         n = self.plan.n_windows
         self.gather, self.frame_range = gather, frame_range
@@ -437,9 +436,14 @@ class DrivePipeline:
         self.records = records if records is not None else torch.empty((n, 64), dtype=torch.uint8, device=dev)
         self.trajectory = torch.empty((4, drives.n_frames), dtype=torch.float64, device=dev)
         self.graphs = None
+        ctx = _lib.context(dev.index)
+        before = ctx.launch_count()
         self._search()                                # eager warm-up: sets kernel attributes
         self._write_back()
         torch.cuda.synchronize(dev)
+        # kernels of one pass, as the library counted them: the preparation pass (small grids), the
+        # plan (time mode), the search, the second kernel (where windows may be parked), the write-back
+        self.kernels_per_pass = ctx.launch_count() - before
         if use_graph:
             # split: the search and the write-back are separate graphs so that a caller can put
             # the record gather between them (bench.py, N > 1)
