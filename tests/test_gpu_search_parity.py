@@ -209,3 +209,48 @@ def test_search_without_planned_extents_matches_planned(cuda_device):
                 assert_records_match(b[lo:hi], oracle_windows(cfg, t[d], batch.dt, vo[d]))
     with pytest.raises(ValueError, match="frames"):
         plan_windows(SearchConfig(window_mode="time"), drives, extents=False)
+
+
+PRUNE_CASES = {
+    # two-pass kernel, packed scan, chunks dealt middle-out (config 2's shape)
+    "vo_32x32_w30": (SearchConfig(grid_v=32, grid_s=32, window_frames=30), 400, {}),
+    # the same through the generic scan
+    "vo_32x32_generic": (SearchConfig(grid_v=32, grid_s=32, window_frames=30), 300, {"fast_scan": 0}),
+    # many-pass kernel (eight-warp teams, middle-out passes), packed scan
+    "vo_128x128_w60": (SearchConfig(grid_v=128, grid_s=128, window_frames=60), 130, {}),
+    # two position terms + yaw term: generic scan, eight-warp teams
+    "vo_gps_imu_64x64": (SearchConfig(grid_v=64, grid_s=64, window_frames=40, w_vo=1.0, w_gps=0.5,
+                                      w_imu=40.0), 120, {}),
+    # a grid whose item count is not a multiple of the warp (partial vote masks)
+    "vo_40x20": (SearchConfig(grid_v=40, grid_s=20, window_frames=25), 150, {}),
+    # votes after every step
+    "vo_32x32_every1": (SearchConfig(grid_v=32, grid_s=32, window_frames=30), 200, {"prune_every": 1}),
+}
+
+
+@pytest.mark.parametrize("name", sorted(PRUNE_CASES))
+def test_pruned_scan_gives_the_exhaustive_records(cuda_device, tuning, name):
+    """A warp stops scanning once every hypothesis it holds has passed the candidate threshold of the
+    bound its team held at the start of the pass: index, float64 cost and first pose of every window
+    are those of the exhaustive scan BIT FOR BIT (and those of the oracle)."""
+    cfg, frames, tune = PRUNE_CASES[name]
+    for k, v in tune.items():
+        tuning(k, v)
+    batch = synthetic_drives(1, frames, seed=zlib.crc32(name.encode()) % 1000)
+    t, vo, gps, imu = batch.drive(0)
+    kw = {"vo": [vo]}
+    if cfg.w_gps:
+        kw["gps"] = [gps]
+    if cfg.w_imu:
+        kw["imu"] = [imu]
+    drives = DriveSet.from_arrays([t], [batch.dt], **kw)
+    plan = plan_windows(cfg, drives)
+    pruned = grid_search(cfg, drives, plan).records()
+    tuning("prune", 0)
+    full = grid_search(cfg, drives, plan).records()
+    for f in ("best_idx", "n_steps", "status"):
+        np.testing.assert_array_equal(pruned[f], full[f])
+    for f in ("best_cost", "x1", "y1", "theta1", "v_seed", "s_seed"):
+        np.testing.assert_array_equal(pruned[f].view(np.uint64), full[f].view(np.uint64))
+    ref = oracle_windows(cfg, t, batch.dt, vo, gps if cfg.w_gps else None, imu if cfg.w_imu else None)
+    assert_records_match(pruned, ref)

@@ -56,7 +56,7 @@ def build():
     after("        U = fminf(U, bm);\n", "        CLK(7);\n")
     after("          if (!overflow) break;\n          process_list();\n        }\n", "        CLK(8);\n")
     after("      if (!deferred) process_list();\n", "      CLK(9);\n")
-    before("    team.sync();\n  }\n}\n\n// ---- second kernel", "    CLK(10);\n")
+    before("    team.sync();\n  }\n}\n\n// ---- window preparation as a pass", "    CLK(10);\n")
     s = s.replace("namespace vmvo {\n", "namespace vmvo {\n__device__ unsigned long long g_clk[2][12];\n"
                   "#define CLK(i) do { if (lane == 0 && warp < 2) { long long t_ = clock64(); "
                   "s_clk[team.id][warp][i] += t_ - s_prev[team.id][warp]; s_prev[team.id][warp] = t_; } } while (0)\n", 1)
@@ -94,6 +94,9 @@ def run():
     dr = DriveSet.from_arrays([t], [b.dt], vo=[vo])
     plan = plan_windows(cfg, dr)
     lib = _lib.context(0).lib
+    for a in sys.argv[2:]:            # key=value: the library's tuning hook
+        k, v = a.split("=")
+        _lib.context(0).set_tuning(k, int(v))
     for _ in range(3):
         grid_search(cfg, dr, plan)
     out = (C.c_ulonglong * 24)()

@@ -46,6 +46,7 @@ struct SearchParams {
   int team_warps;        // warps per team (1, 2, 4 or 8)
   int cand_cap;          // candidate list entries per team (<= kCandPerWarp * team_warps)
   int allow_fast;        // use the packed / rotation scan where its preconditions hold
+  int prune_every;       // steps between two pruning votes of a scanning warp (0: every scan runs to the end)
   // launch constants the kernel would otherwise divide for, window after window: passes per window,
   // threads that share a rate in the TL fill / a column in the VD fill, and log2 of gs, vd_cols and
   // the team's thread count when they are powers of two (-1: divide)
@@ -458,14 +459,24 @@ struct ScanOut {
   float J[C];
 };
 
+// Pruning (both scans).  The partial sums of a cost only grow (every term is a square, rounding is
+// monotone), so a hypothesis whose partial cost has passed the candidate threshold T(U) of its item
+// under the bound U the team held when the pass began can neither become a candidate of this pass
+// (T(U') <= T(U) for the pass's own U' <= U) nor lower U (its J + err(J) > T(U) >= U): when that holds
+// for every hypothesis of every lane the warp stops scanning, and the caller treats its items like
+// items outside the grid.  Candidates, bounds and records are those of the exhaustive scan, bit for
+// bit.  `Tq` is the threshold on the FIRST position term's accumulator (w_A * J_A is a lower bound of
+// the cost; +inf: never), `every` the steps between two votes, `lanes` the lanes that scan.
+// Returns true when the warp stopped early.
 template <int C, bool DUAL, bool IMU>
-__device__ __forceinline__ void scan_item(int N, int gs, int vd_cols, int j, int m0,
+__device__ __forceinline__ bool scan_item(int N, int gs, int vd_cols, int j, int m0,
                                           const float* __restrict__ TL,
                                           const float* __restrict__ VD,
                                           const float2* __restrict__ Df,
                                           const float2* __restrict__ Dab,
                                           const float* __restrict__ fI, float wA, float wB,
-                                          float wI, float kJS, ScanOut<C>& out) {
+                                          float wI, float kJS, float Tq, int every, unsigned lanes,
+                                          ScanOut<C>& out) {
   float th[C], ex[C], ey[C], JA[C], JB[C], JI[C];
 #pragma unroll
   for (int c = 0; c < C; ++c) th[c] = ex[c] = ey[c] = JA[c] = JB[c] = JI[c] = 0.f;
@@ -475,8 +486,13 @@ __device__ __forceinline__ void scan_item(int N, int gs, int vd_cols, int j, int
   const float* vd = VD + m0;
   const float2* df = Df;
   const int tl_step = gs * 4, vd_step = vd_cols * 4;     // byte strides, computed once (not an IMAD per step)
+  bool pruned = false;
+  int k = 1;
 #pragma unroll 1
-  for (int k = 1; k <= N; ++k, tl = reinterpret_cast<const float*>(reinterpret_cast<const char*>(tl) + tl_step),
+  for (int kend = every;; kend += every) {
+  const int ke = kend < N ? kend : N;
+#pragma unroll 1
+  for (; k <= ke; ++k, tl = reinterpret_cast<const float*>(reinterpret_cast<const char*>(tl) + tl_step),
            vd = reinterpret_cast<const float*>(reinterpret_cast<const char*>(vd) + vd_step)) {
     const float tlk = *tl;
     float v[C];
@@ -511,6 +527,15 @@ __device__ __forceinline__ void scan_item(int N, int gs, int vd_cols, int j, int
       }
     }
   }
+  if (k > N) break;
+  float mn = JA[0];
+#pragma unroll
+  for (int c = 1; c < C; ++c) mn = fminf(mn, JA[c]);
+  if (__all_sync(lanes, mn > Tq)) {
+    pruned = true;
+    break;
+  }
+  }
 #pragma unroll
   for (int c = 0; c < C; ++c) {
     float t = fmaf(wA, JA[c], kJS);
@@ -518,6 +543,7 @@ __device__ __forceinline__ void scan_item(int N, int gs, int vd_cols, int j, int
     if (IMU) t = fmaf(wI, JI[c], t);
     out.J[c] = t;
   }
+  return pruned;
 }
 
 // ---- packed FP32x2 + rotation scan (C = 8, no IMU term, V_w >= 0) --------------------------------
@@ -535,13 +561,13 @@ __device__ __forceinline__ void rot_pair(float2 c2, float2 s2, float cr, float s
 }
 
 template <bool DUAL>
-__device__ __forceinline__ void scan_item_fast(int N, int gs, int vd_cols, int j, int m0,
+__device__ __forceinline__ bool scan_item_fast(int N, int gs, int vd_cols, int j, int m0,
                                                const float* __restrict__ TL,
                                                const float* __restrict__ VD,
                                                const float2* __restrict__ Df,
                                                const float2* __restrict__ Dab, float wA, float wB,
                                                float kJS, float vwdt, float dt2, float a0, float da,
-                                               ScanOut<8>& out) {
+                                               float Tq, int every, unsigned lanes, ScanOut<8>& out) {
   // x and y cost terms accumulate separately (JA / JA2): one chain of dependent FFMA2 per
   // accumulator measured 7 % faster on the dense grid than a single merged one
   float2 ex[4], ey[4], JA[4], JA2[4], JB[4];
@@ -597,11 +623,31 @@ __device__ __forceinline__ void scan_item_fast(int N, int gs, int vd_cols, int j
       }
     }
   };
+  // groups of `every` steps with a pruning vote behind each (see scan_item); x and y terms accumulate
+  // apart here, so the vote adds them first
+  bool pruned = false;
+  int k = 1;
 #pragma unroll 1
-  for (int k = 1; k <= N; ++k) {
-    float2 c2[4], s2[4];
-    trig(k, c2, s2);
-    step(k, c2, s2);
+  for (int kend = every;; kend += every) {
+    const int ke = kend < N ? kend : N;
+#pragma unroll 1
+    for (; k <= ke; ++k) {
+      float2 c2[4], s2[4];
+      trig(k, c2, s2);
+      step(k, c2, s2);
+    }
+    if (k > N) break;
+    float2 m2 = __fadd2_rn(JA[0], JA2[0]);
+#pragma unroll
+    for (int q = 1; q < 4; ++q) {
+      const float2 t2 = __fadd2_rn(JA[q], JA2[q]);
+      m2.x = fminf(m2.x, t2.x);
+      m2.y = fminf(m2.y, t2.y);
+    }
+    if (__all_sync(lanes, fminf(m2.x, m2.y) > Tq)) {
+      pruned = true;
+      break;
+    }
   }
   // (running the SFU one step ahead of the FMA pipe -- a two-stage software pipeline -- needs 16
   // more registers, spills, and measured 13 % slower)
@@ -616,6 +662,7 @@ __device__ __forceinline__ void scan_item_fast(int N, int gs, int vd_cols, int j
     out.J[2 * q] = t0;
     out.J[2 * q + 1] = t1;
   }
+  return pruned;
 }
 
 // ---- the kernel -----------------------------------------------------------------------------
@@ -1331,9 +1378,57 @@ vmvo_window_search_kernel(const SearchParams p) {
         unsigned valid = 0;
         Band band{0.f, 0.f, 0.f};
         const bool fast = fast_w;
-        if (q < p.n_items) {
+        const bool in_grid = q < p.n_items;
+        if (in_grid) {
           ic = div_sh(q, p.gs, p.gs_sh);
           j = q - ic * p.gs;
+          // two passes over a whole-window VD table: the acceleration chunks are dealt middle-out, so
+          // that the first pass holds the accelerations around zero and the second one -- the
+          // hardest braking and the hardest acceleration -- is scanned under the first one's bound
+          if (!use_skip && vd_full) {
+            const int mid = (p.n_ic - 1) >> 1;
+            ic = (ic & 1) ? mid + ((ic + 1) >> 1) : mid - (ic >> 1);
+          }
+#pragma unroll
+          for (int c = 0; c < kC; ++c)
+            if (ic * kC + c < p.gv) valid |= 1u << c;
+        }
+        // the item's band inputs, from the per-rate table statistics instead of from the loop:
+        // largest step of its fastest hypothesis (V_k is monotone in k, VD non-decreasing in i)
+        // and a bound on the total heading variation, sum_k step_k * |TL_k| with
+        // step_k <= max(V_w, 0) dt + a k dt^2  (a = largest |a_i| of the chunk's valid
+        // hypotheses for the affine headings of the packed scan, max(a_last, 0) otherwise)
+        auto item_band = [&]() {
+          const int i0 = ic * kC;
+          const int il = i0 + kC - 1 < p.gv ? i0 + kC - 1 : p.gv - 1;
+          const float inv = (float)p.acc_step;
+          const float a_first = inv * (float)(2 * i0 - (p.gv - 1));
+          const float a_last = inv * (float)(2 * il - (p.gv - 1));
+          const float acoef = fast ? fmaxf(fabsf(a_first), fabsf(a_last)) : fmaxf(a_last, 0.f);
+          const float dtf = (float)dt;
+          const float* vdc = VD + (ic - ic0) * kC + (kC - 1);
+          const float vmax = fmaxf(vdc[0], vdc[(N - 1) * p.vd_cols]);
+          const float tv = 1.000002f * fmaf(fmaxf((float)v_seed, 0.f) * dtf, TS[gs4 + j],
+                                            1.000002f * acoef * dtf * dtf * TS[2 * gs4 + j]);
+          return make_band<IMU>(hd->bw, vmax, tv, TS[j], fast);
+        };
+        // Pruning (see scan_item): from the second pass on the team holds a bound U, and a warp whose
+        // hypotheses have all passed T(U) stops scanning.  The vote compares the first position
+        // term's accumulator with T(U) / w_A, rounded up (without a steering penalty the cost is
+        // >= fl(w_A * J_A), which then exceeds T(U)).
+        float Tq = CUDART_INF_F;
+        int every = N > 0 ? N : 1;
+        if (p.prune_every > 0 && U < CUDART_INF_F && !ksteer && in_grid) {     // (U: team-uniform)
+          Tq = __fdividef(item_band().threshold(U), wA) * 1.000002f;
+          Tq = Tq == Tq ? Tq : CUDART_INF_F;
+        }
+        if (p.prune_every > 0 && U < CUDART_INF_F && !ksteer) every = p.prune_every;
+        const unsigned lanes = __ballot_sync(FULL, in_grid);
+        // (opaque to the compiler: it would otherwise recompute the vote period and the scan's float
+        // constants -- float64 products and conversions -- behind every vote instead of keeping them)
+        asm volatile("" : "+r"(every), "+f"(Tq));
+        bool pruned = false;
+        if (in_grid) {
           if constexpr (C == 8 && !IMU) {
             if (fast) {
               // a_i by multiplication with 1/(G-1): last-bit differences from the spec's
@@ -1342,18 +1437,19 @@ vmvo_window_search_kernel(const SearchParams p) {
               const int i0 = ic * kC;
               const double a0d = inv * (double)(2 * i0 - (p.gv - 1));
               const double dtd = dt * dt;
-              scan_item_fast<DUAL>(N, p.gs, p.vd_cols, j, (ic - ic0) * kC, TL, VD, Df, Dab, wA, wB,
-                                   ksteer ? JS[j] : 0.f, (float)(v_seed * dt), (float)dtd,
-                                   (float)a0d, (float)(2.0 * inv), so);
+              float f_vwdt = (float)(v_seed * dt), f_dt2 = (float)dtd, f_a0 = (float)a0d,
+                    f_da = (float)(2.0 * inv);
+              asm volatile("" : "+f"(f_vwdt), "+f"(f_dt2), "+f"(f_a0), "+f"(f_da));
+              pruned = scan_item_fast<DUAL>(N, p.gs, p.vd_cols, j, (ic - ic0) * kC, TL, VD, Df, Dab, wA, wB,
+                                            ksteer ? JS[j] : 0.f, f_vwdt, f_dt2, f_a0, f_da, Tq, every,
+                                            lanes, so);
             }
           }
           if (!fast)
-            scan_item<C, DUAL, IMU>(N, p.gs, p.vd_cols, j, (ic - ic0) * kC, TL, VD, Df, Dab, fI, wA, wB,
-                                    wI, ksteer ? JS[j] : 0.f, so);
-#pragma unroll
-          for (int c = 0; c < kC; ++c)
-            if (ic * kC + c < p.gv) valid |= 1u << c;
+            pruned = scan_item<C, DUAL, IMU>(N, p.gs, p.vd_cols, j, (ic - ic0) * kC, TL, VD, Df, Dab, fI, wA,
+                                             wB, wI, ksteer ? JS[j] : 0.f, Tq, every, lanes, so);
         }
+        if (pruned) valid = 0;         // nothing of this warp can matter: m = inf, no candidates
         float mj = CUDART_INF_F;       // the item's smallest cost; fminf drops NaN
         bool has_nan = false;
 #pragma unroll
@@ -1370,25 +1466,7 @@ vmvo_window_search_kernel(const SearchParams p) {
           if (!work) valid = 0;        // nothing of this warp can matter: m = inf, no candidates
         }
         if (valid) {
-          {
-            // the item's band inputs, from the per-rate table statistics instead of from the loop:
-            // largest step of its fastest hypothesis (V_k is monotone in k, VD non-decreasing in i)
-            // and a bound on the total heading variation, sum_k step_k * |TL_k| with
-            // step_k <= max(V_w, 0) dt + a k dt^2  (a = largest |a_i| of the chunk's valid
-            // hypotheses for the affine headings of the packed scan, max(a_last, 0) otherwise)
-            const int i0 = ic * kC;
-            const int il = i0 + kC - 1 < p.gv ? i0 + kC - 1 : p.gv - 1;
-            const float inv = (float)p.acc_step;
-            const float a_first = inv * (float)(2 * i0 - (p.gv - 1));
-            const float a_last = inv * (float)(2 * il - (p.gv - 1));
-            const float acoef = fast ? fmaxf(fabsf(a_first), fabsf(a_last)) : fmaxf(a_last, 0.f);
-            const float dtf = (float)dt;
-            const float* vdc = VD + (ic - ic0) * kC + (kC - 1);
-            const float vmax = fmaxf(vdc[0], vdc[(N - 1) * p.vd_cols]);
-            const float tv = 1.000002f * fmaf(fmaxf((float)v_seed, 0.f) * dtf, TS[gs4 + j],
-                                              1.000002f * acoef * dtf * dtf * TS[2 * gs4 + j]);
-            band = make_band<IMU>(hd->bw, vmax, tv, TS[j], fast);
-          }
+          band = item_band();
           if (p.dbg_cost) {
 #pragma unroll
             for (int c = 0; c < kC; ++c)
@@ -2318,6 +2396,10 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
   // window 2.5 -> 2.8); on smaller grids the per-item preamble outweighs the loop.
   p.allow_fast = p.n_items >= 128;
   if (ctx->tune.fast_scan >= 0) p.allow_fast = ctx->tune.fast_scan != 0;                 // test hook
+  // pruning votes every four steps (the debug export wants every cost in full)
+  p.prune_every = d_dbg_cost ? 0 : 4;
+  if (ctx->tune.prune == 0) p.prune_every = 0;                                            // test hook
+  if (ctx->tune.prune_every >= 1 && p.prune_every) p.prune_every = ctx->tune.prune_every; // test hook
   if (ctx->tune.cand_cap >= 1 && ctx->tune.cand_cap < p.cand_cap) p.cand_cap = ctx->tune.cand_cap;   // test hook
   const int threads = tw * 32;
   // accelerations one pass can touch: items [pass*T, pass*T + T) span at most this many chunks
