@@ -236,7 +236,7 @@ def pooled_drives(workload, world, dev, seed0=BASE_SEED):
     return n_frames, cfg, DriveSet.from_arrays(t, dt, vo=vo, device=dev), np.concatenate(t), np.concatenate(vo)
 
 
-def measure_workload(workload, dev, world, rank, timer, steps, warmup, seed0=BASE_SEED):
+def measure_workload(workload, dev, world, rank, timer, steps, warmup, seed0=BASE_SEED, exhaustive=False):
     """Device-resident step time, search-kernel time, end-to-end (pipelined and serial) for one
     workload; at world > 1 through the window scheduler and the fused exchange."""
     import torch
@@ -291,6 +291,28 @@ def measure_workload(workload, dev, world, rank, timer, steps, warmup, seed0=BAS
     kk = max(3, min(steps, 50))
     kern_ms = timer(only.replay, kk, 2, collective=False) / kk
     out["kernel_ms_all_windows_one_gpu"] = kern_ms
+    if world == 1 and exhaustive:
+        # the same step and the same search launches with the pruning votes off (every scan runs to its
+        # last step; the library's tuning hook, read when the graphs are captured): identical records
+        ctx = _lib.context(dev.index)
+        with ctx.tuning(prune=0):
+            full_pipe = DrivePipeline(cfg, drives, blend_gps=False)
+            full_alone = torch.empty((n_win, 64), dtype=torch.uint8, device=dev)
+            grid_search(cfg, drives, last.plan, out=full_alone)
+            torch.cuda.synchronize(dev)
+            full_only = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(full_only):
+                grid_search(cfg, drives, last.plan, out=full_alone)
+        full_ms = timer(full_pipe.run, steps, warmup, collective=False) / steps
+        full_kern = timer(full_only.replay, kk, 2, collective=False) / kk
+        torch.cuda.synchronize(dev)
+        if not records_equal(alone, full_alone):
+            raise SystemExit("the pruned search and the exhaustive search disagree")
+        out["exhaustive"] = {"ms_per_step": full_ms, "value": hsteps / (full_ms * 1e-3), "unit": UNIT,
+                             "kernel_ms_per_launch": full_kern, "records_identical_to_pruned": True,
+                             "note": "every hypothesis rolled to its last step (pruning votes off): the "
+                                     "same records bit for bit; `value` above is the default, pruned search"}
+        del full_pipe, full_only
     if world > 1:
         torch.cuda.synchronize(dev)
         if not records_equal(alone, last.records):
@@ -682,7 +704,8 @@ def run_b200(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    res = measure_workload(args.workload, dev, world, rank, timer, args.steps, args.warmup)
+    res = measure_workload(args.workload, dev, world, rank, timer, args.steps, args.warmup,
+                           exhaustive=not args.no_extras)
     clocks = sampler.stop() if rank == 0 else None
     cfg, n_frames = res["cfg"], res["n_frames"]
 
@@ -691,10 +714,10 @@ def run_b200(args):
         if world == 1:
             other = [w for w in sorted(WORKLOADS) if w != args.workload]
             for w in other:                      # the other single-GPU config as a first-class object
-                r2 = measure_workload(w, dev, 1, 0, timer, 3 if "config3" in w else 20, 2)
+                r2 = measure_workload(w, dev, 1, 0, timer, 3 if "config3" in w else 20, 2, exhaustive=True)
                 key = "config3" if "config3" in w else "config2"
                 obj = {k: r2[k] for k in ("workload", "n_win", "hsteps", "ms_per_step", "value",
-                                          "rescored_per_window", "e2e", "e2e_serial")}
+                                          "rescored_per_window", "e2e", "e2e_serial", "exhaustive")}
                 obj.update(unit=UNIT, windows_per_s=r2["n_win"] / (r2["ms_per_step"] * 1e-3),
                            config=config_of(w, r2["n_frames"], r2["cfg"]),
                            roofline=roofline(ctx, dev, r2, clocks),
@@ -718,7 +741,13 @@ def run_b200(args):
         "e2e": res["e2e"], "e2e_serial": res["e2e_serial"],
         "clocks": clocks,
         "rescored_per_window": res["rescored_per_window"],
+        "search": "exact branch and bound: a scanning warp stops once every hypothesis it holds has passed "
+                  "the candidate threshold of the bound its team held when the pass began; `value` counts "
+                  "the grid's hypothesis-steps (G_v x G_s x N per window, SURVEY 8d), records are those of "
+                  "the exhaustive scan bit for bit (`exhaustive`: the same step with the votes off)",
     }
+    if "exhaustive" in res:
+        line["exhaustive"] = res["exhaustive"]
     if rank == 0:
         line["roofline"] = roofline(ctx, dev, res, clocks, extras=not args.no_extras)
         line.update(extras)

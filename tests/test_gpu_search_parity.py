@@ -216,9 +216,13 @@ PRUNE_CASES = {
     "vo_32x32_w30": (SearchConfig(grid_v=32, grid_s=32, window_frames=30), 400, {}),
     # the same through the generic scan
     "vo_32x32_generic": (SearchConfig(grid_v=32, grid_s=32, window_frames=30), 300, {"fast_scan": 0}),
-    # many-pass kernel (eight-warp teams, middle-out passes), packed scan
+    # many-pass kernel (four-warp teams, middle-out passes), packed scan
     "vo_128x128_w60": (SearchConfig(grid_v=128, grid_s=128, window_frames=60), 130, {}),
-    # two position terms + yaw term: generic scan, eight-warp teams
+    # the dense grid of BASELINE configs[2]: eight-warp teams, one acceleration chunk per pass
+    "vo_256x256_w60": (SearchConfig(grid_v=256, grid_s=256, window_frames=60), 128, {}),
+    # the same grid as the first many-pass case with eight-warp teams
+    "vo_128x128_w60_tw8": (SearchConfig(grid_v=128, grid_s=128, window_frames=60), 126, {"team_warps": 8}),
+    # two position terms + yaw term: generic scan, many passes
     "vo_gps_imu_64x64": (SearchConfig(grid_v=64, grid_s=64, window_frames=40, w_vo=1.0, w_gps=0.5,
                                       w_imu=40.0), 120, {}),
     # a grid whose item count is not a multiple of the warp (partial vote masks)

@@ -2367,9 +2367,13 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
   p.gs = cfg->grid_s;
   p.n_ic = (p.gv + kC - 1) / kC;
   p.n_items = p.n_ic * p.gs;
-  // team size: about two passes of 32 items per warp (measured best on 32x32: two warps)
+  // team size: about two passes of 32 items per warp (measured best on 32x32: two warps) -- but at most
+  // four warps where the tables of two such teams still leave room for two CTAs per SM: with pruning a
+  // pass ends with its slowest warp (the one that holds the best steering rates), and the warps that
+  // stopped early wait for it at the barrier; four-warp teams measured 5 % faster on 128x128 (the
+  // loop below grows the team again when the tables do not fit: 256x256 keeps eight warps)
   int tw = 1;
-  while (tw < cta_warps && p.n_items > tw * 32 * 2) tw *= 2;
+  while (tw < cta_warps / 2 && p.n_items > tw * 32 * 2) tw *= 2;
   // window preparation as a pass of its own (vmvo_window_prep_kernel): for the small teams of small
   // grids, where the serial float64 work of phases A1-A3 is a tenth of a window's time
   const bool want_prep = !d_run_offsets && !d_dbg_cost && ctx->tune.prep != 0;
