@@ -258,3 +258,32 @@ def test_pruned_scan_gives_the_exhaustive_records(cuda_device, tuning, name):
         np.testing.assert_array_equal(pruned[f].view(np.uint64), full[f].view(np.uint64))
     ref = oracle_windows(cfg, t, batch.dt, vo, gps if cfg.w_gps else None, imu if cfg.w_imu else None)
     assert_records_match(pruned, ref)
+
+
+@pytest.mark.parametrize("name", ["vo_32x32_w30", "vo_128x128_w60", "vo_gps_imu_64x64"])
+def test_lean_kernels_give_the_generic_kernels_records(cuda_device, tuning, name):
+    """The specialised kernels (MODE 1: switches of the non-default features compiled out; MODE 2: also
+    always fed preparation records) against the generic one (MODE 0), and MODE 1 against MODE 2 on
+    the small grid: the same records bit for bit."""
+    cfg, frames, _ = PRUNE_CASES[name]
+    batch = synthetic_drives(1, frames, seed=zlib.crc32(name.encode()) % 1000 + 1)
+    t, vo, gps, imu = batch.drive(0)
+    kw = {"vo": [vo]}
+    if cfg.w_gps:
+        kw["gps"] = [gps]
+    if cfg.w_imu:
+        kw["imu"] = [imu]
+    drives = DriveSet.from_arrays([t], [batch.dt], **kw)
+    plan = plan_windows(cfg, drives)
+    got = {}
+    for label, tune in (("default", {}), ("generic", {"lean": 0}), ("lean_no_prep", {"prep": 0})):
+        for k, v in tune.items():
+            tuning(k, v)
+        got[label] = grid_search(cfg, drives, plan).records()
+        for k in tune:
+            tuning(k, -1)
+    for label in ("generic", "lean_no_prep"):
+        for f in ("best_idx", "n_steps", "status"):
+            np.testing.assert_array_equal(got[label][f], got["default"][f])
+        for f in ("best_cost", "x1", "y1", "theta1", "v_seed", "s_seed"):
+            np.testing.assert_array_equal(got[label][f].view(np.uint64), got["default"][f].view(np.uint64))

@@ -30,17 +30,17 @@ print(f"total warp-instructions {ti}, samples {ts}")
 for f, n, src, e, s in sorted(lines, key=lambda l: -l[4])[:top]:
     print(f"{100 * s / ts:5.1f}% smp {100 * e / ti:5.1f}% inst  {f}:{n:<5d} {src[:100]}")
 
-# ---- per-phase totals for vmvo_search.cu (line ranges found from the phase markers of the file) ----
+# ---- per-phase totals for vmvo_search_kernels.cuh (line ranges found from the phase markers of the file) ----
 import os
 import re
 
 src_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
-                        "vehiclemodelvisualodometry_b200", "csrc", "vmvo_search.cu")
+                        "vehiclemodelvisualodometry_b200", "csrc", "vmvo_search_kernels.cuh")
 if os.path.isfile(src_path):
     text = open(src_path).read().splitlines()
     marks = []
     pats = [("band / make_band", r"^struct BandWin"), ("float64 re-score (warp_cost64)", r"^__device__ double warp_cost64"),
-            ("scan loop: generic", r"^__device__ __forceinline__ void scan_item\("),
+            ("scan loop: generic", r"^__device__ __forceinline__ bool scan_item\("),
             ("scan loop: packed / rotation", r"^__device__ __forceinline__ float2 pk\("),
             ("kernel prologue / queue / TMA wait", r"^vmvo_window_search_kernel\("),
             ("A1 local frames", r"// ---- phase A1"), ("A2 seeds / decimation", r"// ---- phase A2"),
@@ -57,7 +57,7 @@ if os.path.isfile(src_path):
     marks.sort()
     tot = {}
     for f, n, src, e, s in lines:
-        if f == "vmvo_search.cu":
+        if f in ("vmvo_search.cu", "vmvo_search_kernels.cuh"):
             name = "before"
             for ln, nm in marks:
                 if n >= ln:

@@ -5,7 +5,7 @@ window), on a separately built, instrumented copy of the library -- the shipped 
                                            # markers, compiles tools/_build/libvmvo_clk.so
     python tools/phase_clocks.py run       # on the GPU box: config 2, prints clk per window and phase
 
-The markers are placed by text anchors in vmvo_search.cu (the script fails loudly when one moves).
+The markers are placed by text anchors in vmvo_search_kernels.cuh (the script fails loudly when one moves).
 Lane 0 of the first two warps of every team adds the clocks since its previous marker to a
 shared-memory accumulator; the totals are added to a device array at kernel end and read back
 through vmvo_exp_clk (exported by the instrumented build only).
@@ -33,7 +33,7 @@ def build():
         t = open(f).read()
         if '"../../include/vmvo_b200.h"' in t:
             open(f, "w").write(t.replace('"../../include/vmvo_b200.h"', '"%s"' % inc))
-    p = os.path.join(SRC, "vmvo_search.cu")
+    p = os.path.join(SRC, "vmvo_search_kernels.cuh")
     s = open(p).read()
 
     def after(anchor, text):
@@ -73,7 +73,7 @@ def build():
     open(p, "w").write(s)
     cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--shared",
            "-Xcompiler", "-fPIC", "--threads", "4", "-o", LIB] + [os.path.join(SRC, f) for f in
-                                                                 ("vmvo_search.cu", "vmvo_aux.cu", "vmvo_prep.cu", "vmvo_csv.cu")]
+                                                                 ("vmvo_search.cu", "vmvo_search_lean.cu", "vmvo_search_prep.cu", "vmvo_aux.cu", "vmvo_prep.cu", "vmvo_csv.cu")]
     subprocess.run(cmd, check=True)
     print("built", LIB)
 

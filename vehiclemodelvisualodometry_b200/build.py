@@ -9,13 +9,13 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libvmvo_b200.so")
-SOURCES = ["vmvo_search.cu", "vmvo_aux.cu", "vmvo_prep.cu", "vmvo_csv.cu"]
-HEADERS = ["vmvo_device.cuh", "vmvo_internal.h", "vmvo_pow10.inc", os.path.join("..", "..", "include", "vmvo_b200.h")]
+SOURCES = ["vmvo_search.cu", "vmvo_search_lean.cu", "vmvo_search_prep.cu", "vmvo_aux.cu", "vmvo_prep.cu", "vmvo_csv.cu"]
+HEADERS = ["vmvo_search_kernels.cuh", "vmvo_device.cuh", "vmvo_internal.h", "vmvo_pow10.inc", os.path.join("..", "..", "include", "vmvo_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "--shared", "-Xcompiler", "-fPIC",
-    "--threads", "4",               # the four translation units compile side by side
+    "--threads", "6",               # the translation units compile side by side
 ]
 
 

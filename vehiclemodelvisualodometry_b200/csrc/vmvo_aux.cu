@@ -400,7 +400,7 @@ extern "C" int vmvo_ctx_create(int device, vmvo_ctx** out) {
   ctx->h_stage = nullptr;
   ctx->h_stage_bytes = 0;
   ctx->host_stream = nullptr;
-  ctx->tune = vmvo_tuning{-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
+  ctx->tune = vmvo_tuning{-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
   for (int q = 0; q < kLaunchSlots; ++q) ctx->slots[q] = vmvo_launch_slot{nullptr, nullptr, 0, nullptr, false, false};
   DeviceGuard guard(device);
   cudaDeviceProp prop;
@@ -452,7 +452,8 @@ extern "C" int vmvo_debug_set_tuning(vmvo_ctx* ctx, const char* key, int32_t val
             : !strcmp(key, "pdl") ? &ctx->tune.pdl
             : !strcmp(key, "prep") ? &ctx->tune.prep
             : !strcmp(key, "prune") ? &ctx->tune.prune
-            : !strcmp(key, "prune_every") ? &ctx->tune.prune_every : nullptr;
+            : !strcmp(key, "prune_every") ? &ctx->tune.prune_every
+            : !strcmp(key, "lean") ? &ctx->tune.lean : nullptr;
   if (!slot) return fail(ctx, VMVO_ERR_BAD_ARG, "unknown tuning key '%s'", key);
   *slot = value < 0 ? -1 : value;
   return VMVO_OK;

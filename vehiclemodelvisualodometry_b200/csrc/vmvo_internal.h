@@ -27,7 +27,7 @@ constexpr int kLaunchSlots = 256;
 // test / tuning overrides (vmvo_debug_set_tuning); -1 = the library's own choice
 struct vmvo_tuning {
   int team_warps, fast_scan, cand_cap, defer_min, max_ctas_per_sm, defer_warps, cta_teams, pdl, prep;
-  int prune, prune_every;
+  int prune, prune_every, lean;
 };
 
 struct vmvo_ctx {
