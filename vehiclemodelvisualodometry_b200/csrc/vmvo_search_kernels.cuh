@@ -668,6 +668,21 @@ __device__ __forceinline__ bool scan_item_fast(int N, int gs, int vd_cols, int j
   return pruned;
 }
 
+// A window that is not searched leaves this record (one thread stores it to every destination).
+static __device__ __forceinline__ void store_unsearched(vmvo_window_result* dst, int st, int n_steps, double vs,
+                                              double ss) {
+  vmvo_window_result r;
+  r.best_idx = -1;
+  r.n_steps = n_steps;
+  r.status = st;
+  r.n_rescored = 0;
+  r.best_cost = CUDART_NAN;
+  r.v_seed = vs;
+  r.s_seed = ss;
+  r.x1 = r.y1 = r.theta1 = CUDART_NAN;
+  *dst = r;
+}
+
 // ---- the kernel -----------------------------------------------------------------------------
 // WARPS warps per CTA, MINB CTAs per SM.  Only <8, 2> (128 registers per thread, 16 warps/SM) is
 // instantiated: at 80 or 64 registers (24 / 32 warps/SM) both scan loops spill inside the loop and
@@ -892,28 +907,17 @@ vmvo_window_search_kernel(const SearchParams p) {
     }
 
     // the record of a window that is not searched (too long / empty): everything but the status,
-    // the step count and the seeds stays "none"
+    // the step count and the seeds stays "none" (one thread, every destination: store_unsearched)
     auto write_unsearched = [&](int st, int n_steps, double vs, double ss) {
-      vmvo_window_result r;
-      r.best_idx = -1;
-      r.n_steps = n_steps;
-      r.status = st;
-      r.n_rescored = 0;
-      r.best_cost = CUDART_NAN;
-      r.v_seed = vs;
-      r.s_seed = ss;
-      r.x1 = r.y1 = r.theta1 = CUDART_NAN;
-      store_record(w, r);
+      for (int t = 0; t <= p.n_mirrors; ++t)
+        store_unsearched((t == 0 ? p.results : p.mirrors[t - 1]) + w, st, n_steps, vs, ss);
     };
 
     if (len > P || len < 1) {  // uniform branch
       // no pose at all (an empty time extent, NaN stamps): "No frames found", schema.py:122
-      if (warp == 0) {
-        if (lane == 0)
-          write_unsearched(len < 1 ? (VMVO_WIN_EMPTY | VMVO_WIN_NO_FRAMES) : VMVO_WIN_TOO_LONG, 0,
-                           CUDART_NAN, CUDART_NAN);
-        flush_record(w);
-      }
+      if (tid == 0)
+        write_unsearched(len < 1 ? (VMVO_WIN_EMPTY | VMVO_WIN_NO_FRAMES) : VMVO_WIN_TOO_LONG, 0,
+                         CUDART_NAN, CUDART_NAN);
       team.sync();
       continue;
     }
@@ -1136,31 +1140,18 @@ vmvo_window_search_kernel(const SearchParams p) {
         const double c0 = s_seed * kd, ck = rdt * kd, kstep = (double)kpar;
         const float kstepf = (float)kpar;
         float mx = 0.f, s0 = 0.f, s1 = 0.f;
-        // fast: no clamps, polynomial tangent; full: all four steps are inside the window -- the
-        // common group is then one straight line of code (the lambda is specialised per call)
-        auto group = [&](int k0, const bool fast, const bool full) {
+        // the common case -- no rate reaches the steering limit inside the window, every angle inside
+        // the polynomial's range -- four steps at a time (independent chains); otherwise one entry
+        // at a time through the clamps and tan_steer (one copy of that code: it is rarely run, and
+        // what the kernel's code weighs is paid for in instruction fetches by every window)
+        auto group = [&](int k0, const bool full) {     // full: all four steps inside the window
           float x[4], tl[4];
           const double kq = (double)k0;
           const float kf = (float)k0;
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const double ku = fma((double)u, kstep, kq);     // k = k0 + u * kpar
-            if (fast || noclamp) {
-              x[u] = (float)fma(ck, ku, c0);
-            } else {
-              double sd = dadd(s_seed, dmul(rdt, ku));
-              sd = sd < -p.max_steer ? -p.max_steer : sd;
-              sd = sd > p.max_steer ? p.max_steer : sd;
-              x[u] = (float)(sd * kd);
-            }
-          }
-          if (fast || poly) {
+          for (int u = 0; u < 4; ++u) x[u] = (float)fma(ck, fma((double)u, kstep, kq), c0);   // k = k0 + u * kpar
 #pragma unroll
-            for (int u = 0; u < 4; ++u) tl[u] = tan_poly(x[u]) * invL;
-          } else {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) tl[u] = tan_steer(x[u]) * invL;
-          }
+          for (int u = 0; u < 4; ++u) tl[u] = tan_poly(x[u]) * invL;
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int k = k0 + u * kpar;
@@ -1173,13 +1164,29 @@ vmvo_window_search_kernel(const SearchParams p) {
             }
           }
         };
-        const bool fastpath = noclamp && poly;     // window-uniform
-        for (int k0 = 1 + ks; k0 <= N; k0 += 4 * kpar) {
-          if (fastpath) {
-            if (k0 + 3 * kpar <= N) group(k0, true, true);
-            else group(k0, true, false);
-          } else {
-            group(k0, false, false);
+        if (noclamp && poly) {     // window-uniform
+          for (int k0 = 1 + ks; k0 <= N; k0 += 4 * kpar) {     // (the lambda is specialised per call)
+            if (k0 + 3 * kpar <= N) group(k0, true);
+            else group(k0, false);
+          }
+        } else {
+#pragma unroll 1
+          for (int k = 1 + ks; k <= N; k += kpar) {
+            float x;
+            if (noclamp) {
+              x = (float)fma(ck, (double)k, c0);
+            } else {
+              double sd = dadd(s_seed, dmul(rdt, (double)k));
+              sd = sd < -p.max_steer ? -p.max_steer : sd;
+              sd = sd > p.max_steer ? p.max_steer : sd;
+              x = (float)(sd * kd);
+            }
+            const float tl = (poly ? tan_poly(x) : tan_steer(x)) * invL;
+            TL[(k - 1) * p.gs + j] = tl;
+            const float a = fabsf(tl);
+            mx = fmaxf(mx, a);
+            s0 += a;
+            s1 = fmaf((float)k, a, s1);
           }
         }
         float* tp = TSP + 3 * gs4 * ks;
@@ -1229,10 +1236,7 @@ vmvo_window_search_kernel(const SearchParams p) {
     const WinInfo& wi = hd->wi;
 
     if (status & VMVO_WIN_EMPTY) {
-      if (warp == 0) {
-        if (lane == 0) write_unsearched(status, N, v_seed, s_seed);
-        flush_record(w);
-      }
+      if (tid == 0) write_unsearched(status, N, v_seed, s_seed);
       team.sync();
       continue;
     }
