@@ -1356,9 +1356,38 @@ vmvo_window_search_kernel(const SearchParams p) {
       // WIDEST band around U skips its band and candidate work (it still meets the barriers).
       constexpr bool use_skip = SKIP;
       Band loose{0.f, 0.f, 0.f};
+      // ... starting from the pass that holds the acceleration the window itself suggests: the chord to
+      // the target of the last step against V_w * t (any order gives the same records; this one has U
+      // tight after the first pass also when the vehicle speeds up or brakes, which is what the
+      // pruning votes of all later passes work with)
+      int p_lo = 0, p_hi = 0;
+      bool p_up = true;
+      if (use_skip) {
+        int p_est = (n_pass - 1) >> 1;
+        const int tl_ = N - off;
+        if (tl_ >= 0 && tl_ < n_targets && p.gv > 1) {
+          const double tx = tgt[tl_], ty = tgt[P + tl_], tt = (double)N * dt;
+          const double chord = copysign(sqrt(tx * tx + ty * ty), tx);
+          const double a_est = 2.0 * (chord - v_seed * tt) / (tt * tt);
+          if (fabs(a_est) <= 1e6) {       // (NaN / Inf: keep the middle)
+            double fi = (a_est + p.max_accel) * (0.5 / p.max_accel) * (double)(p.gv - 1);
+            fi = fi < 0.0 ? 0.0 : fi;
+            fi = fi > (double)(p.gv - 1) ? (double)(p.gv - 1) : fi;
+            const long long item = (long long)((int)fi / kC) * p.gs + (p.gs >> 1);
+            p_est = (int)(item / T);
+            p_est = p_est < n_pass ? p_est : n_pass - 1;
+          }
+        }
+        p_lo = p_est - 1;
+        p_hi = p_est;
+      }
       for (int pidx = 0; pidx < n_pass; ++pidx) {
-        const int mid = (n_pass - 1) >> 1;
-        const int pass = !use_skip ? pidx : (pidx & 1) ? mid + ((pidx + 1) >> 1) : mid - (pidx >> 1);
+        int pass = pidx;
+        if (use_skip) {      // p_est, then alternately above and below it while either side lasts
+          const bool take_hi = (p_up && p_hi < n_pass) || p_lo < 0;
+          pass = take_hi ? p_hi++ : p_lo--;
+          p_up = !p_up;
+        }
         // VD[k][m] = V_k(ic0*C + m) * dt for the accelerations this pass touches
         // (a table that covers every acceleration is filled once per window: vd_full)
         const int ic0 = vd_full ? 0 : dv(pass * T, p.gs, p.gs_sh);
