@@ -54,10 +54,10 @@ def build():
     before("        if (pidx == 0 && use_skip) {   // hd->bw and hd->ts are visible now", "        CLK(5);\n")
     before("        float mj = CUDART_INF_F;       // the item's smallest cost", "        CLK(6);\n")
     after("        U = fminf(U, bm);\n", "        CLK(7);\n")
-    after("          if (!overflow) break;\n          process_list();\n        }\n", "        CLK(8);\n")
-    after("      if (!deferred) process_list();\n", "      CLK(9);\n")
+    before("          const int overflow = team.any(pend != 0);\n", "          CLK(8);\n")
+    after("          if (overflow || (last && !deferred)) process_list();\n", "          CLK(9);\n")
     before("    team.sync();\n  }\n}\n\n// ---- window preparation as a pass", "    CLK(10);\n")
-    s = s.replace("namespace vmvo {\n", "namespace vmvo {\n__device__ unsigned long long g_clk[2][12];\n"
+    s = s.replace("namespace vmvo {\n", "namespace vmvo {\nstatic __device__ unsigned long long g_clk[2][12];\n"
                   "#define CLK(i) do { if (lane == 0 && warp < 2) { long long t_ = clock64(); "
                   "s_clk[team.id][warp][i] += t_ - s_prev[team.id][warp]; s_prev[team.id][warp] = t_; } } while (0)\n", 1)
     before("  const bool fetcher = tid == T - 32;\n",
@@ -67,6 +67,10 @@ def build():
     after("    CLK(10);\n    team.sync();\n  }\n",
           "  if (lane == 0 && warp < 2) for (int i = 0; i < 12; ++i) "
           "atomicAdd(&g_clk[warp][i], (unsigned long long)s_clk[team.id][warp][i]);\n")
+    open(p, "w").write(s)
+    # the counters are per translation unit: read those of the MODE 2 kernels (config 2 runs them)
+    p = os.path.join(SRC, "vmvo_search_prep.cu")
+    s = open(p).read()
     s += ('\nextern "C" int vmvo_exp_clk(unsigned long long* out) {\n  unsigned long long z[24] = {0};\n'
           "  cudaDeviceSynchronize();\n  cudaMemcpyFromSymbol(out, vmvo::g_clk, sizeof(z));\n"
           "  cudaMemcpyToSymbol(vmvo::g_clk, z, sizeof(z));\n  return 0;\n}\n")
