@@ -451,8 +451,14 @@ def roofline(ctx, dev, res, clocks, extras=True):
     out["sfu_frac_algorithmic"] = hsteps * MUFU_PER_HSTEP / sec / mufu
     out["sfu_frac_executed"] = hsteps * out["executed_mufu_per_hypothesis_step"] / sec / mufu
     if counts:
+        if counts.get("mufu_per_hypothesis_step"):      # as counted under ncu (pruning included)
+            out["executed_mufu_per_hypothesis_step"] = counts["mufu_per_hypothesis_step"]
+            out["sfu_frac_executed"] = hsteps * counts["mufu_per_hypothesis_step"] / sec / mufu
         lane_ops = counts["fp32_lane_ops_per_hypothesis_step"] * hsteps
         out["executed_fp32_lane_ops_per_hypothesis_step"] = counts["fp32_lane_ops_per_hypothesis_step"]
+        # (per hypothesis-step of the GRID: the pruning votes stop scans early, so the kernel executes
+        # this share of them -- and the algorithmic fractions below may exceed what a pipe can do)
+        out["executed_share_of_hypothesis_steps"] = counts.get("executed_share_of_hypothesis_steps")
         out["achieved"] = lane_ops / sec / 1e9
         out["frac"] = lane_ops / sec / ffma
         # the hardware's own view of the same launch (captured under ncu, profiles/): share of cycles the

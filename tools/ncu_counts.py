@@ -62,6 +62,9 @@ entry = {
     "fp32_lane_ops_per_hypothesis_step": sum(ops[o] * n for o, n in LANE_OPS.items()) * 32 / hsteps,
     "fma_pipe_clk_per_hypothesis_step": sum(ops[o] * c for o, c in FMA_PIPE_CLK.items()) * 32 / hsteps,
     "mufu_per_hypothesis_step": ops["MUFU"] * 32 / hsteps,
+    # share of the grid's hypothesis-steps the scans executed (the rest: pruned).  The packed scan runs
+    # 20 FFMA2 per 8 hypothesis-steps of a thread and FFMA2 occurs nowhere else in the kernel
+    "executed_share_of_hypothesis_steps": ops["FFMA2"] / 20 * 8 * 32 / hsteps,
     "hw_pipe_fma_cycles_active_pct": get("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
     "hw_pipe_xu_inst_pct": get("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"),
     "hw_issue_active_pct": get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
