@@ -392,8 +392,10 @@ int vmvo_tan_steer_f32(vmvo_ctx* ctx, int64_t n, const float* d_delta, float* d_
 int vmvo_peak_probe(vmvo_ctx* ctx, int32_t kind, int32_t blocks, int32_t threads,
                     int32_t iters, float* d_sink, void* stream);
 /* Test / tuning hook, NOT part of the product surface: overrides one of the launch heuristics of
- * this ctx ("team_warps", "fast_scan", "cand_cap", "defer_min", "max_ctas_per_sm", "defer_warps", "cta_teams", "pdl", "prep"); value < 0
- * restores the library's own choice.  The environment is never consulted.                      */
+ * this ctx ("team_warps", "fast_scan", "cand_cap", "defer_min", "max_ctas_per_sm", "defer_warps", "cta_teams", "pdl", "prep",
+ * "prune" (0: every scan runs to its last step), "prune_every" (steps between two pruning votes), "lean" (0: the
+ * generic kernel mode)); value < 0 restores the library's own choice.  None of them changes a result.  The
+ * environment is never consulted.                                                               */
 int vmvo_debug_set_tuning(vmvo_ctx* ctx, const char* key, int32_t value);
 /* kernels launched by this ctx since creation (for bench.py's gpu_launches)             */
 int64_t vmvo_launch_count(const vmvo_ctx* ctx);
