@@ -259,3 +259,39 @@ def test_sklansky_scan_properties_the_packed_rescore_relies_on():
         out = hillis_steele(z)
         differs += int(not np.all(out[2:] == out[2]))
     assert differs > 0
+
+
+def test_pass_and_chunk_orders_are_permutations():
+    """The orders the search kernel walks its passes in (vmvo_search_kernels.cuh: many-pass kernels start
+    at an estimated pass and alternate outward while either side lasts; two-pass kernels deal the
+    acceleration chunks middle-out) restated: every pass / chunk exactly once, nearest first.  Any order
+    gives the same records (the pruning votes are exact); this pins that none is skipped."""
+    def pass_order(n_pass, p_est):
+        p_lo, p_hi, up, out = p_est - 1, p_est, True, []
+        for _ in range(n_pass):
+            take_hi = (up and p_hi < n_pass) or p_lo < 0
+            if take_hi:
+                out.append(p_hi)
+                p_hi += 1
+            else:
+                out.append(p_lo)
+                p_lo -= 1
+            up = not up
+        return out
+
+    for n_pass in (1, 2, 3, 7, 16, 32, 33):
+        for p_est in range(n_pass):
+            order = pass_order(n_pass, p_est)
+            assert sorted(order) == list(range(n_pass)), (n_pass, p_est, order)
+            assert order[0] == p_est
+            dist = [abs(q - p_est) for q in order]
+            # never further out than one step beyond what the other side has reached
+            assert all(dist[i + 1] >= dist[i] - 1 for i in range(n_pass - 1))
+
+    def chunk_of(ic, n_ic):
+        mid = (n_ic - 1) >> 1
+        return mid + ((ic + 1) >> 1) if ic & 1 else mid - (ic >> 1)
+
+    for n_ic in (1, 2, 3, 4, 5, 8):
+        assert sorted(chunk_of(c, n_ic) for c in range(n_ic)) == list(range(n_ic))
+    assert [chunk_of(c, 4) for c in range(4)] == [1, 2, 0, 3]      # 32 accelerations: the middle 16 first
