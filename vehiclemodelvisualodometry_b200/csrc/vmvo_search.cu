@@ -318,8 +318,9 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
     if (slots > budget) slots = budget;
     need = (size_t)slots * slot_bytes;
   }
-  // the scratch buffer of a launch: [window preparation records][ready words, one per slot][slots]
-  const size_t ready_bytes = ((size_t)slots * 4 + 127) & ~(size_t)127;
+  // the scratch buffer of a launch: [window preparation records][counters, 128 bytes][ready words, one
+  // per slot][slots] -- counters and ready words side by side, so that ONE memset node clears both
+  const size_t ready_bytes = (((size_t)slots * 4 + 127) & ~(size_t)127) + 128;
   if (need > 0) need += ready_bytes;
   size_t prep_total = 0;
   if (want_prep && tw <= 2) {
@@ -332,9 +333,8 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
     return fail(ctx, VMVO_ERR_UNSUPPORTED, "%d searches of this ctx are in flight or captured in graphs: "
                 "no launch slot left", kLaunchSlots);
   // queue head, slot allocation count, finished teams
-  VMVO_CUDA(ctx, cudaMemsetAsync(ls->d_counters, 0, 4 * sizeof(unsigned long long), st));
-  p.work_counter = ls->d_counters;
-  p.windows_done = ls->d_counters + 2;
+  unsigned long long* counters = ls->d_counters;
+  bool counters_cleared = false;
   p.defer_ready = nullptr;
   p.n_todo = 0;
   p.prep = nullptr;
@@ -346,14 +346,19 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
       base += prep_total;
     }
     if (need > 0 && slots > 0) {
-      p.defer_ready = reinterpret_cast<unsigned*>(base);
+      counters = reinterpret_cast<unsigned long long*>(base);
+      p.defer_ready = reinterpret_cast<unsigned*>(base + 128);
       p.defer_buf = base + ready_bytes;
       p.defer_slots = (int)(slots > 0x7fffffff ? 0x7fffffff : slots);
       p.defer_slot_bytes = (int)slot_bytes;
-      p.defer_count = reinterpret_cast<unsigned*>(ls->d_counters + 1);
-      VMVO_CUDA(ctx, cudaMemsetAsync(p.defer_ready, 0, (size_t)p.defer_slots * 4, st));
+      p.defer_count = reinterpret_cast<unsigned*>(counters + 1);
+      VMVO_CUDA(ctx, cudaMemsetAsync(base, 0, 128 + (size_t)p.defer_slots * 4, st));
+      counters_cleared = true;
     }
   }
+  if (!counters_cleared) VMVO_CUDA(ctx, cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned long long), st));
+  p.work_counter = counters;
+  p.windows_done = counters + 2;
 
   const bool dual = use_vo && use_gps;
   // the kernel MODE (vmvo_search_kernels.cuh): lean when nothing outside the default path is asked for
