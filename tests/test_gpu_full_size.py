@@ -86,3 +86,22 @@ def test_config5_fused_vo_gps_imu(cuda_device):
     cfg = SearchConfig(grid_v=128, grid_s=128, window_frames=60, w_vo=1.0, w_gps=0.05, w_imu=30.0)
     batch = synthetic_drives(4, 200, seed=55)
     _check(cfg, batch, 4, sample=96, with_gps=True, with_imu=True)
+
+
+@pytest.mark.parametrize("shape", ["config2", "config3"])
+def test_full_size_pruned_search_equals_exhaustive_search(cuda_device, tuning, shape):
+    """A size-independent property at BASELINE's full sizes: the pruning votes and the specialised kernels
+    change no byte of any record (all 9 940 windows of configs[1]; 4 096 windows of configs[2])."""
+    if shape == "config2":
+        cfg, frames = SearchConfig(grid_v=32, grid_s=32, window_frames=30), 10000
+    else:
+        cfg, frames = SearchConfig(grid_v=256, grid_s=256, window_frames=60), 4216
+    batch = synthetic_drives(1, frames, seed=77)
+    drives = DriveSet.from_arrays([batch.time[0]], [batch.dt], vo=[batch.vo[0]])
+    plan = plan_windows(cfg, drives)
+    fast = grid_search(cfg, drives, plan).results.clone()
+    tuning("prune", 0)
+    tuning("lean", 0)
+    full = grid_search(cfg, drives, plan).results.clone()
+    # (bytes 12..15: n_rescored, a run-to-run diagnostic -- see above)
+    assert torch.equal(fast[:, :12], full[:, :12]) and torch.equal(fast[:, 16:], full[:, 16:])

@@ -33,11 +33,17 @@ class Variant(DrivePipeline):
     mirrors = True
     arrival = True
     search_only = False
+    local_dummy = False      # the "peer" buffers are local memory: the stores' code path without NVLink
 
     def _ex(self, on):
         ex = _lib.Exchange.from_buffer_copy(self.gather.exchange)
         if not on:
             ex.n_peers = 0
+        elif self.local_dummy:
+            if not hasattr(self, "_dummy"):
+                self._dummy = [torch.empty((n_win, 64), dtype=torch.uint8, device=dev) for _ in range(ex.n_peers)]
+            for i in range(ex.n_peers):
+                ex.peer_records[i] = self._dummy[i].data_ptr()
         return ex
 
     def _search(self):
@@ -53,8 +59,9 @@ class Variant(DrivePipeline):
                    frame_range=self.frame_range, exchange=self._ex_w)
 
 
-def run(name, mirrors, arrival, align=False, steps=40, search_only=False):
-    cls = type("V", (Variant,), {"mirrors": mirrors, "arrival": arrival, "search_only": search_only})
+def run(name, mirrors, arrival, align=False, steps=40, search_only=False, local_dummy=False):
+    cls = type("V", (Variant,), {"mirrors": mirrors, "arrival": arrival, "search_only": search_only,
+                                 "local_dummy": local_dummy})
     sets = [PeerGather(n_win, dev, block=block) for _ in range(2)]
     pipes = [cls(cfg, drives, blend_gps=False, gather=g, frame_range=fr) for g in sets]
     st = {"n": 0}
@@ -94,6 +101,8 @@ def run(name, mirrors, arrival, align=False, steps=40, search_only=False):
 if rank == 0:
     print(f"world {world}, {n_win} windows pooled, block {block}", flush=True)
 run("search of this rank's deal only (no peer stores, no write-back)", False, False, search_only=True)
+run("search of this rank's deal + the same stores into LOCAL memory", True, False, search_only=True,
+    local_dummy=True)
 run("search of this rank's deal + peer stores (no write-back)", True, False, search_only=True)
 run("deal + peer stores + arrival words (the shipped step)", True, True)
 run("the shipped step, ranks aligned before each timed step", True, True, align=True)
