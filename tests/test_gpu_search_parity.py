@@ -287,3 +287,17 @@ def test_lean_kernels_give_the_generic_kernels_records(cuda_device, tuning, name
             np.testing.assert_array_equal(got[label][f], got["default"][f])
         for f in ("best_cost", "x1", "y1", "theta1", "v_seed", "s_seed"):
             np.testing.assert_array_equal(got[label][f].view(np.uint64), got["default"][f].view(np.uint64))
+
+
+def test_random_configurations_default_equals_generic_exhaustive(cuda_device):
+    """tools/random_equivalence.py: 40 random grids / windows / cost terms / target modes / stream widths,
+    the default search (pruning votes, lean and preparation kernels) against the generic exhaustive one,
+    and against its own repeat: bit-identical records."""
+    import subprocess
+    import sys as _sys
+    import os as _os
+
+    root = _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))
+    r = subprocess.run([_sys.executable, _os.path.join(root, "tools", "random_equivalence.py"), "40", "11"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
