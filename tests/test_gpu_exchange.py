@@ -64,6 +64,28 @@ if mode != "chained":
     assert g.step() == 1 and g.timed_out() == 0
 g.close()
 
+# 1b. windows that are not searched (more poses than max_window_poses: status TOO_LONG) and windows with
+#     a non-finite pose leave their records on both ranks as well
+if mode != "chained":
+    import dataclasses
+    vo_nan = [v.copy() for v in batch.vo]
+    vo_nan[1][40:43, 0] = np.nan
+    drives_nan = DriveSet.from_arrays(list(batch.time), [batch.dt] * 3, vo=vo_nan, gps=list(batch.gps), device=dev)
+    cfg_long = SearchConfig(grid_v=8, grid_s=8, window_mode="time", horizon_time=1.0, horizon_frames=20,
+                            max_window_poses=16)
+    for cfg_u, dr_u in ((cfg_long, drives), (cfg, drives_nan)):
+        plan_u = plan_windows(cfg_u, dr_u)
+        alone_u = grid_search(cfg_u, dr_u, plan_u)
+        st = alone_u.records()["status"]
+        assert (st != 0).any()
+        g = PeerGather(plan_u.n_windows, dev, block=4)
+        grid_search(cfg_u, dr_u, plan_u, out=g.buffer, exchange=g.exchange)
+        g.publish()
+        g.wait()
+        torch.cuda.synchronize()
+        same_records(g.buffer, alone_u.results, "unsearched / non-finite windows")
+        g.close()
+
 # 2. the pipeline: two buffer sets used alternately, CUDA graphs, no host synchronisation between
 #    steps; the write-back of this rank's frames consumes both ranks' records
 sets = [PeerGather(n, dev, block={block}) for _ in range(2)]
