@@ -314,6 +314,36 @@ def measure_workload(workload, dev, world, rank, timer, steps, warmup, seed0=BAS
                                      "same records bit for bit; `value` above is the default, pruned search"}
         del full_pipe, full_only
     if world > 1:
+        # what part of the gap to N x (one GPU) is the workload and what part the exchange: the search
+        # launches of (i) the N = 1 workload (drive base + 0 alone) and (ii) this rank's deal of the pool
+        # with no record stores and no arrival words, both graph-replayed like `kern_ms`
+        from vehiclemodelvisualodometry_b200 import DriveSet, plan_windows
+
+        d0 = DriveSet.from_arrays([time_h[:n_frames]], [float(drives.dt[0].item())], vo=[vo_h[:n_frames]], device=dev)
+        p0 = plan_windows(cfg, d0, extents=False)
+        o0 = torch.empty((p0.n_windows, 64), dtype=torch.uint8, device=dev)
+        ex0 = _lib.Exchange.from_buffer_copy(sets[0].exchange)
+        ex0.n_peers = 0                                     # the deal only
+        ex0.epoch = None                                    # (and the exchange's step counter stays put)
+        share = torch.empty((n_win, 64), dtype=torch.uint8, device=dev)
+        graphs = []
+        for fn in (lambda: grid_search(cfg, d0, p0, out=o0),
+                   lambda: grid_search(cfg, drives, last.plan, out=share, exchange=ex0)):
+            fn()
+            torch.cuda.synchronize(dev)
+            gph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gph):
+                fn()
+            graphs.append(gph)
+        n1_ms = timer(graphs[0].replay, kk, 2) / kk
+        share_ms = timer(graphs[1].replay, kk, 2) / kk
+        out["scaling_breakdown"] = {
+            "n1_workload_search_ms": n1_ms, "rank_share_of_pool_search_ms": share_ms,
+            "step_ms": ms_per_step,
+            "note": "max over ranks; search launches only.  The pool holds drives base + 0 .. N - 1 and the "
+                    "N = 1 workload is drive base + 0 alone: (share - n1) is the workload's part of the gap "
+                    "to N x (one GPU), (step - share) the exchange, the write-back and the slowest rank"}
+        del graphs
         torch.cuda.synchronize(dev)
         if not records_equal(alone, last.records):
             raise SystemExit(f"rank {rank}: the gathered records differ from a one-GPU search of the pool")
@@ -747,6 +777,7 @@ def run_b200(args):
         "e2e": res["e2e"], "e2e_serial": res["e2e_serial"],
         "clocks": clocks,
         "rescored_per_window": res["rescored_per_window"],
+        **({"scaling_breakdown": res["scaling_breakdown"]} if "scaling_breakdown" in res else {}),
         "search": "exact branch and bound: a scanning warp stops once every hypothesis it holds has passed "
                   "the candidate threshold of the bound its team held when the pass began; `value` counts "
                   "the grid's hypothesis-steps (G_v x G_s x N per window, SURVEY 8d), records are those of "
