@@ -537,8 +537,10 @@ def batch_config(name, cfg, n_drives, n_frames, dev, world, rank, timer, sensors
     gather = PeerGather(n_win, dev, block=DEAL_BLOCK) if world > 1 else None
     pipe = DrivePipeline(cfg, drives, blend_gps="gps" in sensors, gather=gather, use_graph=False,
                          frame_range=shard_range(drives.n_frames, world, rank) if world > 1 else None)
-    k = 2
-    ms = timer(pipe.run, k, 1) / k
+    # (the median of three separately timed passes after one warm-up: a single slow pass -- seen once at
+    # N = 8, 52 ms instead of 14 -- would otherwise double a two-pass mean)
+    timer(pipe.run, 1, 1)
+    ms = float(np.median([timer(pipe.run, 1, 0) for _ in range(3)]))
     torch.cuda.synchronize(dev)
     rec = pipe.result_records()
     hsteps = int(cfg.grid_v) * int(cfg.grid_s) * int(rec["n_steps"].astype(np.int64).sum())
@@ -546,7 +548,8 @@ def batch_config(name, cfg, n_drives, n_frames, dev, world, rank, timer, sensors
            "grid": [cfg.grid_v, cfg.grid_s], "window_steps": cfg.window_frames, "sensors": sensors,
            "windows": n_win, "hypothesis_steps": hsteps, "ms_per_step": ms,
            "value": hsteps / (ms * 1e-3), "unit": UNIT, "windows_per_s": n_win / (ms * 1e-3),
-           "rescored_per_window": float(rec["n_rescored"].mean()), "note": note}
+           "rescored_per_window": float(rec["n_rescored"].mean()), "note": note,
+           "timing": "median of three timed passes (max over ranks each)"}
     if world > 1:
         # the same batch on ONE GPU (rank 0 alone; the others wait), and the gathered records checked
         alone = torch.empty((n_win, 64), dtype=torch.uint8, device=dev)
