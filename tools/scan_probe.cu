@@ -103,6 +103,20 @@ __device__ __forceinline__ void trig8(float A, float B, const Aff& f, float* cs,
     rot(cs[4], sn[4], cr2, sr2, cs[6], sn[6]);
     rot(cs[2], sn[2], cr2, -sr2, cs[0], sn[0]);
     rot(cs[5], sn[5], cr2, sr2, cs[7], sn[7]);
+  } else if (TRIG == 5) {
+    // MUFU at {1, 2, 5, 6}; the outer four by the three-term recurrence c(i-1) = 2 cos(da B) c(i) - c(i+1)
+    // (one FFMA per value instead of a rotation's two; error 5 eps_MUFU instead of 2): 9 MUFU
+    const float a1 = f.a0 + f.da, a2 = fmaf(2.f, f.da, f.a0), a5 = fmaf(5.f, f.da, f.a0), a6 = fmaf(6.f, f.da, f.a0);
+    __sincosf(fmaf(a1, B, A), &sn[1], &cs[1]);
+    __sincosf(fmaf(a2, B, A), &sn[2], &cs[2]);
+    __sincosf(fmaf(a5, B, A), &sn[5], &cs[5]);
+    __sincosf(fmaf(a6, B, A), &sn[6], &cs[6]);
+    float K = __cosf(f.da * B);
+    K += K;
+    cs[0] = fmaf(K, cs[1], -cs[2]); sn[0] = fmaf(K, sn[1], -sn[2]);
+    cs[3] = fmaf(K, cs[2], -cs[1]); sn[3] = fmaf(K, sn[2], -sn[1]);
+    cs[4] = fmaf(K, cs[5], -cs[6]); sn[4] = fmaf(K, sn[5], -sn[6]);
+    cs[7] = fmaf(K, cs[6], -cs[5]); sn[7] = fmaf(K, sn[6], -sn[5]);
   } else {
     const float a1 = f.a0 + f.da, a5 = fmaf(5.f, f.da, f.a0);
     float sr, cr, sr2, cr2;
@@ -121,7 +135,8 @@ __device__ __forceinline__ void trig8(float A, float B, const Aff& f, float* cs,
 }
 
 // PACK 0: scalar position / cost; 1: packed FFMA2 / FADD2 (pairs (0,1) (2,3) ...); 2: pairs 0,1 packed, 2,3 scalar
-template <int TRIG, int PACK, int JSPLIT>
+// VDREG 1: the step lengths max(0, vwdt + a_c k dt^2) worked out in registers instead of read from VD[k][8]
+template <int TRIG, int PACK, int JSPLIT, int VDREG = 0>
 __device__ __forceinline__ void loop_affine(const float* tl, const float* vd, const float2* Df, const Aff& f,
                                             Out& o) {
   float A = 0.f, B = 0.f, tv = 0.f, tlmax = 0.f, vmax = 0.f, kdt2 = 0.f;
@@ -131,11 +146,17 @@ __device__ __forceinline__ void loop_affine(const float* tl, const float* vd, co
 #pragma unroll 1
   for (int k = 1; k <= kN; ++k) {
     const float tlk = tl[(k - 1) * kGS];
-    const float4 va = *reinterpret_cast<const float4*>(vd + (k - 1) * 8);
-    const float4 vb = *reinterpret_cast<const float4*>(vd + (k - 1) * 8 + 4);
-    const float v[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
-    const float2 d = Df[k];
+    float v[8];
     kdt2 += f.dt2;
+    if (VDREG) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) v[c] = fmaxf(fmaf(fmaf((float)c, f.da, f.a0), kdt2, f.vwdt), 0.f);
+    } else {
+      const float4 va = *reinterpret_cast<const float4*>(vd + (k - 1) * 8);
+      const float4 vb = *reinterpret_cast<const float4*>(vd + (k - 1) * 8 + 4);
+      v[0] = va.x; v[1] = va.y; v[2] = va.z; v[3] = va.w; v[4] = vb.x; v[5] = vb.y; v[6] = vb.z; v[7] = vb.w;
+    }
+    const float2 d = Df[k];
     A = fmaf(f.vwdt, tlk, A);
     B = fmaf(kdt2, tlk, B);
     tv = fmaf(fmaf(f.amax, kdt2, f.vwdt), fabsf(tlk), tv);
@@ -209,6 +230,8 @@ __global__ void __launch_bounds__(kGS, MINB) probe(int windows, float* sink) {
     if (VAR == 11) loop_affine<1, 2, 0>(TL + j, VD, Df, f, o);  // 10 MUFU, half packed
     if (VAR == 12) loop_affine<0, 0, 0>(TL + j, VD, Df, f, o);  // affine headings, 16 MUFU, scalar
     if (VAR == 13) loop_affine<0, 1, 0>(TL + j, VD, Df, f, o);  // affine headings, 16 MUFU, packed
+    if (VAR == 14) loop_affine<1, 1, 1, 1>(TL + j, VD, Df, f, o);  // the shipped scan without the VD table
+    if (VAR == 15) loop_affine<5, 1, 1>(TL + j, VD, Df, f, o);     // 9 MUFU, three-term recurrence, packed, split J
 #pragma unroll
     for (int c = 0; c < 8; ++c) acc += o.J[c];
     acc += o.stat;
@@ -266,6 +289,8 @@ int main() {
   RUN3(12, "affine 16 MUFU scalar");
   RUN3(13, "affine 16 MUFU packed");
   RUN3(1, "shipped fast: 10 MUFU, packed, split J");
+  RUN3(14, "shipped, step lengths in registers (no VD)");
+  RUN3(15, "9 MUFU three-term recurrence, packed");
   RUN3(2, "10 MUFU scalar");
   RUN3(11, "10 MUFU half packed");
   RUN3(7, "8 MUFU depth1 scalar");
