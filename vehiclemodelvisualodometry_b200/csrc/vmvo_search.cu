@@ -298,7 +298,25 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
   cudaStreamIsCapturing(st, &capture);
   const bool capturing = capture != cudaStreamCaptureStatusNone;
 
-  // deferred windows: a slot per window up to a 64 MiB budget.  Not with chained seeds (the next
+  // Scratch budgets.  Small launches stay within 64 MiB of slots and 256 MiB of preparation records; a
+  // large batch (BASELINE configs[3]: 3.0e6 windows) may take up to 1 GiB / 8 GiB where a quarter of
+  // the device's free memory covers it -- measured on the 512-drive batch: 112.0 -> 91.7 ms with the
+  // preparation records, 88.8 ms with the slots as well (one run in five or six reads 103-117 ms with
+  // either: something about where the 6 GB land).  (cudaMemGetInfo only for such launches.)
+  size_t mem_quarter = 0;
+  auto free_quarter = [&]() {
+    if (!mem_quarter) {
+      RelaxedCapture relaxed(capturing);
+      size_t free_b = 0, total_b = 0;
+      if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) {
+        cudaGetLastError();
+        free_b = 0;
+      }
+      mem_quarter = free_b / 4 + 1;
+    }
+    return mem_quarter;
+  };
+  // deferred windows: a slot per window up to the budget.  Not with chained seeds (the next
   // window needs this one's optimum at once), rollout outputs or the debug export.
   p.defer_buf = nullptr;
   p.defer_count = nullptr;
@@ -314,7 +332,12 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
     const int n_arr = 2 + ((use_vo && use_gps) ? 2 : 0) + (use_imu ? 1 : 0);
     slot_bytes = ((size_t)kDeferHdrBytes + (size_t)n_arr * p.maxp * 8 + (size_t)p.cand_cap * 8 + 127) & ~(size_t)127;
     slots = p.run_offsets ? 0 : (p.n_local < n_windows ? p.n_local : n_windows);
-    const long long budget = (64LL << 20) / (long long)slot_bytes;
+    long long budget = (64LL << 20) / (long long)slot_bytes;
+    if (slots > budget) {
+      size_t big = (size_t)slots * slot_bytes;
+      if (big > ((size_t)1 << 30)) big = (size_t)1 << 30;
+      if (big <= free_quarter()) budget = (long long)(big / slot_bytes);
+    }
     if (slots > budget) slots = budget;
     need = (size_t)slots * slot_bytes;
   }
@@ -325,7 +348,8 @@ static int grid_search_impl(vmvo_ctx* ctx, const vmvo_search_cfg* cfg, int64_t n
   size_t prep_total = 0;
   if (want_prep && tw <= 2) {
     prep_total = (size_t)p.n_local * (size_t)prep_rec_bytes;
-    if (prep_total > (256ull << 20)) prep_total = 0;       // (a batch this large keeps the fused phases)
+    if (prep_total > (256ull << 20) && (prep_total > (8ull << 30) || prep_total + need > free_quarter()))
+      prep_total = 0;                                      // (a batch this large keeps the fused phases)
   }
   const size_t need_all = need + prep_total;
   vmvo_launch_slot* ls = acquire_launch_slot(ctx, need_all, capturing);
